@@ -1,0 +1,260 @@
+/* vsf.h — C ABI of libvsf_cuda.so: the B200 (sm_100a) replacement for the
+ * descriptor-matching / stereo / triangulation hot path of
+ * ut-amrl/vision_slam_frontend.
+ *
+ * The reference has no plugin or operator registry.  The seam is the set of
+ * private Frontend helpers and the two OpenCV calls they make; each entry point
+ * below names the reference interface it replaces (paths relative to the
+ * reference checkout).  All signatures are plain C: pointers, sizes, scalars.
+ * Host-pointer entry points never keep a caller pointer past return.  One
+ * vsf_ctx = one CUDA device + one stream; calls on a ctx must be serialised by
+ * the caller, different ctxs may be used concurrently (one per GPU / rank).
+ * There is no CPU fallback: every entry point fails with VSF_ERR_CUDA when the
+ * device or the kernels are unavailable.
+ *
+ * Return value: 0 (VSF_OK) or a VSF_ERR_* code; vsf_last_error(ctx) gives a
+ * human-readable message for the last failure on that ctx.  The library never
+ * aborts (the reference's CHECK/exit behaviour is re-created, by choice, in the
+ * C++ Frontend mirror above this ABI).
+ */
+#ifndef VSF_H_
+#define VSF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSF_VERSION_STRING "0.1.0"
+
+enum {
+  VSF_OK = 0,
+  VSF_ERR_BAD_ARG = 1,   /* null pointer, negative size, unsupported width */
+  VSF_ERR_CAPACITY = 2,  /* more rows / frames than the ctx was created for */
+  VSF_ERR_CUDA = 3,      /* CUDA runtime error (message has the detail)     */
+  VSF_ERR_STATE = 4      /* call not valid in the current ctx state         */
+};
+
+/* Layout-identical to cv::DMatch (16 bytes): what Frontend::GetMatches returns
+ * (src/slam_frontend.cc:521-538).  distance holds an exact small integer. */
+typedef struct vsf_dmatch {
+  int32_t queryIdx;
+  int32_t trainIdx;
+  int32_t imgIdx;
+  float distance;
+} vsf_dmatch;
+
+/* Layout-identical to cv::KeyPoint (28 bytes): Frame::keypoints_
+ * (src/slam_frontend.h:107).  Only x,y are read on the device. */
+typedef struct vsf_keypoint {
+  float x, y;
+  float size, angle, response;
+  int32_t octave, class_id;
+} vsf_keypoint;
+
+/* Layout-identical to slam_types::FeatureMatch (src/slam_types.h:77-89). */
+typedef struct vsf_feature_match {
+  uint64_t feature_idx_initial;
+  uint64_t feature_idx_current;
+} vsf_feature_match;
+
+typedef struct vsf_ctx vsf_ctx;
+
+/* ------------------------------------------------------------------ context */
+
+/* device: CUDA ordinal.  max_features: largest number of descriptor rows in
+ * one frame.  desc_bytes: descriptor width as stored by the caller (1..64;
+ * 32 = ORB, 61 = AKAZE, 64 = BRISK/FREAK); rows are zero-padded to 32 or 64
+ * bytes on the device, which leaves Hamming distances unchanged.  window:
+ * FrontendConfig::frame_life_ (src/slam_frontend.cc:556), the number of past
+ * frames kept resident for vsf_window_* / vsf_observe_features. */
+int vsf_create(int device, int max_features, int desc_bytes, int window,
+               vsf_ctx** out);
+void vsf_destroy(vsf_ctx* ctx);
+const char* vsf_last_error(const vsf_ctx* ctx);
+const char* vsf_version(void);
+
+/* Run the ctx's work on an existing CUDA stream (cudaStream_t passed as
+ * void*; NULL restores the ctx's own stream).  Lets a caller time or overlap
+ * the asynchronous *_device entry points with its own events. */
+int vsf_set_stream(vsf_ctx* ctx, void* cuda_stream);
+int vsf_synchronize(vsf_ctx* ctx);
+
+/* Kernel tuning knobs (0 = library default).  popc_mode: 0 = 8 POPC per
+ * 256-bit comparison, 2/3 = carry-save variants with 5/4 POPC.  train_split:
+ * force the number of train-dimension splits. */
+int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split, int queries_per_thread);
+
+/* ---------------------------------------------- a1: BFMatcher::knnMatch k=2 */
+
+/* Replaces `matcher_->knnMatch(query.descriptors_, train.descriptors_,
+ * matches, 2)` with matcher_ = cv::BFMatcher(NORM_HAMMING)
+ * (src/slam_frontend.cc:525-527, :247).
+ * q: nq rows of desc_bytes bytes, q_stride bytes apart (cv::Mat::step);
+ * idx, dist: nq x 2 int32, neighbour 0 then 1, ordered by (distance, trainIdx)
+ * ascending — ties resolve to the lowest train index, as OpenCV does.  Missing
+ * neighbours (nt < 2) are reported as idx = -1, dist = -1. */
+int vsf_knn2(vsf_ctx* ctx, const uint8_t* q, int nq, size_t q_stride,
+             const uint8_t* t, int nt, size_t t_stride,
+             int32_t* idx, int32_t* dist);
+
+/* ------------------------------------------------- a2: Frontend::GetMatches */
+
+/* Replaces Frontend::GetMatches(frame_query, frame_train, nn_match_ratio)
+ * (src/slam_frontend.cc:521-538): kNN k=2 then `dist1 < ratio * dist2`
+ * evaluated in double.  out receives the survivors in ascending queryIdx order
+ * (imgIdx = 0); *n_out their number.  nt < 2 yields no match (the reference
+ * reads out of bounds there).  VSF_ERR_CAPACITY if cap is too small. */
+int vsf_get_matches(vsf_ctx* ctx, const uint8_t* q, int nq, size_t q_stride,
+                    const uint8_t* t, int nt, size_t t_stride,
+                    double nn_match_ratio, vsf_dmatch* out, int cap, int* n_out);
+
+/* --------------------------- a3/a4: window loop of Frontend::ObserveImage */
+
+/* The sliding window `frame_list_` (src/slam_frontend.h:193) lives on the
+ * device.  vsf_window_push appends a frame's descriptors and evicts the oldest
+ * one first when the window already holds `window` frames — the order used at
+ * src/slam_frontend.cc:467-470. */
+int vsf_window_push(vsf_ctx* ctx, uint64_t frame_id, const uint8_t* desc, int n,
+                    size_t stride);
+/* Push the frame most recently handed to vsf_window_match /
+ * vsf_window_feature_matches (it is already on the device) without uploading
+ * it again; n = its row count. */
+int vsf_window_commit(vsf_ctx* ctx, uint64_t frame_id, int n);
+int vsf_window_clear(vsf_ctx* ctx);
+int vsf_window_size(const vsf_ctx* ctx);
+
+/* Replaces the loop `for (Frame& past_frame : frame_list_)
+ * GetMatches(past_frame, curr_frame, ratio)` (src/slam_frontend.cc:424-434 with
+ * :287-288) by ONE kernel launch over all resident past frames (query side)
+ * against the current frame (train side).  Output for past frame j (oldest
+ * first): frame_ids[j], counts[j] and counts[j] matches at
+ * out + j*cap_per_frame, in ascending queryIdx order.  *n_frames = number of
+ * past frames.  Does not push the current frame. */
+int vsf_window_match(vsf_ctx* ctx, const uint8_t* desc, int n, size_t stride,
+                     double nn_match_ratio, uint64_t* frame_ids, int* counts,
+                     vsf_dmatch* out, int cap_per_frame, int* n_frames);
+
+/* Same, followed by the rest of Frontend::GetFeatureMatches
+ * (src/slam_frontend.cc:289-296): order by distance, keep the first
+ * int(count * best_percent), emit FeatureMatch(queryIdx, trainIdx).
+ * sort_mode 0: the sort runs on the device and is stable, i.e. ordered by
+ * (distance, queryIdx); sort_mode 1: the library calls std::sort on the host
+ * exactly as the reference does (its order inside equal-distance groups is
+ * libstdc++-specific).  The two differ only inside groups of equal distance. */
+int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
+                               size_t stride, double nn_match_ratio,
+                               float best_percent, int sort_mode,
+                               uint64_t* frame_ids, int* counts,
+                               vsf_feature_match* out, int cap_per_frame,
+                               int* n_frames);
+
+/* ------------------------- a5: stereo L->R match + RemoveAmbigStereo */
+
+/* Replaces `GetMatches(curr, right, ratio)` + Frontend::RemoveAmbigStereo
+ * (src/slam_frontend.cc:414-417, :353-398).
+ * fundamental: 9 floats row-major, convention x_left^T F x_right (:380-381).
+ * The adaptive threshold (file-scope static at :353 in the reference) lives in
+ * the ctx: starts at 10000, becomes mean(residual over all matches) + 2 after
+ * every call; vsf_set/get_stereo_threshold expose it (the 1-float halo needed
+ * to start a shard in the middle of a sequence).
+ * Outputs (all optional except n_kept): kept_left/kept_right = indices into the
+ * input frames of the M surviving pairs, in match order, so left'[i] =
+ * left[kept_left[i]], right'[i] = right[kept_right[i]]; stereo_matches /
+ * residuals / n_stereo = the pre-filter L->R matches and their residuals.
+ * (vsf_observe_features is the fused entry point that keeps the compacted
+ * frames on the device for the window and triangulation stages.) */
+int vsf_stereo_filter(vsf_ctx* ctx,
+                      const vsf_keypoint* kp_left, const uint8_t* desc_left,
+                      int n_left, size_t stride_left,
+                      const vsf_keypoint* kp_right, const uint8_t* desc_right,
+                      int n_right, size_t stride_right,
+                      const float* fundamental, double nn_match_ratio,
+                      int32_t* kept_left, int32_t* kept_right, int* n_kept,
+                      vsf_dmatch* stereo_matches, float* residuals, int* n_stereo);
+int vsf_set_stereo_threshold(vsf_ctx* ctx, float value);
+int vsf_get_stereo_threshold(vsf_ctx* ctx, float* value);
+
+/* ------------------------------------------- a6: cv::triangulatePoints */
+
+/* Replaces cv::triangulatePoints(P1, P2, pts1, pts2, out)
+ * (src/slam_frontend.cc:152-156).  P1, P2: 3x4 row-major float32.  x1, x2:
+ * n (x,y) float32 pairs.  X4: 4 x n row-major float32 like the 4xN CV_32F
+ * matrix OpenCV returns (unit-norm homogeneous columns; the sign of a column
+ * is arbitrary and cancels in xyz/w).  Internals are fp64. */
+int vsf_triangulate(vsf_ctx* ctx, const float* P1, const float* P2,
+                    const float* x1, const float* x2, int n, float* X4);
+
+/* ----------------- whole matching path of Frontend::ObserveImage, fused */
+
+typedef struct vsf_observe_out {
+  /* stereo stage (a5) */
+  int32_t* kept_left;          /* [cap] */
+  int32_t* kept_right;         /* [cap] */
+  int n_kept;                  /* M */
+  float stereo_threshold_next; /* threshold after this frame */
+  /* window stage (a4): past frames oldest first */
+  int n_frames;
+  uint64_t* frame_ids;         /* [window] */
+  int* window_counts;          /* [window] */
+  vsf_dmatch* window_matches;  /* [window][cap], query order */
+  /* triangulation stage (a6): R'->L' matches in query order + their points */
+  int n_tri;
+  vsf_dmatch* tri_matches;     /* [cap] */
+  float* tri_X4;               /* [cap][4] homogeneous points, match order */
+  int cap;                     /* capacity of the per-frame arrays */
+} vsf_observe_out;
+
+/* Replaces everything Frontend::ObserveImage does between ExtractFeatures and
+ * the SLAMNode assembly (src/slam_frontend.cc:414-437), device-resident:
+ * stereo kNN + ratio + epipolar filter + compaction, window kNN against all
+ * resident frames, R'->L' kNN + ratio + triangulation, then pushes the
+ * compacted left frame into the window (evicting per :467-469).  The sort /
+ * best_percent cut / FeatureMatch book-keeping stay with the caller (the C++
+ * Frontend mirror does them with std::sort like the reference). */
+int vsf_observe_features(vsf_ctx* ctx, uint64_t frame_id,
+                         const vsf_keypoint* kp_left, const uint8_t* desc_left,
+                         int n_left, size_t stride_left,
+                         const vsf_keypoint* kp_right, const uint8_t* desc_right,
+                         int n_right, size_t stride_right,
+                         const float* fundamental, const float* P_left,
+                         const float* P_right, double nn_match_ratio,
+                         vsf_observe_out* out);
+
+/* ------------------------ device-resident entry points (no host copies) */
+
+/* Asynchronous on the ctx stream; all pointers are device pointers.
+ * Descriptor rows must already be padded to vsf_device_row_bytes(ctx). */
+int vsf_device_row_bytes(const vsf_ctx* ctx);
+
+/* Window matching for one pose of a device-resident sequence: query frame j
+ * has nq[j] rows at d_queries[j], train frame has nt rows at d_train.  Results
+ * go to the ctx's device buffers (read them back with vsf_fetch_window). */
+int vsf_window_match_device(vsf_ctx* ctx, const void* const* d_queries,
+                            const int* nq, int n_frames, const void* d_train,
+                            int nt, double nn_match_ratio);
+int vsf_fetch_window(vsf_ctx* ctx, int n_frames, int* counts, vsf_dmatch* out,
+                     int cap_per_frame);
+
+/* Synthetic sequence generator (bench / test frame source; counter-based so
+ * any pose range can be produced on any rank): pose p observes landmarks
+ * [stride*p, stride*p + n) in a per-pose affine permutation, every bit flipped
+ * with probability 1/32.  Writes n rows per pose for poses
+ * [first_pose, first_pose + n_poses) at d_out. */
+int vsf_synth_sequence_device(vsf_ctx* ctx, void* d_out, int n, int first_pose,
+                              int n_poses, int stride, uint64_t seed);
+
+/* Integer-pipe probe used for the roofline denominator: runs `iters` dependent
+ * instructions of kind (0 = POPC, 1 = LOP3, 2 = POPC+LOP3 interleaved 1:1,
+ * 3 = IMAD, 4 = VIMNMX, 5 = POPC+LOP3 1:2, 6 = IADD3) on every SM and returns
+ * the measured lane-operations per second. */
+int vsf_probe_pipe(vsf_ctx* ctx, int kind, int iters, double* ops_per_second);
+
+int vsf_device_sm_count(const vsf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VSF_H_ */

@@ -1,0 +1,302 @@
+// Kernel 1: batched brute-force k=2 Hamming kNN + Lowe ratio test + ordered
+// compaction, for sm_100a.
+//
+// Replaces, for a whole batch of (query frame, train frame) problems in one
+// launch, what the reference does per pair with
+//   matcher_->knnMatch(q, t, matches, 2)            src/slam_frontend.cc:525-527
+//   if (dist1 < nn_match_ratio * dist2) keep first   src/slam_frontend.cc:529-536
+// and the loop over the sliding window                src/slam_frontend.cc:424-434.
+//
+// Mapping
+//   grid  = (query blocks, problems, train splits)
+//   CTA   = 8 consumer warps + 1 TMA producer warp
+//   each consumer thread keeps R query descriptors in registers (32*R queries
+//   per CTA); the CTA's train rows stream through a 4-stage shared-memory ring
+//   filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier); the rows of a tile
+//   are dealt round-robin to the 8 warps, every lane of a warp reads the same
+//   train row (LDS.128 broadcast), XOR + POPC on the integer pipe, and the
+//   running top-2 lives in registers as packed (distance<<22 | trainIdx) keys
+//   so min/max implement the lexicographic (distance, trainIdx) order.
+//   Warps are merged through shared memory, train splits through global memory
+//   (last-arriver pattern), and the last CTA of a problem compacts the ratio
+//   survivors in ascending query order.
+#include "vsf_device.cuh"
+
+namespace vsf {
+
+template <int WORDS, int MODE>
+__device__ __forceinline__ uint32_t hamming_row(const uint32_t* q, const uint32_t* t) {
+  uint32_t d = hamming256<MODE>(q, t);
+  if (WORDS == 16) d += hamming256<MODE>(q + 8, t + 8);
+  return d;
+}
+
+template <int WORDS, int R, int MODE>
+__global__ void __launch_bounds__(kKnnThreads)
+knn2_kernel(const __grid_constant__ KnnBatch batch) {
+  constexpr int QB = 32 * R;
+  constexpr int ROW_BYTES = WORDS * 4;
+  constexpr int TILE_ROWS = kTileBytes / ROW_BYTES;
+  constexpr int SCAN_CHUNK = 1024;
+
+  __shared__ __align__(128) uint8_t s_tile[kStages][kTileBytes];
+  __shared__ __align__(8) uint64_t s_full[kStages];
+  __shared__ __align__(8) uint64_t s_empty[kStages];
+  __shared__ uint32_t s_merge[kConsumerWarps][QB][2];
+  __shared__ uint32_t s_off[SCAN_CHUNK];
+  __shared__ int s_flag;
+
+  const KnnProblem& P = batch.p[blockIdx.y];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  int nq = P.nq, nt = P.nt;
+  if (P.nq_dev) nq = min(nq, *P.nq_dev);
+  if (P.nt_dev) nt = min(nt, *P.nt_dev);
+
+  if (nq <= 0) {
+    if (blockIdx.x == 0 && blockIdx.z == 0 && tid == 0) *P.match_count = 0;
+    return;
+  }
+  const int qb = blockIdx.x;
+  const int q0 = qb * QB;
+  if (q0 >= nq) return;
+  const int nqb = (nq + QB - 1) / QB;
+
+  const int S = batch.split;
+  const int z = blockIdx.z;
+  const int rows_per_split = (nt + S - 1) / S;
+  const int t_begin = min(nt, z * rows_per_split);
+  const int t_end = min(nt, t_begin + rows_per_split);
+  const int ntiles = (t_end - t_begin + TILE_ROWS - 1) / TILE_ROWS;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  uint32_t m1[R], m2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) m1[r] = m2[r] = kKeySentinel;
+
+  if (warp == kConsumerWarps) {
+    // ---------------- TMA producer: one elected lane ----------------
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(P.t) + size_t(t_begin) * ROW_BYTES;
+      for (int k = 0; k < ntiles; ++k) {
+        const int s = k % kStages;
+        const int u = k / kStages;
+        if (u > 0) mbar_wait(&s_empty[s], (u - 1) & 1);
+        const int rows = min(TILE_ROWS, t_end - t_begin - k * TILE_ROWS);
+        const uint32_t bytes = uint32_t(rows) * ROW_BYTES;
+        mbar_arrive_expect_tx(&s_full[s], bytes);
+        tma_load_1d(s_tile[s], src + size_t(k) * kTileBytes, bytes, &s_full[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- consumers ----------------
+    uint32_t qreg[R][WORDS];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int q = q0 + r * 32 + lane;
+      const uint4* src = reinterpret_cast<const uint4*>(P.q + size_t(q) * WORDS);
+#pragma unroll
+      for (int v = 0; v < WORDS / 4; ++v) {
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (q < nq) w = __ldg(src + v);
+        qreg[r][4 * v + 0] = w.x;
+        qreg[r][4 * v + 1] = w.y;
+        qreg[r][4 * v + 2] = w.z;
+        qreg[r][4 * v + 3] = w.w;
+      }
+    }
+    for (int k = 0; k < ntiles; ++k) {
+      const int s = k % kStages;
+      const int u = k / kStages;
+      mbar_wait(&s_full[s], u & 1);
+      const int rows = min(TILE_ROWS, t_end - t_begin - k * TILE_ROWS);
+      const uint32_t row_base = uint32_t(t_begin + k * TILE_ROWS);
+      const uint4* tile = reinterpret_cast<const uint4*>(s_tile[s]);
+#pragma unroll 2
+      for (int row = warp; row < rows; row += kConsumerWarps) {
+        uint32_t tw[WORDS];
+#pragma unroll
+        for (int v = 0; v < WORDS / 4; ++v) {
+          const uint4 w = tile[row * (WORDS / 4) + v];  // same address in every lane: broadcast
+          tw[4 * v + 0] = w.x;
+          tw[4 * v + 1] = w.y;
+          tw[4 * v + 2] = w.z;
+          tw[4 * v + 3] = w.w;
+        }
+        const uint32_t idx = row_base + uint32_t(row);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint32_t d = hamming_row<WORDS, MODE>(qreg[r], tw);
+          const uint32_t key = (d << kIdxBits) + idx;
+          top2_insert(m1[r], m2[r], key);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      s_merge[warp][r * 32 + lane][0] = m1[r];
+      s_merge[warp][r * 32 + lane][1] = m2[r];
+    }
+  }
+  __syncthreads();
+
+  // ---------------- merge the 8 warps (thread tid < QB owns query q0+tid) ----------------
+  uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
+  if (tid < QB) {
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) top2_merge(k1, k2, s_merge[w][tid][0], s_merge[w][tid][1]);
+  }
+
+  const int row = P.row0 + q0 + tid;  // row of this thread's query in knn_out / partial
+  if (S > 1) {
+    // ---------------- merge the train splits: last arriver does it ----------------
+    if (tid < QB) {
+      batch.partial[size_t(row) * S + z] = make_uint2(k1, k2);
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(&batch.qblock_arrivals[P.qb0 + qb], 1u);
+      const int last = (prev == unsigned(S - 1));
+      if (last) batch.qblock_arrivals[P.qb0 + qb] = 0u;  // self-reset for the next launch
+      s_flag = last;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    if (tid < QB) {
+      k1 = k2 = kKeySentinel;
+      for (int s = 0; s < S; ++s) {
+        const uint2 p = __ldcg(&batch.partial[size_t(row) * S + s]);
+        top2_merge(k1, k2, p.x, p.y);
+      }
+    }
+  }
+
+  // ---------------- finalize: unpack, ratio test ----------------
+  bool pass = false;
+  if (tid < QB && q0 + tid < nq) {
+    const int i0 = (k1 == kKeySentinel) ? -1 : int(k1 & kIdxMask);
+    const int i1 = (k2 == kKeySentinel) ? -1 : int(k2 & kIdxMask);
+    const int d0 = (k1 == kKeySentinel) ? -1 : int(k1 >> kIdxBits);
+    const int d1 = (k2 == kKeySentinel) ? -1 : int(k2 >> kIdxBits);
+    batch.knn_out[row] = make_uint4(uint32_t(i0), uint32_t(i1), uint32_t(d0), uint32_t(d1));
+    // `dist1 < nn_match_ratio * dist2` in double (src/slam_frontend.cc:533);
+    // fewer than 2 train rows: no match passes.
+    pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
+    __threadfence();
+  }
+  const int npass = __syncthreads_count(pass);
+  if (tid == 0) {
+    batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
+    __threadfence();
+    const unsigned prev = atomicAdd(&batch.problem_arrivals[blockIdx.y], 1u);
+    const int last = (prev == unsigned(nqb - 1));
+    if (last) batch.problem_arrivals[blockIdx.y] = 0u;
+    s_flag = last;
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+
+  // ---------------- tail: the problem's last CTA compacts survivors in query order -------------
+  uint32_t base = 0;
+  for (int c0 = 0; c0 < nqb; c0 += SCAN_CHUNK) {
+    const int cn = min(SCAN_CHUNK, nqb - c0);
+    if (warp == 0) {
+      // exclusive scan of the per-query-block survivor counts of this chunk
+      uint32_t run = base;
+      for (int i = lane; i < ((cn + 31) & ~31); i += 32) {
+        const uint32_t c = (i < cn) ? __ldcg(&batch.qblock_pass[P.qb0 + c0 + i]) : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n;
+        }
+        if (i < cn) s_off[i] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) s_flag = int(run);
+    }
+    __syncthreads();
+    for (int b = warp; b < cn; b += kKnnThreads / 32) {
+      uint32_t off = s_off[b];
+#pragma unroll
+      for (int g = 0; g < R; ++g) {
+        const int q = (c0 + b) * QB + g * 32 + lane;
+        bool ok = false;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (q < nq) {
+          rec = __ldcg(&batch.knn_out[P.row0 + q]);
+          ok = (int(rec.y) >= 0) && (double(int(rec.z)) < batch.ratio * double(int(rec.w)));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const uint32_t dst = off + __popc(bal & ((1u << lane) - 1u));
+          int4 m;
+          m.x = q;            // queryIdx
+          m.y = int(rec.x);   // trainIdx
+          m.z = 0;            // imgIdx
+          m.w = __float_as_int(float(int(rec.z)));  // distance
+          reinterpret_cast<int4*>(P.matches)[dst] = m;
+        }
+        off += __popc(bal);
+      }
+    }
+    __syncthreads();
+    base = uint32_t(s_flag);
+    __syncthreads();
+  }
+  if (tid == 0) *P.match_count = int(base);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int WORDS, int R, int MODE>
+static cudaError_t launch_one(const KnnBatch& batch, int max_qblocks, cudaStream_t stream) {
+  dim3 grid(max_qblocks, batch.num_problems, batch.split);
+  knn2_kernel<WORDS, R, MODE><<<grid, kKnnThreads, 0, stream>>>(batch);
+  return cudaGetLastError();
+}
+
+template <int WORDS, int R>
+static cudaError_t launch_mode(const KnnBatch& b, int mode, int mq, cudaStream_t s) {
+  switch (mode) {
+    case 0: return launch_one<WORDS, R, 0>(b, mq, s);
+    case 2: return launch_one<WORDS, R, 2>(b, mq, s);
+    case 3: return launch_one<WORDS, R, 3>(b, mq, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// words: 8 or 16; R: queries per thread (1, 2 or 4; 4 only for 8 words).
+// max_qblocks: ceil(max nq / (32*R)) over the batch's problems.
+cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int max_qblocks,
+                        cudaStream_t stream) {
+  if (batch.num_problems <= 0 || max_qblocks <= 0) return cudaSuccess;
+  if (words == 8) {
+    if (R == 1) return launch_mode<8, 1>(batch, mode, max_qblocks, stream);
+    if (R == 2) return launch_mode<8, 2>(batch, mode, max_qblocks, stream);
+    if (R == 4) return launch_mode<8, 4>(batch, mode, max_qblocks, stream);
+  } else if (words == 16) {
+    if (R == 1) return launch_mode<16, 1>(batch, mode, max_qblocks, stream);
+    if (R == 2) return launch_mode<16, 2>(batch, mode, max_qblocks, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace vsf

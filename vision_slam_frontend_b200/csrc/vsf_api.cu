@@ -1,0 +1,856 @@
+// C ABI of libvsf_cuda.so (declared in include/vsf.h): context, buffers, host<->device
+// staging and the launch sequences.  No CPU fallback anywhere: if CUDA is unavailable
+// every entry point reports VSF_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "stereo_args.cuh"
+#include "vsf_device.cuh"
+
+namespace vsf {
+cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int max_qblocks,
+                        cudaStream_t stream);
+cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
+                         uint64_t seed, cudaStream_t stream);
+int probe_ops_per_step(int kind);
+cudaError_t launch_probe(int kind, uint32_t* sink, int iters, int blocks, int threads,
+                         cudaStream_t stream);
+cudaError_t launch_triangulate_pairs(const float* P1, const float* P2, const float2* x1,
+                                     const float2* x2, int n, float* X4, cudaStream_t stream);
+cudaError_t launch_triangulate_matches(const float* P1, const float* P2, const vsf_dmatch* matches,
+                                       const int* n_matches, int max_matches,
+                                       const float2* xy_left_c, const float2* xy_right_c,
+                                       float4* X4, cudaStream_t stream);
+cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* counts,
+                            int n_problems, float best_percent, vsf_feature_match* out,
+                            int out_stride, int* out_counts, int max_matches, cudaStream_t stream);
+}  // namespace vsf
+
+
+using namespace vsf;
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct ProblemSpec {
+  const void* q;
+  int nq;
+  const int* nq_dev;
+  const void* t;
+  int nt;
+  const int* nt_dev;
+  int region;  // which d_matches region / d_match_count slot receives the survivors
+};
+
+struct vsf_ctx {
+  int device = 0, max_features = 0, desc_bytes = 0, row_bytes = 0, words = 0, window = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int popc_mode = 0, force_split = 0, force_R = 0;
+
+  int rows_pad = 0;    // max_features rounded up to 128
+  int regions = 0;     // window + 2
+  // device
+  uint8_t* d_ring = nullptr;
+  uint8_t *d_raw_left = nullptr, *d_raw_right = nullptr, *d_right_c = nullptr;
+  float2 *d_xy_left = nullptr, *d_xy_right = nullptr, *d_xy_left_c = nullptr, *d_xy_right_c = nullptr;
+  uint4* d_knn_out = nullptr;
+  uint2* d_partial = nullptr;
+  size_t partial_cap = 0;
+  unsigned *d_qblock_arrivals = nullptr, *d_qblock_pass = nullptr, *d_problem_arrivals = nullptr;
+  vsf_dmatch* d_matches = nullptr;
+  int* d_match_count = nullptr;
+  float* d_resid = nullptr;
+  unsigned* d_chunk_keep = nullptr;
+  int *d_kept_left = nullptr, *d_kept_right = nullptr, *d_n_kept = nullptr;
+  float* d_thresh = nullptr;  // [2], ping-pong
+  int thresh_cur = 0;
+  float4* d_X4 = nullptr;
+  float* d_tri_io = nullptr;  // stateless triangulate: x1 | x2 | X4
+  uint32_t* d_sink = nullptr;
+  vsf_feature_match* d_fm = nullptr;  // [window][rows_pad] sorted+cut feature matches
+  int* d_fm_count = nullptr;
+  // pinned host staging
+  uint8_t* h_desc[2] = {nullptr, nullptr};
+  float2* h_xy[2] = {nullptr, nullptr};
+  int* h_counts = nullptr;         // kMaxProblems + 8
+  vsf_dmatch* h_matches = nullptr;  // regions * rows_pad
+  int* h_kept[2] = {nullptr, nullptr};
+  float* h_resid = nullptr;
+  float4* h_X4 = nullptr;
+  uint4* h_knn = nullptr;
+  float* h_tri_io = nullptr;
+  float* h_scalar = nullptr;
+  vsf_feature_match* h_fm = nullptr;
+  // sliding window (frame_list_) state
+  std::vector<int> slot_count;
+  std::vector<uint64_t> slot_frame;
+  std::deque<int> live;   // slot indices, oldest first
+  int staging_slot = 0;
+  int last_n_frames = 0;  // of the last vsf_window_match_device
+
+  uint8_t* slot_ptr(int s) const { return d_ring + size_t(s) * rows_pad * row_bytes; }
+  vsf_dmatch* region_ptr(int r) const { return d_matches + size_t(r) * rows_pad; }
+};
+
+#define VSF_CUDA(ctx, expr)                                                             \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                 \
+      return VSF_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+static int fail(vsf_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+static int pick_free_slot(const vsf_ctx* c) {
+  for (int s = 0; s <= c->window; ++s)
+    if (std::find(c->live.begin(), c->live.end(), s) == c->live.end()) return s;
+  return 0;
+}
+
+// frame_list_ eviction + push (src/slam_frontend.cc:467-470)
+static void commit_staging(vsf_ctx* c, uint64_t frame_id, int count) {
+  if (int(c->live.size()) >= c->window) c->live.pop_front();
+  c->slot_count[c->staging_slot] = count;
+  c->slot_frame[c->staging_slot] = frame_id;
+  c->live.push_back(c->staging_slot);
+  c->staging_slot = pick_free_slot(c);
+}
+
+// Pack caller rows (stride apart, desc_bytes wide) into pinned staging padded to
+// row_bytes, then one async H2D copy.
+static int upload_desc(vsf_ctx* c, int which, const uint8_t* src, int n, size_t stride,
+                       uint8_t* d_dst) {
+  if (n == 0) return VSF_OK;
+  uint8_t* h = c->h_desc[which];
+  if (stride == size_t(c->row_bytes) && c->desc_bytes == c->row_bytes) {
+    std::memcpy(h, src, size_t(n) * c->row_bytes);
+  } else {
+    for (int i = 0; i < n; ++i) {
+      std::memcpy(h + size_t(i) * c->row_bytes, src + size_t(i) * stride, c->desc_bytes);
+      if (c->desc_bytes < c->row_bytes)
+        std::memset(h + size_t(i) * c->row_bytes + c->desc_bytes, 0, c->row_bytes - c->desc_bytes);
+    }
+  }
+  VSF_CUDA(c, cudaMemcpyAsync(d_dst, h, size_t(n) * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
+  return VSF_OK;
+}
+
+static int upload_xy(vsf_ctx* c, int which, const vsf_keypoint* kp, int n, float2* d_dst) {
+  if (n == 0) return VSF_OK;
+  float2* h = c->h_xy[which];
+  for (int i = 0; i < n; ++i) h[i] = make_float2(kp[i].x, kp[i].y);
+  VSF_CUDA(c, cudaMemcpyAsync(d_dst, h, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  return VSF_OK;
+}
+
+// Build the batch, choose (R, split) and launch kernel 1.
+static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio) {
+  if (specs.empty()) return VSF_OK;
+  if (int(specs.size()) > kMaxProblems) return fail(c, VSF_ERR_CAPACITY, "too many problems in one batch");
+  KnnBatch b;
+  std::memset(&b, 0, sizeof(b));
+  b.num_problems = int(specs.size());
+  b.ratio = ratio;
+  b.knn_out = c->d_knn_out;
+  b.partial = c->d_partial;
+  b.qblock_arrivals = c->d_qblock_arrivals;
+  b.qblock_pass = c->d_qblock_pass;
+  b.problem_arrivals = c->d_problem_arrivals;
+  int row0 = 0, qb0 = 0, max_nq = 0, max_nt = 0;
+  long long total_q = 0;
+  for (int i = 0; i < b.num_problems; ++i) {
+    const ProblemSpec& s = specs[i];
+    if (s.nq > c->max_features || s.nt > c->max_features || s.nq < 0 || s.nt < 0)
+      return fail(c, VSF_ERR_CAPACITY, "frame has more rows than max_features");
+    KnnProblem& p = b.p[i];
+    p.q = static_cast<const uint32_t*>(s.q);
+    p.t = static_cast<const uint32_t*>(s.t);
+    p.nq_dev = s.nq_dev;
+    p.nt_dev = s.nt_dev;
+    p.nq = s.nq;
+    p.nt = s.nt;
+    p.matches = c->region_ptr(s.region);
+    p.match_count = c->d_match_count + s.region;
+    p.row0 = row0;
+    p.qb0 = qb0;
+    row0 += round_up(std::max(s.nq, 1), 128);
+    qb0 += round_up(std::max(s.nq, 1), 128) / 32;
+    max_nq = std::max(max_nq, s.nq);
+    max_nt = std::max(max_nt, s.nt);
+    total_q += s.nq;
+  }
+  if (max_nq == 0) {
+    // nothing to match: every problem reports zero survivors
+    for (int i = 0; i < b.num_problems; ++i)
+      VSF_CUDA(c, cudaMemsetAsync(c->d_match_count + specs[i].region, 0, sizeof(int), c->stream));
+    return VSF_OK;
+  }
+  // queries per thread: the largest R that still gives every SM two CTAs
+  int R = c->force_R;
+  if (R == 0) {
+    R = 1;
+    const int cand[3] = {4, 2, 1};
+    for (int k = 0; k < 3; ++k) {
+      if (cand[k] == 4 && c->words != 8) continue;
+      long long qblocks = 0;
+      for (const ProblemSpec& s : specs) qblocks += (s.nq + 32 * cand[k] - 1) / (32 * cand[k]);
+      if (qblocks >= 2LL * c->sm_count) {
+        R = cand[k];
+        break;
+      }
+    }
+  }
+  if (c->words == 16 && R > 2) R = 2;
+  long long qblocks = 0;
+  for (const ProblemSpec& s : specs) qblocks += (s.nq + 32 * R - 1) / (32 * R);
+  // train splits: aim for ~3 CTAs per SM, keep >= 64 train rows per split
+  int S = c->force_split;
+  if (S == 0) {
+    S = int((3LL * c->sm_count + qblocks - 1) / std::max(1LL, qblocks));
+    S = std::min(S, std::max(1, max_nt / 64));
+  }
+  S = std::max(1, std::min(S, 32));
+  while (S > 1 && size_t(row0) * S > c->partial_cap) --S;
+  b.split = S;
+  const int max_qblocks = (max_nq + 32 * R - 1) / (32 * R);
+  VSF_CUDA(c, launch_knn2(b, c->words, R, c->popc_mode, max_qblocks, c->stream));
+  return VSF_OK;
+}
+
+// ------------------------------------------------------------------------------------ context
+
+extern "C" const char* vsf_version(void) { return VSF_VERSION_STRING; }
+
+extern "C" const char* vsf_last_error(const vsf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" void vsf_destroy(vsf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  void* dev[] = {c->d_ring, c->d_raw_left, c->d_raw_right, c->d_right_c, c->d_xy_left, c->d_xy_right,
+                 c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_qblock_arrivals,
+                 c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
+                 c->d_chunk_keep, c->d_kept_left, c->d_kept_right, c->d_n_kept, c->d_thresh, c->d_X4,
+                 c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  void* host[] = {c->h_desc[0], c->h_desc[1], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches,
+                  c->h_kept[0], c->h_kept[1], c->h_resid, c->h_X4, c->h_knn, c->h_tri_io,
+                  c->h_scalar, c->h_fm};
+  for (void* p : host)
+    if (p) cudaFreeHost(p);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+#define VSF_ALLOC(ctx, ptr, bytes)                                                      \
+  do {                                                                                  \
+    cudaError_t e__ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));            \
+    if (e__ != cudaSuccess) {                                                           \
+      std::fprintf(stderr, "vsf_create: cudaMalloc(%zu) failed: %s\n", size_t(bytes),   \
+                   cudaGetErrorString(e__));                                            \
+      vsf_destroy(ctx);                                                                 \
+      return VSF_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+#define VSF_ALLOC_HOST(ctx, ptr, bytes)                                                 \
+  do {                                                                                  \
+    cudaError_t e__ = cudaMallocHost(reinterpret_cast<void**>(&(ptr)), (bytes));        \
+    if (e__ != cudaSuccess) {                                                           \
+      std::fprintf(stderr, "vsf_create: cudaMallocHost(%zu) failed: %s\n",              \
+                   size_t(bytes), cudaGetErrorString(e__));                             \
+      vsf_destroy(ctx);                                                                 \
+      return VSF_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+extern "C" int vsf_create(int device, int max_features, int desc_bytes, int window, vsf_ctx** out) {
+  if (!out) return VSF_ERR_BAD_ARG;
+  *out = nullptr;
+  if (max_features < 1 || max_features > kMaxRows || desc_bytes < 1 || desc_bytes > 64 ||
+      window < 1 || window > kMaxProblems - 2)
+    return VSF_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    std::fprintf(stderr, "vsf_create: CUDA device %d not available (no CPU fallback exists)\n", device);
+    return VSF_ERR_CUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return VSF_ERR_CUDA;
+  vsf_ctx* c = new vsf_ctx();
+  c->device = device;
+  c->max_features = max_features;
+  c->desc_bytes = desc_bytes;
+  c->row_bytes = desc_bytes <= 32 ? 32 : 64;
+  c->words = c->row_bytes / 4;
+  c->window = window;
+  c->rows_pad = round_up(max_features, 128);
+  c->regions = window + 2;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return VSF_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+
+  const size_t N = size_t(c->rows_pad);
+  const size_t rows_cap = size_t(c->regions) * N;
+  VSF_ALLOC(c, c->d_ring, size_t(window + 1) * N * c->row_bytes);
+  VSF_ALLOC(c, c->d_raw_left, N * c->row_bytes);
+  VSF_ALLOC(c, c->d_raw_right, N * c->row_bytes);
+  VSF_ALLOC(c, c->d_right_c, N * c->row_bytes);
+  VSF_ALLOC(c, c->d_xy_left, N * sizeof(float2));
+  VSF_ALLOC(c, c->d_xy_right, N * sizeof(float2));
+  VSF_ALLOC(c, c->d_xy_left_c, N * sizeof(float2));
+  VSF_ALLOC(c, c->d_xy_right_c, N * sizeof(float2));
+  VSF_ALLOC(c, c->d_knn_out, rows_cap * sizeof(uint4));
+  c->partial_cap = rows_cap * 2 + 262144;
+  VSF_ALLOC(c, c->d_partial, c->partial_cap * sizeof(uint2));
+  const size_t qb_cap = rows_cap / 32 + kMaxProblems * 4;
+  VSF_ALLOC(c, c->d_qblock_arrivals, qb_cap * sizeof(unsigned));
+  VSF_ALLOC(c, c->d_qblock_pass, qb_cap * sizeof(unsigned));
+  VSF_ALLOC(c, c->d_problem_arrivals, kMaxProblems * sizeof(unsigned));
+  cudaMemset(c->d_qblock_arrivals, 0, qb_cap * sizeof(unsigned));
+  cudaMemset(c->d_qblock_pass, 0, qb_cap * sizeof(unsigned));
+  cudaMemset(c->d_problem_arrivals, 0, kMaxProblems * sizeof(unsigned));
+  VSF_ALLOC(c, c->d_matches, rows_cap * sizeof(vsf_dmatch));
+  VSF_ALLOC(c, c->d_match_count, kMaxProblems * sizeof(int));
+  cudaMemset(c->d_match_count, 0, kMaxProblems * sizeof(int));
+  VSF_ALLOC(c, c->d_resid, N * sizeof(float));
+  VSF_ALLOC(c, c->d_chunk_keep, (N / 256 + 2) * sizeof(unsigned));
+  VSF_ALLOC(c, c->d_kept_left, N * sizeof(int));
+  VSF_ALLOC(c, c->d_kept_right, N * sizeof(int));
+  VSF_ALLOC(c, c->d_n_kept, sizeof(int));
+  VSF_ALLOC(c, c->d_thresh, 2 * sizeof(float));
+  VSF_ALLOC(c, c->d_X4, N * sizeof(float4));
+  VSF_ALLOC(c, c->d_tri_io, N * 8 * sizeof(float));
+  VSF_ALLOC(c, c->d_sink, 64);
+  VSF_ALLOC(c, c->d_fm, size_t(window) * N * sizeof(vsf_feature_match));
+  VSF_ALLOC(c, c->d_fm_count, kMaxProblems * sizeof(int));
+  {
+    const float init[2] = {10000.0f, 10000.0f};  // stereo_ambig_constraint (src/slam_frontend.cc:353)
+    cudaMemcpy(c->d_thresh, init, sizeof(init), cudaMemcpyHostToDevice);
+  }
+  for (int k = 0; k < 2; ++k) {
+    VSF_ALLOC_HOST(c, c->h_desc[k], N * c->row_bytes);
+    VSF_ALLOC_HOST(c, c->h_xy[k], N * sizeof(float2));
+    VSF_ALLOC_HOST(c, c->h_kept[k], N * sizeof(int));
+  }
+  VSF_ALLOC_HOST(c, c->h_counts, (kMaxProblems + 8) * sizeof(int));
+  VSF_ALLOC_HOST(c, c->h_matches, rows_cap * sizeof(vsf_dmatch));
+  VSF_ALLOC_HOST(c, c->h_resid, N * sizeof(float));
+  VSF_ALLOC_HOST(c, c->h_X4, N * sizeof(float4));
+  VSF_ALLOC_HOST(c, c->h_knn, N * sizeof(uint4));
+  VSF_ALLOC_HOST(c, c->h_tri_io, N * 8 * sizeof(float));
+  VSF_ALLOC_HOST(c, c->h_scalar, 16 * sizeof(float));
+  VSF_ALLOC_HOST(c, c->h_fm, size_t(window) * N * sizeof(vsf_feature_match));
+  c->slot_count.assign(window + 1, 0);
+  c->slot_frame.assign(window + 1, 0);
+  c->staging_slot = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    vsf_destroy(c);
+    return VSF_ERR_CUDA;
+  }
+  *out = c;
+  return VSF_OK;
+}
+
+extern "C" int vsf_set_stream(vsf_ctx* c, void* cuda_stream) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  cudaSetDevice(c->device);
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return VSF_OK;
+}
+
+extern "C" int vsf_synchronize(vsf_ctx* c) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  cudaSetDevice(c->device);
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VSF_OK;
+}
+
+extern "C" int vsf_set_tuning(vsf_ctx* c, int popc_mode, int train_split, int queries_per_thread) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!(popc_mode == 0 || popc_mode == 2 || popc_mode == 3)) return fail(c, VSF_ERR_BAD_ARG, "popc_mode must be 0, 2 or 3");
+  if (train_split < 0 || train_split > 32) return fail(c, VSF_ERR_BAD_ARG, "train_split must be 0..32");
+  if (!(queries_per_thread == 0 || queries_per_thread == 1 || queries_per_thread == 2 ||
+        queries_per_thread == 4))
+    return fail(c, VSF_ERR_BAD_ARG, "queries_per_thread must be 0, 1, 2 or 4");
+  c->popc_mode = popc_mode;
+  c->force_split = train_split;
+  c->force_R = queries_per_thread;
+  return VSF_OK;
+}
+
+extern "C" int vsf_device_sm_count(const vsf_ctx* c) { return c ? c->sm_count : 0; }
+extern "C" int vsf_device_row_bytes(const vsf_ctx* c) { return c ? c->row_bytes : 0; }
+
+// ------------------------------------------------------------------------- a1 / a2 (stateless)
+
+static int check_pair(vsf_ctx* c, const uint8_t* q, int nq, size_t qs, const uint8_t* t, int nt, size_t ts) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (nq < 0 || nt < 0 || (nq > 0 && !q) || (nt > 0 && !t)) return fail(c, VSF_ERR_BAD_ARG, "bad descriptor arguments");
+  if ((nq > 0 && qs < size_t(c->desc_bytes)) || (nt > 0 && ts < size_t(c->desc_bytes)))
+    return fail(c, VSF_ERR_BAD_ARG, "row stride smaller than desc_bytes");
+  if (nq > c->max_features || nt > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
+  return VSF_OK;
+}
+
+static int knn_pair(vsf_ctx* c, const uint8_t* q, int nq, size_t qs, const uint8_t* t, int nt, size_t ts,
+                    double ratio) {
+  cudaSetDevice(c->device);
+  int rc;
+  if ((rc = upload_desc(c, 0, q, nq, qs, c->d_raw_left))) return rc;
+  if ((rc = upload_desc(c, 1, t, nt, ts, c->d_raw_right))) return rc;
+  std::vector<ProblemSpec> specs(1);
+  specs[0] = ProblemSpec{c->d_raw_left, nq, nullptr, c->d_raw_right, nt, nullptr, c->window + 1};
+  return run_knn(c, specs, ratio);
+}
+
+extern "C" int vsf_knn2(vsf_ctx* c, const uint8_t* q, int nq, size_t q_stride, const uint8_t* t, int nt,
+                        size_t t_stride, int32_t* idx, int32_t* dist) {
+  int rc = check_pair(c, q, nq, q_stride, t, nt, t_stride);
+  if (rc) return rc;
+  if (nq == 0) return VSF_OK;
+  if (!idx || !dist) return fail(c, VSF_ERR_BAD_ARG, "null output");
+  if ((rc = knn_pair(c, q, nq, q_stride, t, nt, t_stride, 1.0))) return rc;
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_knn, c->d_knn_out, size_t(nq) * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nq; ++i) {
+    const uint4 r = c->h_knn[i];
+    idx[2 * i] = int32_t(r.x);
+    idx[2 * i + 1] = int32_t(r.y);
+    dist[2 * i] = int32_t(r.z);
+    dist[2 * i + 1] = int32_t(r.w);
+  }
+  return VSF_OK;
+}
+
+extern "C" int vsf_get_matches(vsf_ctx* c, const uint8_t* q, int nq, size_t q_stride, const uint8_t* t,
+                               int nt, size_t t_stride, double ratio, vsf_dmatch* out, int cap, int* n_out) {
+  int rc = check_pair(c, q, nq, q_stride, t, nt, t_stride);
+  if (rc) return rc;
+  if (!n_out || cap < 0 || (cap > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
+  *n_out = 0;
+  if (nq == 0) return VSF_OK;
+  if ((rc = knn_pair(c, q, nq, q_stride, t, nt, t_stride, ratio))) return rc;
+  const int region = c->window + 1;
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_match_count + region, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int n = c->h_counts[0];
+  if (n > cap) return fail(c, VSF_ERR_CAPACITY, "output capacity too small");
+  if (n > 0) {
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_matches, c->region_ptr(region), size_t(n) * sizeof(vsf_dmatch),
+                                cudaMemcpyDeviceToHost, c->stream));
+    VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(out, c->h_matches, size_t(n) * sizeof(vsf_dmatch));
+  }
+  *n_out = n;
+  return VSF_OK;
+}
+
+// ----------------------------------------------------------------------------- a4 (the window)
+
+extern "C" int vsf_window_size(const vsf_ctx* c) { return c ? int(c->live.size()) : 0; }
+
+extern "C" int vsf_window_clear(vsf_ctx* c) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  c->live.clear();
+  c->staging_slot = 0;
+  return VSF_OK;
+}
+
+extern "C" int vsf_window_push(vsf_ctx* c, uint64_t frame_id, const uint8_t* desc, int n, size_t stride) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (n < 0 || (n > 0 && !desc) || (n > 0 && stride < size_t(c->desc_bytes))) return fail(c, VSF_ERR_BAD_ARG, "bad frame");
+  if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
+  cudaSetDevice(c->device);
+  int rc = upload_desc(c, 0, desc, n, stride, c->slot_ptr(c->staging_slot));
+  if (rc) return rc;
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));  // pinned staging is reused by the next call
+  commit_staging(c, frame_id, n);
+  return VSF_OK;
+}
+
+extern "C" int vsf_window_commit(vsf_ctx* c, uint64_t frame_id, int n) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (n < 0 || n > c->max_features) return fail(c, VSF_ERR_BAD_ARG, "bad row count");
+  commit_staging(c, frame_id, n);
+  return VSF_OK;
+}
+
+static int window_launch(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio) {
+  if (n < 0 || (n > 0 && !desc) || (n > 0 && stride < size_t(c->desc_bytes))) return fail(c, VSF_ERR_BAD_ARG, "bad frame");
+  if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
+  cudaSetDevice(c->device);
+  int rc = upload_desc(c, 0, desc, n, stride, c->slot_ptr(c->staging_slot));
+  if (rc) return rc;
+  std::vector<ProblemSpec> specs;
+  int j = 0;
+  for (int s : c->live)
+    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, c->slot_ptr(c->staging_slot), n, nullptr, j++});
+  return run_knn(c, specs, ratio);
+}
+
+// counts first, then exactly the survivors of every region
+static int fetch_regions(vsf_ctx* c, int n_regions, int first_region) {
+  if (n_regions == 0) return VSF_OK;
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_match_count + first_region, n_regions * sizeof(int),
+                              cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int j = 0; j < n_regions; ++j) {
+    const int n = c->h_counts[j];
+    if (n > 0)
+      VSF_CUDA(c, cudaMemcpyAsync(c->h_matches + size_t(first_region + j) * c->rows_pad,
+                                  c->region_ptr(first_region + j), size_t(n) * sizeof(vsf_dmatch),
+                                  cudaMemcpyDeviceToHost, c->stream));
+  }
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VSF_OK;
+}
+
+extern "C" int vsf_window_match(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio,
+                                uint64_t* frame_ids, int* counts, vsf_dmatch* out, int cap_per_frame,
+                                int* n_frames) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!n_frames || !counts || cap_per_frame < 0 || (cap_per_frame > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
+  int rc = window_launch(c, desc, n, stride, ratio);
+  if (rc) return rc;
+  const int nf = int(c->live.size());
+  if ((rc = fetch_regions(c, nf, 0))) return rc;
+  *n_frames = nf;
+  for (int j = 0; j < nf; ++j) {
+    const int cnt = c->h_counts[j];
+    if (cnt > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
+    counts[j] = cnt;
+    if (frame_ids) frame_ids[j] = c->slot_frame[c->live[j]];
+    if (cnt) std::memcpy(out + size_t(j) * cap_per_frame, c->h_matches + size_t(j) * c->rows_pad, size_t(cnt) * sizeof(vsf_dmatch));
+  }
+  return VSF_OK;
+}
+
+namespace {
+struct ByDistance {  // cv::DMatch::operator<
+  bool operator()(const vsf_dmatch& a, const vsf_dmatch& b) const { return a.distance < b.distance; }
+};
+}  // namespace
+
+extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio,
+                                          float best_percent, int sort_mode, uint64_t* frame_ids, int* counts,
+                                          vsf_feature_match* out, int cap_per_frame, int* n_frames) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!n_frames || !counts || cap_per_frame < 0 || (cap_per_frame > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
+  if (sort_mode != 0 && sort_mode != 1) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 or 1");
+  int rc = window_launch(c, desc, n, stride, ratio);
+  if (rc) return rc;
+  const int nf = int(c->live.size());
+  *n_frames = nf;
+  if (sort_mode == 0) {
+    // device: stable counting sort by distance + best_percent cut, only survivors come back
+    std::vector<const vsf_dmatch*> mp(nf);
+    std::vector<const int*> cp(nf);
+    int max_matches = 0;
+    for (int j = 0; j < nf; ++j) {
+      mp[j] = c->region_ptr(j);
+      cp[j] = c->d_match_count + j;
+      max_matches = std::max(max_matches, c->slot_count[c->live[j]]);
+    }
+    if (nf > 0) {
+      VSF_CUDA(c, launch_sort_cut(mp.data(), cp.data(), nf, best_percent, c->d_fm, c->rows_pad,
+                                  c->d_fm_count, max_matches, c->stream));
+      VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_fm_count, nf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+      for (int j = 0; j < nf; ++j)
+        if (c->h_counts[j] > 0)
+          VSF_CUDA(c, cudaMemcpyAsync(c->h_fm + size_t(j) * c->rows_pad, c->d_fm + size_t(j) * c->rows_pad,
+                                      size_t(c->h_counts[j]) * sizeof(vsf_feature_match),
+                                      cudaMemcpyDeviceToHost, c->stream));
+      VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    for (int j = 0; j < nf; ++j) {
+      const int cnt = c->h_counts[j];
+      if (cnt > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
+      counts[j] = cnt;
+      if (frame_ids) frame_ids[j] = c->slot_frame[c->live[j]];
+      if (cnt) std::memcpy(out + size_t(j) * cap_per_frame, c->h_fm + size_t(j) * c->rows_pad, size_t(cnt) * sizeof(vsf_feature_match));
+    }
+    return VSF_OK;
+  }
+  // sort_mode 1: the reference's own host sequence (src/slam_frontend.cc:289-296)
+  if ((rc = fetch_regions(c, nf, 0))) return rc;
+  for (int j = 0; j < nf; ++j) {
+    vsf_dmatch* m = c->h_matches + size_t(j) * c->rows_pad;
+    const int cnt = c->h_counts[j];
+    std::sort(m, m + cnt, ByDistance());
+    const int good = int(float(size_t(cnt)) * best_percent);
+    if (good > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
+    counts[j] = good;
+    if (frame_ids) frame_ids[j] = c->slot_frame[c->live[j]];
+    vsf_feature_match* o = out + size_t(j) * cap_per_frame;
+    for (int i = 0; i < good; ++i) {
+      o[i].feature_idx_initial = uint64_t(m[i].queryIdx);
+      o[i].feature_idx_current = uint64_t(m[i].trainIdx);
+    }
+  }
+  return VSF_OK;
+}
+
+// ------------------------------------------------------------------------------ a5 (stereo)
+
+static void fill_stereo_args(vsf_ctx* c, StereoArgs& a, const float* F) {
+  std::memset(&a, 0, sizeof(a));
+  const int region = c->window + 1;
+  a.matches = c->region_ptr(region);
+  a.n_matches = c->d_match_count + region;
+  a.xy_left = c->d_xy_left;
+  a.xy_right = c->d_xy_right;
+  for (int i = 0; i < 9; ++i) a.F[i] = F[i];
+  a.thresh_cur = c->d_thresh + c->thresh_cur;
+  a.thresh_next = c->d_thresh + (c->thresh_cur ^ 1);
+  a.resid = c->d_resid;
+  a.chunk_keep = c->d_chunk_keep;
+  a.kept_left = c->d_kept_left;
+  a.kept_right = c->d_kept_right;
+  a.n_kept = c->d_n_kept;
+  a.desc_left = reinterpret_cast<const uint32_t*>(c->d_raw_left);
+  a.desc_right = reinterpret_cast<const uint32_t*>(c->d_raw_right);
+  a.desc_left_c = reinterpret_cast<uint32_t*>(c->slot_ptr(c->staging_slot));
+  a.desc_right_c = reinterpret_cast<uint32_t*>(c->d_right_c);
+  a.xy_left_c = c->d_xy_left_c;
+  a.xy_right_c = c->d_xy_right_c;
+  a.words = c->words;
+}
+
+// upload both frames, L->R kNN + ratio, epipolar filter + compaction (all async)
+static int stereo_stage(vsf_ctx* c, const vsf_keypoint* kpl, const uint8_t* dl, int nl, size_t sl,
+                        const vsf_keypoint* kpr, const uint8_t* dr, int nr, size_t sr, const float* F,
+                        double ratio) {
+  if (nl < 0 || nr < 0 || (nl > 0 && (!kpl || !dl)) || (nr > 0 && (!kpr || !dr)) || !F)
+    return fail(c, VSF_ERR_BAD_ARG, "bad stereo arguments");
+  if ((nl > 0 && sl < size_t(c->desc_bytes)) || (nr > 0 && sr < size_t(c->desc_bytes)))
+    return fail(c, VSF_ERR_BAD_ARG, "row stride smaller than desc_bytes");
+  if (nl > c->max_features || nr > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
+  cudaSetDevice(c->device);
+  int rc;
+  if ((rc = upload_desc(c, 0, dl, nl, sl, c->d_raw_left))) return rc;
+  if ((rc = upload_desc(c, 1, dr, nr, sr, c->d_raw_right))) return rc;
+  if ((rc = upload_xy(c, 0, kpl, nl, c->d_xy_left))) return rc;
+  if ((rc = upload_xy(c, 1, kpr, nr, c->d_xy_right))) return rc;
+  std::vector<ProblemSpec> specs(1);
+  specs[0] = ProblemSpec{c->d_raw_left, nl, nullptr, c->d_raw_right, nr, nullptr, c->window + 1};
+  if ((rc = run_knn(c, specs, ratio))) return rc;
+  StereoArgs a;
+  fill_stereo_args(c, a, F);
+  VSF_CUDA(c, launch_stereo_filter(a, std::max(nl, 1), c->stream));
+  c->thresh_cur ^= 1;
+  return VSF_OK;
+}
+
+extern "C" int vsf_stereo_filter(vsf_ctx* c, const vsf_keypoint* kpl, const uint8_t* dl, int nl, size_t sl,
+                                 const vsf_keypoint* kpr, const uint8_t* dr, int nr, size_t sr, const float* F,
+                                 double ratio, int32_t* kept_left, int32_t* kept_right, int* n_kept,
+                                 vsf_dmatch* stereo_matches, float* residuals, int* n_stereo) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!n_kept) return fail(c, VSF_ERR_BAD_ARG, "n_kept is required");
+  int rc = stereo_stage(c, kpl, dl, nl, sl, kpr, dr, nr, sr, F, ratio);
+  if (rc) return rc;
+  const int region = c->window + 1;
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_match_count + region, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int M = c->h_counts[0], ns = c->h_counts[1];
+  if (M > 0) {
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[0], c->d_kept_left, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[1], c->d_kept_right, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (ns > 0 && stereo_matches)
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_matches, c->region_ptr(region), size_t(ns) * sizeof(vsf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+  if (ns > 0 && residuals)
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_resid, c->d_resid, size_t(ns) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_kept = M;
+  if (n_stereo) *n_stereo = ns;
+  if (M > 0 && kept_left) std::memcpy(kept_left, c->h_kept[0], size_t(M) * sizeof(int));
+  if (M > 0 && kept_right) std::memcpy(kept_right, c->h_kept[1], size_t(M) * sizeof(int));
+  if (ns > 0 && stereo_matches) std::memcpy(stereo_matches, c->h_matches, size_t(ns) * sizeof(vsf_dmatch));
+  if (ns > 0 && residuals) std::memcpy(residuals, c->h_resid, size_t(ns) * sizeof(float));
+  return VSF_OK;
+}
+
+extern "C" int vsf_set_stereo_threshold(vsf_ctx* c, float value) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  cudaSetDevice(c->device);
+  c->h_scalar[0] = value;
+  VSF_CUDA(c, cudaMemcpyAsync(c->d_thresh + c->thresh_cur, c->h_scalar, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VSF_OK;
+}
+
+extern "C" int vsf_get_stereo_threshold(vsf_ctx* c, float* value) {
+  if (!c || !value) return VSF_ERR_BAD_ARG;
+  cudaSetDevice(c->device);
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_thresh + c->thresh_cur, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  *value = c->h_scalar[0];
+  return VSF_OK;
+}
+
+// --------------------------------------------------------------------------- a6 (triangulate)
+
+extern "C" int vsf_triangulate(vsf_ctx* c, const float* P1, const float* P2, const float* x1, const float* x2,
+                               int n, float* X4) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (n < 0 || !P1 || !P2 || (n > 0 && (!x1 || !x2 || !X4))) return fail(c, VSF_ERR_BAD_ARG, "bad triangulate arguments");
+  if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more points than max_features");
+  if (n == 0) return VSF_OK;
+  cudaSetDevice(c->device);
+  std::memcpy(c->h_tri_io, x1, size_t(n) * 2 * sizeof(float));
+  std::memcpy(c->h_tri_io + size_t(n) * 2, x2, size_t(n) * 2 * sizeof(float));
+  VSF_CUDA(c, cudaMemcpyAsync(c->d_tri_io, c->h_tri_io, size_t(n) * 4 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  float* dX = c->d_tri_io + size_t(c->rows_pad) * 4;
+  VSF_CUDA(c, launch_triangulate_pairs(P1, P2, reinterpret_cast<const float2*>(c->d_tri_io),
+                                       reinterpret_cast<const float2*>(c->d_tri_io + size_t(n) * 2), n, dX, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_tri_io, dX, size_t(n) * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::memcpy(X4, c->h_tri_io, size_t(n) * 4 * sizeof(float));
+  return VSF_OK;
+}
+
+// ------------------------------------------------------------------- fused ObserveImage path
+
+extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_keypoint* kpl, const uint8_t* dl,
+                                    int nl, size_t sl, const vsf_keypoint* kpr, const uint8_t* dr, int nr,
+                                    size_t sr, const float* F, const float* P_left, const float* P_right,
+                                    double ratio, vsf_observe_out* out) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!out || !P_left || !P_right) return fail(c, VSF_ERR_BAD_ARG, "null argument");
+  const int nf = int(c->live.size());
+  if (out->cap < nl) return fail(c, VSF_ERR_CAPACITY, "vsf_observe_out.cap must be >= n_left");
+  // a5: stereo L->R + filter; the compacted left frame lands in the ring's staging slot
+  int rc = stereo_stage(c, kpl, dl, nl, sl, kpr, dr, nr, sr, F, ratio);
+  if (rc) return rc;
+  // a4 + a6 matching in one launch: every resident past frame vs the compacted left
+  // frame, and compacted right (query) vs compacted left (train)
+  std::vector<ProblemSpec> specs;
+  int j = 0;
+  uint8_t* cur = c->slot_ptr(c->staging_slot);
+  for (int s : c->live)
+    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, cur, nl, c->d_n_kept, j++});
+  const int tri_region = c->window;
+  specs.push_back(ProblemSpec{c->d_right_c, nl, c->d_n_kept, cur, nl, c->d_n_kept, tri_region});
+  if ((rc = run_knn(c, specs, ratio))) return rc;
+  VSF_CUDA(c, launch_triangulate_matches(P_left, P_right, c->region_ptr(tri_region),
+                                         c->d_match_count + tri_region, nl, c->d_xy_left_c,
+                                         c->d_xy_right_c, c->d_X4, c->stream));
+  // results: counts first, then exactly-sized copies
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_match_count, (c->window + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts + kMaxProblems, c->d_n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_thresh + c->thresh_cur, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int M = c->h_counts[kMaxProblems];
+  const int n_tri = c->h_counts[tri_region];
+  if (M > 0) {
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[0], c->d_kept_left, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[1], c->d_kept_right, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  for (int k = 0; k < nf; ++k)
+    if (c->h_counts[k] > 0)
+      VSF_CUDA(c, cudaMemcpyAsync(c->h_matches + size_t(k) * c->rows_pad, c->region_ptr(k),
+                                  size_t(c->h_counts[k]) * sizeof(vsf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+  if (n_tri > 0) {
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_matches + size_t(tri_region) * c->rows_pad, c->region_ptr(tri_region),
+                                size_t(n_tri) * sizeof(vsf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_X4, c->d_X4, size_t(n_tri) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  }
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  out->n_kept = M;
+  out->stereo_threshold_next = c->h_scalar[0];
+  out->n_frames = nf;
+  out->n_tri = n_tri;
+  if (M > 0 && out->kept_left) std::memcpy(out->kept_left, c->h_kept[0], size_t(M) * sizeof(int));
+  if (M > 0 && out->kept_right) std::memcpy(out->kept_right, c->h_kept[1], size_t(M) * sizeof(int));
+  for (int k = 0; k < nf; ++k) {
+    if (out->frame_ids) out->frame_ids[k] = c->slot_frame[c->live[k]];
+    if (out->window_counts) out->window_counts[k] = c->h_counts[k];
+    if (out->window_matches && c->h_counts[k] > 0)
+      std::memcpy(out->window_matches + size_t(k) * out->cap, c->h_matches + size_t(k) * c->rows_pad,
+                  size_t(c->h_counts[k]) * sizeof(vsf_dmatch));
+  }
+  if (n_tri > 0 && out->tri_matches)
+    std::memcpy(out->tri_matches, c->h_matches + size_t(tri_region) * c->rows_pad, size_t(n_tri) * sizeof(vsf_dmatch));
+  if (n_tri > 0 && out->tri_X4) std::memcpy(out->tri_X4, c->h_X4, size_t(n_tri) * sizeof(float4));
+  commit_staging(c, frame_id, M);
+  return VSF_OK;
+}
+
+// ----------------------------------------------------------------- device-resident entry points
+
+extern "C" int vsf_window_match_device(vsf_ctx* c, const void* const* d_queries, const int* nq, int n_frames,
+                                       const void* d_train, int nt, double ratio) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (n_frames < 0 || n_frames > c->window || (n_frames > 0 && (!d_queries || !nq)) || nt < 0 || (nt > 0 && !d_train))
+    return fail(c, VSF_ERR_BAD_ARG, "bad device window arguments");
+  cudaSetDevice(c->device);
+  std::vector<ProblemSpec> specs;
+  for (int j = 0; j < n_frames; ++j)
+    specs.push_back(ProblemSpec{d_queries[j], nq[j], nullptr, d_train, nt, nullptr, j});
+  c->last_n_frames = n_frames;
+  return run_knn(c, specs, ratio);
+}
+
+extern "C" int vsf_fetch_window(vsf_ctx* c, int n_frames, int* counts, vsf_dmatch* out, int cap_per_frame) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (n_frames < 0 || n_frames > c->window || (n_frames > 0 && !counts)) return fail(c, VSF_ERR_BAD_ARG, "bad fetch arguments");
+  cudaSetDevice(c->device);
+  int rc = fetch_regions(c, n_frames, 0);
+  if (rc) return rc;
+  for (int j = 0; j < n_frames; ++j) {
+    counts[j] = c->h_counts[j];
+    if (out) {
+      if (counts[j] > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
+      if (counts[j]) std::memcpy(out + size_t(j) * cap_per_frame, c->h_matches + size_t(j) * c->rows_pad, size_t(counts[j]) * sizeof(vsf_dmatch));
+    }
+  }
+  return VSF_OK;
+}
+
+extern "C" int vsf_synth_sequence_device(vsf_ctx* c, void* d_out, int n, int first_pose, int n_poses, int stride,
+                                         uint64_t seed) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!d_out || n < 1 || n_poses < 0 || first_pose < 0 || stride < 0 || c->row_bytes != 32)
+    return fail(c, VSF_ERR_BAD_ARG, "bad synth arguments (generator produces 32-byte rows)");
+  cudaSetDevice(c->device);
+  VSF_CUDA(c, launch_synth(static_cast<uint32_t*>(d_out), n, first_pose, n_poses, stride, seed, c->stream));
+  return VSF_OK;
+}
+
+extern "C" int vsf_probe_pipe(vsf_ctx* c, int kind, int iters, double* ops_per_second) {
+  if (!c || !ops_per_second || iters < 1 || kind < 0 || kind > 6) return VSF_ERR_BAD_ARG;
+  cudaSetDevice(c->device);
+  const int blocks = c->sm_count * 2, threads = 1024;
+  VSF_CUDA(c, launch_probe(kind, c->d_sink, iters, blocks, threads, c->stream));  // warm-up
+  VSF_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  VSF_CUDA(c, launch_probe(kind, c->d_sink, iters, blocks, threads, c->stream));
+  VSF_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  VSF_CUDA(c, cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  VSF_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  const double ops = double(blocks) * threads * 8.0 * iters * probe_ops_per_step(kind);
+  *ops_per_second = ops / (double(ms) * 1e-3);
+  return VSF_OK;
+}

@@ -1,0 +1,156 @@
+// Shared device-side definitions for libvsf_cuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vsf.h"
+
+namespace vsf {
+
+// ---- packed (distance, trainIdx) keys -------------------------------------
+// key = distance << 22 | trainIdx.  Unsigned min over keys is the lexicographic
+// minimum of (distance, trainIdx): the lowest train index wins ties for both
+// neighbours, which is cv::BFMatcher's rule, and the reduction is independent
+// of the order in which train rows are visited (so the train dimension can be
+// split over warps and CTAs).  distance <= 512 (64-byte descriptors) needs 10
+// bits; 22 bits of index allow 4M train rows.
+constexpr int kIdxBits = 22;
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+constexpr uint32_t kKeySentinel = 0xFFFFFFFFu;
+constexpr int kMaxRows = 1 << kIdxBits;
+
+// ---- kernel 1 geometry -----------------------------------------------------
+constexpr int kConsumerWarps = 8;                 // train rows of a tile are dealt to these
+constexpr int kKnnThreads = (kConsumerWarps + 1) * 32;  // + 1 TMA producer warp
+constexpr int kStages = 4;                        // smem ring depth
+constexpr int kTileBytes = 8192;                  // per stage (256 rows of 32 B)
+constexpr int kMaxProblems = 40;                  // window (<= 38) + stereo pair
+
+// One query-frame x train-frame matching problem.  A launch processes a batch
+// of them (the whole sliding window, or stereo L->R / R->L) at once.
+struct KnnProblem {
+  const uint32_t* q;       // [nq][WORDS]
+  const uint32_t* t;       // [nt][WORDS]
+  const int* nq_dev;       // when non-null the row counts are read from the
+  const int* nt_dev;       //   device (compacted frames), nq/nt are upper bounds
+  vsf_dmatch* matches;     // compacted survivors of the ratio test, query order
+  int* match_count;
+  int nq, nt;
+  int row0;                // first row of this problem in knn_out / partial
+  int qb0;                 // first slot of this problem in the per-query-block counters
+};
+
+struct KnnBatch {
+  int num_problems;
+  int split;               // number of train-dimension splits (gridDim.z)
+  double ratio;            // nn_match_ratio, compared in double like the reference
+  uint4* knn_out;          // [rows] {idx0, idx1, d0, d1}
+  uint2* partial;          // [rows][split] partial top-2 keys (split > 1)
+  unsigned* qblock_arrivals;  // [qblocks]   self-resetting counters
+  unsigned* qblock_pass;      // [qblocks]   ratio survivors per query block
+  unsigned* problem_arrivals; // [problems]  self-resetting counters
+  KnnProblem p[kMaxProblems];
+};
+
+// ---- PTX helpers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  // make the initialised barriers visible to the async (TMA) proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier
+// (SASS: UBLKCP).  dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// top-2 insert of one key into (m1 <= m2)
+__device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t key) {
+  m2 = umin32(m2, umax32(m1, key));
+  m1 = umin32(m1, key);
+}
+// top-2 merge of two sorted pairs
+__device__ __forceinline__ void top2_merge(uint32_t& m1, uint32_t& m2, uint32_t b1, uint32_t b2) {
+  const uint32_t lo = umin32(m1, b1);
+  const uint32_t hi = umax32(m1, b1);
+  m2 = umin32(hi, umin32(m2, b2));
+  m1 = lo;
+}
+
+// 3-input bitwise primitives; the compiler maps each to one LOP3.LUT
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+  return (a & b) | (a & c) | (b & c);
+}
+
+// Hamming distance of two 256-bit blocks held as 8 words each.
+//   MODE 0: 8 XOR + 8 POPC (the naive count the roofline is quoted against)
+//   MODE 2: carry-save adders fold 8 words to 2 "ones" + 3 "twos": 5 POPC, 14 LOP3
+//   MODE 3: full Harley-Seal tree: 4 POPC, 20 LOP3
+template <int MODE>
+__device__ __forceinline__ uint32_t hamming256(const uint32_t* q, const uint32_t* t) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = q[i] ^ t[i];
+  if (MODE == 0) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d += __popc(x[i]);
+    return d;
+  } else {
+    const uint32_t sa = xor3(x[0], x[1], x[2]), ca = maj3(x[0], x[1], x[2]);
+    const uint32_t sb = xor3(x[3], x[4], x[5]), cb = maj3(x[3], x[4], x[5]);
+    const uint32_t sc = xor3(x[6], x[7], sa), cc = maj3(x[6], x[7], sa);
+    if (MODE == 2) {
+      const uint32_t ones = __popc(sb) + __popc(sc);
+      const uint32_t twos = __popc(ca) + __popc(cb) + __popc(cc);
+      return ones + 2u * twos;
+    } else {
+      const uint32_t ones = sb ^ sc, cd = sb & sc;
+      const uint32_t ts = xor3(ca, cb, cc), fa = maj3(ca, cb, cc);
+      const uint32_t twos = ts ^ cd, fb = ts & cd;
+      return __popc(ones) + 2u * __popc(twos) + 4u * (__popc(fa) + __popc(fb));
+    }
+  }
+}
+
+}  // namespace vsf
