@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--popc-mode", type=int, default=-1)
     ap.add_argument("--split", type=int, default=0)
     ap.add_argument("--qpt", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=-1)
     return ap.parse_args()
 
 
@@ -147,17 +148,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU legs
-def cpu_match_pair(past, cur, cv2_ref, restate, use_cv2):
+class CpuPair:
     """The reference's per-frame-pair CPU work: BFMatcher.knnMatch(k=2) + ratio
-    (Frontend::GetMatches) + sort + best_percent cut (GetFeatureMatches)."""
-    if use_cv2:
-        m = cv2_ref.get_matches(past, cur, RATIO)
-    else:
+    (Frontend::GetMatches, slam_frontend.cc:521-538) + std::sort + best_percent cut
+    (GetFeatureMatches, :289-291).  The C++ reference does the ratio/sort/cut glue
+    in microseconds; Python attribute access on 10^4 cv2.DMatch objects would add
+    milliseconds that the reference never pays, so the timed call is the bare
+    knnMatch plus libstdc++'s std::sort on the (precomputed) survivor distances —
+    i.e. the reference's real cost, nothing more."""
+
+    def __init__(self, past, cur, cv2_ref, restate, use_cv2):
         from oracle import native
-        m = native.get_matches(past, cur, RATIO)
-    order = restate.sort_order_stdsort(m)
-    keep = restate.num_good_matches(len(m), np.float32(BEST_PERCENT))
-    return m[order][:keep]
+        self.past, self.cur = np.ascontiguousarray(past), np.ascontiguousarray(cur)
+        self.cv2_ref, self.restate, self.use_cv2, self.native = cv2_ref, restate, use_cv2, native
+        self.survivors = native.get_matches(past, cur, RATIO)      # untimed, for the sort leg
+
+    def run(self):
+        if self.use_cv2:
+            raw = self.cv2_ref.knn_match_raw(self.past, self.cur)
+        else:
+            raw = self.native.knn2_hamming(self.past, self.cur)
+        order = self.restate.sort_order_stdsort(self.survivors)
+        keep = self.restate.num_good_matches(len(self.survivors), np.float32(BEST_PERCENT))
+        return raw, order[:keep]
 
 
 def cpu_setup():
@@ -179,14 +192,15 @@ def cpu_baseline(a, budget_s):
     cv2_ref, restate, use_cv2, cores, label = cpu_setup()
     n, stride = a.features, (a.stride or max(1, a.features // 10))
     frames = [synth.synth_pose(n, p, stride, SEED) for p in range(3)]
-    cpu_match_pair(frames[0], frames[1], cv2_ref, restate, use_cv2)      # warm-up
+    work = [CpuPair(frames[j], frames[j + 1], cv2_ref, restate, use_cv2) for j in range(2)]
+    work[0].run()                                                         # warm-up
     t0 = time.perf_counter()
     pairs = 0
     while True:
-        cpu_match_pair(frames[pairs % 2], frames[pairs % 2 + 1], cv2_ref, restate, use_cv2)
+        work[pairs % 2].run()
         pairs += 1
         el = time.perf_counter() - t0
-        if el >= budget_s or pairs >= 400:
+        if el >= budget_s or pairs >= 5000:
             break
     return {"value": pairs * n * n / el, "unit": UNIT, "cores": int(cores), "kind": "port",
             "frame_pairs_per_s": pairs / el,
@@ -205,18 +219,18 @@ def run_reference(a):
     pool = [synth.synth_pose(n, p, stride, SEED) for p in range(a.window + 1)]
     # a step = a bounded sample of one pose: ONE (past, current) frame pair of the
     # window (N x N comparisons).  Size the run to a few minutes at most.
+    work = [CpuPair(pool[j], pool[j + 1], cv2_ref, restate, use_cv2) for j in range(a.window)]
     for _ in range(max(1, min(a.warmup, 3))):
-        cpu_match_pair(pool[0], pool[1], cv2_ref, restate, use_cv2)
+        work[0].run()
     t0 = time.perf_counter()
-    cpu_match_pair(pool[0], pool[1], cv2_ref, restate, use_cv2)
+    work[0].run()
     per_pair = time.perf_counter() - t0
     steps = a.steps
     max_steps = max(1, int(150.0 / max(per_pair, 1e-6)))
     timed = min(steps, max_steps)
     t0 = time.perf_counter()
     for s in range(timed):
-        j = s % a.window
-        cpu_match_pair(pool[j], pool[j + 1], cv2_ref, restate, use_cv2)
+        work[s % a.window].run()
     el = time.perf_counter() - t0
     value = timed * n * n / el
     line = {
@@ -258,10 +272,11 @@ def run_b200(a):
 
     ctx = vsf.Context(device=local, max_features=n, desc_bytes=32, window=W)
     L = ctx._L
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: kernels, events and the clock are all on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    if a.popc_mode >= 0 or a.split or a.qpt:
-        ctx.set_tuning(max(a.popc_mode, 0), a.split, a.qpt)
+    ctx.set_tuning(a.popc_mode, a.split, a.qpt, a.variant)
 
     # ---- device-resident sequence: this rank's pose range, larger than L2 ----------------
     frame_bytes = n * 32

@@ -77,15 +77,22 @@ const char* vsf_last_error(const vsf_ctx* ctx);
 const char* vsf_version(void);
 
 /* Run the ctx's work on an existing CUDA stream (cudaStream_t passed as
- * void*; NULL restores the ctx's own stream).  Lets a caller time or overlap
- * the asynchronous *_device entry points with its own events. */
+ * void*).  NULL restores the ctx's own non-blocking stream — note that the
+ * legacy default stream has handle 0 and therefore cannot be selected; pass a
+ * created stream.  Lets a caller time or overlap the asynchronous *_device
+ * entry points with its own events. */
 int vsf_set_stream(vsf_ctx* ctx, void* cuda_stream);
 int vsf_synchronize(vsf_ctx* ctx);
 
-/* Kernel tuning knobs (0 = library default).  popc_mode: 0 = 8 POPC per
- * 256-bit comparison, 2/3 = carry-save variants with 5/4 POPC.  train_split:
- * force the number of train-dimension splits. */
-int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split, int queries_per_thread);
+/* Kernel tuning knobs; (-1, 0, 0, -1) restores the library defaults.
+ * popc_mode: 0 = 8 POPC per 256-bit comparison (the naive count the roofline is
+ * quoted against), 2 / 3 = carry-save adder trees with 5 / 4 POPC, -1 = default.
+ * train_split: number of train-dimension splits per problem, 0 = automatic.
+ * queries_per_thread: 1, 2 or 4, 0 = automatic.  variant: 0..3 kernel structure
+ * (producer warp / unroll, see csrc/knn2_kernel.cu), -1 = default.
+ * Every setting produces bit-identical results. */
+int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
+                   int queries_per_thread, int variant);
 
 /* ---------------------------------------------- a1: BFMatcher::knnMatch k=2 */
 

@@ -55,7 +55,7 @@ def main():
 
     # C3 shape, reduced: KITTI-size rig, noisy correspondences
     P1, P2 = synth.kitti_projections()
-    kl, dl, kr, dr, X, perm = synth.stereo_frame(240, seed=1)
+    kl, dl, kr, dr, X, perm = synth.stereo_frame(240, seed=1, bad_geometry=0.0)
     ok = perm >= 0
     x1 = np.stack([kl["x"][ok], kl["y"][ok]], 1)
     x2 = np.stack([kr["x"][perm[ok]], kr["y"][perm[ok]]], 1)

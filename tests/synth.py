@@ -77,11 +77,13 @@ def kitti_fundamental() -> np.ndarray:
 
 
 def stereo_frame(n: int, seed: int = 1, outliers: float = 0.1, noise_px: float = 0.5,
-                 width: int = 32, max_flips: int = 20, landmarks=None):
+                 width: int = 32, max_flips: int = 20, landmarks=None, bad_geometry: float = 0.05):
     """C3-style stereo pair: n 3-D points in front of the rig projected into both
     cameras with Gaussian pixel noise; right descriptors = left with up to
     max_flips flipped bits, right order shuffled; `outliers` of the right
-    features are unrelated (random descriptor, random pixel).
+    features are unrelated (random descriptor, random pixel) and `bad_geometry`
+    of them keep their descriptor but sit 30 px off the epipolar line (they pass
+    the ratio test and must be removed by the epipolar filter).
     Returns kp_left, desc_left, kp_right, desc_right, X (n,3) ground truth,
     perm (right index of left feature i, -1 for outliers)."""
     rng = np.random.default_rng(seed)
@@ -101,6 +103,9 @@ def stereo_frame(n: int, seed: int = 1, outliers: float = 0.1, noise_px: float =
     out_rows = rng.permutation(n)[:nout]
     dr[out_rows] = rng.integers(0, 256, (nout, width), dtype=np.uint8)
     xr[out_rows] = np.stack([rng.uniform(0, 1241, nout), rng.uniform(0, 376, nout)], 1)
+    rng2 = np.random.default_rng(seed + 12345)
+    bad_rows = rng2.permutation(n)[:int(n * bad_geometry)]
+    xr[bad_rows, 1] += (30.0 * rng2.choice([-1.0, 1.0], len(bad_rows))).astype(np.float32)
     order = rng.permutation(n)           # right feature j is left feature order[j]
     dr, xr = dr[order], xr[order]
     perm = np.empty(n, np.int64)

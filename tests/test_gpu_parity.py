@@ -40,17 +40,17 @@ def test_knn2_against_opencv_golden(name):
     np.testing.assert_array_equal(dist, g["dist"])
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("mode", [-1, 0, 2, 3])
 @pytest.mark.parametrize("R", [0, 1, 2, 4])
-@pytest.mark.parametrize("split", [0, 1, 5, 32])
-def test_knn2_c2_all_kernel_variants(vsf_ctx, mode, R, split):
+@pytest.mark.parametrize("split,variant", [(0, -1), (1, 0), (5, 1), (32, 2), (3, 3), (1, 1), (2, 2)])
+def test_knn2_c2_all_kernel_variants(vsf_ctx, mode, R, split, variant):
     Q, T = synth.descriptor_pair(2000, 2000, seed=0)
     ei, ed = native.knn2_hamming(Q, T)
-    vsf_ctx.set_tuning(mode, split, R)
+    vsf_ctx.set_tuning(mode, split, R, variant)
     try:
         idx, dist = vsf_ctx.knn2(Q, T)
     finally:
-        vsf_ctx.set_tuning(0, 0, 0)
+        vsf_ctx.set_tuning()
     np.testing.assert_array_equal(idx, ei)
     np.testing.assert_array_equal(dist, ed)
 
@@ -59,11 +59,11 @@ def test_knn2_c2_all_kernel_variants(vsf_ctx, mode, R, split):
 def test_knn2_ties_lowest_train_index(vsf_ctx, split):
     Q, T = synth.tie_pair(1500, 2300, seed=3)
     ei, ed = native.knn2_hamming(Q, T)
-    vsf_ctx.set_tuning(0, split, 0)
+    vsf_ctx.set_tuning(-1, split, 0, split % 4)
     try:
         idx, dist = vsf_ctx.knn2(Q, T)
     finally:
-        vsf_ctx.set_tuning(0, 0, 0)
+        vsf_ctx.set_tuning()
     np.testing.assert_array_equal(idx, ei)
     np.testing.assert_array_equal(dist, ed)
     assert (idx[:, 0] < idx[:, 1]).sum() > 100     # ties did occur
@@ -99,8 +99,8 @@ def test_knn2_strided_rows_and_64_byte_descriptors():
         idx, dist = ctx.knn2(Qs[:, :64], T)       # cv::Mat with step 80
         np.testing.assert_array_equal(idx, ei)
         np.testing.assert_array_equal(dist, ed)
-        for mode in (2, 3):
-            ctx.set_tuning(mode, 3, 1)
+        for mode, var in ((0, 1), (2, 2), (3, 3)):
+            ctx.set_tuning(mode, 3, 1, var)
             idx, dist = ctx.knn2(Q, T)
             np.testing.assert_array_equal(idx, ei)
             np.testing.assert_array_equal(dist, ed)
@@ -231,7 +231,7 @@ def test_stereo_filter_sequence_against_oracle():
             np.testing.assert_array_equal(got["kept_right"], sm["trainIdx"][keep])
             assert ctx.get_stereo_threshold().view(np.uint32) == np.float32(thresh_next).view(np.uint32)
             thresh = thresh_next
-        assert keep.sum() > 1000 and (~keep).sum() > 0
+        assert keep.sum() > 1000 and (~keep).sum() > 20
 
 
 def test_stereo_threshold_nan_when_no_matches():
@@ -263,7 +263,7 @@ def test_triangulate_against_opencv_golden(vsf_ctx, name):
 
 def test_triangulate_c3_size_against_oracle(vsf_ctx):
     P1, P2 = synth.kitti_projections()
-    kl, dl, kr, dr, X, perm = synth.stereo_frame(2000, seed=1)
+    kl, dl, kr, dr, X, perm = synth.stereo_frame(2000, seed=1, bad_geometry=0.0)
     ok = perm >= 0
     x1 = np.stack([kl["x"][ok], kl["y"][ok]], 1)
     x2 = np.stack([kr["x"][perm[ok]], kr["y"][perm[ok]]], 1)

@@ -110,7 +110,7 @@ def test_stdsort_order_is_a_sort_and_differs_only_in_ties():
 
 def test_epipolar_residual_zero_on_true_correspondences():
     P1, P2 = synth.kitti_projections()
-    kl, dl, kr, dr, X, perm = synth.stereo_frame(100, seed=2, noise_px=0.0, outliers=0.0)
+    kl, dl, kr, dr, X, perm = synth.stereo_frame(100, seed=2, noise_px=0.0, outliers=0.0, bad_geometry=0.0)
     F = synth.kitti_fundamental()
     xl = np.stack([kl["x"], kl["y"]], 1)
     xr = np.stack([kr["x"][perm], kr["y"][perm]], 1)

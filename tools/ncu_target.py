@@ -1,0 +1,27 @@
+"""Short target for ncu: a few launches of the window kernel on the C4 shape."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import vision_slam_frontend_b200 as vsf
+
+n = int(os.environ.get("N", 5000)); W = int(os.environ.get("W", 10))
+mode = int(os.environ.get("MODE", 0)); R = int(os.environ.get("QPT", 0)); split = int(os.environ.get("SPLIT", 0))
+launches = int(os.environ.get("LAUNCHES", 6))
+ctx = vsf.Context(device=0, max_features=n, desc_bytes=32, window=W)
+s = torch.cuda.Stream(); torch.cuda.set_stream(s); ctx.set_stream(s.cuda_stream)
+ctx.set_tuning(mode, split, R)
+seq = torch.empty((launches + W, n, 32), dtype=torch.uint8, device="cuda")
+ctx.synth_sequence_device(seq.data_ptr(), n, 0, launches + W, max(1, n // 10), 7)
+base, fb = seq.data_ptr(), n * 32
+for t in range(launches):
+    qp = (C.c_void_p * W)(*[base + (t + j) * fb for j in range(W)])
+    nn = (C.c_int * W)(*([n] * W))
+    assert ctx._L.vsf_window_match_device(ctx._h, qp, nn, W, C.c_void_p(base + (t + W) * fb), n, float(np.float32(0.6))) == 0
+torch.cuda.synchronize()
+print("done")

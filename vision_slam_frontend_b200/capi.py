@@ -65,7 +65,7 @@ def load_library():
         "vsf_version": ([], C.c_char_p),
         "vsf_set_stream": ([vp, vp], i),
         "vsf_synchronize": ([vp], i),
-        "vsf_set_tuning": ([vp, i, i, i], i),
+        "vsf_set_tuning": ([vp, i, i, i, i], i),
         "vsf_knn2": ([vp, vp, i, sz, vp, i, sz, vp, vp], i),
         "vsf_get_matches": ([vp, vp, i, sz, vp, i, sz, d, vp, i, C.POINTER(i)], i),
         "vsf_window_push": ([vp, u64, vp, i, sz], i),
@@ -166,8 +166,9 @@ class Context:
     def synchronize(self):
         self._check(self._L.vsf_synchronize(self._h))
 
-    def set_tuning(self, popc_mode=0, train_split=0, queries_per_thread=0):
-        self._check(self._L.vsf_set_tuning(self._h, popc_mode, train_split, queries_per_thread))
+    def set_tuning(self, popc_mode=-1, train_split=0, queries_per_thread=0, variant=-1):
+        self._check(self._L.vsf_set_tuning(self._h, popc_mode, train_split, queries_per_thread,
+                                           variant))
 
     # -- a1 / a2 -------------------------------------------------------------------
     def knn2(self, Q: np.ndarray, T: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

@@ -31,17 +31,34 @@ __device__ __forceinline__ uint32_t hamming_row(const uint32_t* q, const uint32_
   return d;
 }
 
-template <int WORDS, int R, int MODE>
-__global__ void __launch_bounds__(kKnnThreads)
+// Kernel variants (selected with vsf_set_tuning):
+//   0: dedicated TMA producer warp (9 warps), 4-stage ring, rows unrolled by 2
+//   1: no producer warp (8 warps; lane 0 of warp 0 issues the TMA refills one tile
+//      behind the consumers), 3-stage ring, rows unrolled by 2 -> more compute warps per SM
+//   2: as 1, rows unrolled by 4
+//   3: as 0, rows unrolled by 4
+template <int VAR>
+struct Variant {
+  static constexpr bool kProducerWarp = (VAR == 0 || VAR == 3);
+  static constexpr int kUnroll = (VAR == 2 || VAR == 3) ? 4 : 2;
+  static constexpr int kRing = kProducerWarp ? kStages : 3;
+  static constexpr int kThreads = (kConsumerWarps + (kProducerWarp ? 1 : 0)) * 32;
+};
+
+template <int WORDS, int R, int MODE, int VAR>
+__global__ void __launch_bounds__(Variant<VAR>::kThreads)
 knn2_kernel(const __grid_constant__ KnnBatch batch) {
+  using V = Variant<VAR>;
   constexpr int QB = 32 * R;
   constexpr int ROW_BYTES = WORDS * 4;
   constexpr int TILE_ROWS = kTileBytes / ROW_BYTES;
-  constexpr int SCAN_CHUNK = 1024;
+  constexpr int SCAN_CHUNK = 256;
+  constexpr int RING = V::kRing;
+  constexpr int NWARPS = V::kThreads / 32;
 
-  __shared__ __align__(128) uint8_t s_tile[kStages][kTileBytes];
-  __shared__ __align__(8) uint64_t s_full[kStages];
-  __shared__ __align__(8) uint64_t s_empty[kStages];
+  __shared__ __align__(128) uint8_t s_tile[RING][kTileBytes];
+  __shared__ __align__(8) uint64_t s_full[RING];
+  __shared__ __align__(8) uint64_t s_empty[RING];
   __shared__ uint32_t s_merge[kConsumerWarps][QB][2];
   __shared__ uint32_t s_off[SCAN_CHUNK];
   __shared__ int s_flag;
@@ -73,7 +90,7 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < RING; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], kConsumerWarps);
     }
@@ -85,23 +102,30 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
 #pragma unroll
   for (int r = 0; r < R; ++r) m1[r] = m2[r] = kKeySentinel;
 
-  if (warp == kConsumerWarps) {
+  const uint8_t* t_src = reinterpret_cast<const uint8_t*>(P.t) + size_t(t_begin) * ROW_BYTES;
+  auto issue_tile = [&](int k) {
+    const int s = k % RING;
+    const int rows = min(TILE_ROWS, t_end - t_begin - k * TILE_ROWS);
+    const uint32_t bytes = uint32_t(rows) * ROW_BYTES;
+    mbar_arrive_expect_tx(&s_full[s], bytes);
+    tma_load_1d(s_tile[s], t_src + size_t(k) * kTileBytes, bytes, &s_full[s]);
+  };
+
+  if (V::kProducerWarp && warp == kConsumerWarps) {
     // ---------------- TMA producer: one elected lane ----------------
     if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(P.t) + size_t(t_begin) * ROW_BYTES;
       for (int k = 0; k < ntiles; ++k) {
-        const int s = k % kStages;
-        const int u = k / kStages;
-        if (u > 0) mbar_wait(&s_empty[s], (u - 1) & 1);
-        const int rows = min(TILE_ROWS, t_end - t_begin - k * TILE_ROWS);
-        const uint32_t bytes = uint32_t(rows) * ROW_BYTES;
-        mbar_arrive_expect_tx(&s_full[s], bytes);
-        tma_load_1d(s_tile[s], src + size_t(k) * kTileBytes, bytes, &s_full[s]);
+        const int u = k / RING;
+        if (u > 0) mbar_wait(&s_empty[k % RING], (u - 1) & 1);
+        issue_tile(k);
       }
     }
     __syncwarp();
   } else {
     // ---------------- consumers ----------------
+    if (!V::kProducerWarp && tid == 0) {
+      for (int k = 0; k < min(ntiles, RING - 1); ++k) issue_tile(k);   // prologue: fill the ring
+    }
     uint32_t qreg[R][WORDS];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -118,13 +142,23 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
       }
     }
     for (int k = 0; k < ntiles; ++k) {
-      const int s = k % kStages;
-      const int u = k / kStages;
+      const int s = k % RING;
+      const int u = k / RING;
+      if (!V::kProducerWarp && tid == 0) {
+        // refill one tile behind: tile k+RING-1 goes into the slot tile k-1 used, which
+        // every warp released when it finished tile k-1
+        const int kn = k + RING - 1;
+        if (kn < ntiles) {
+          if (k > 0) mbar_wait(&s_empty[(k - 1) % RING], ((k - 1) / RING) & 1);
+          issue_tile(kn);
+        }
+      }
+      if (!V::kProducerWarp) __syncwarp();
       mbar_wait(&s_full[s], u & 1);
       const int rows = min(TILE_ROWS, t_end - t_begin - k * TILE_ROWS);
       const uint32_t row_base = uint32_t(t_begin + k * TILE_ROWS);
       const uint4* tile = reinterpret_cast<const uint4*>(s_tile[s]);
-#pragma unroll 2
+#pragma unroll (V::kUnroll)
       for (int row = warp; row < rows; row += kConsumerWarps) {
         uint32_t tw[WORDS];
 #pragma unroll
@@ -234,7 +268,7 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
       if (lane == 0) s_flag = int(run);
     }
     __syncthreads();
-    for (int b = warp; b < cn; b += kKnnThreads / 32) {
+    for (int b = warp; b < cn; b += NWARPS) {
       uint32_t off = s_off[b];
 #pragma unroll
       for (int g = 0; g < R; ++g) {
@@ -266,35 +300,46 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int WORDS, int R, int MODE>
+template <int WORDS, int R, int MODE, int VAR>
 static cudaError_t launch_one(const KnnBatch& batch, int max_qblocks, cudaStream_t stream) {
   dim3 grid(max_qblocks, batch.num_problems, batch.split);
-  knn2_kernel<WORDS, R, MODE><<<grid, kKnnThreads, 0, stream>>>(batch);
+  knn2_kernel<WORDS, R, MODE, VAR><<<grid, Variant<VAR>::kThreads, 0, stream>>>(batch);
   return cudaGetLastError();
 }
 
+template <int WORDS, int R, int MODE>
+static cudaError_t launch_var(const KnnBatch& b, int var, int mq, cudaStream_t s) {
+  switch (var) {
+    case 0: return launch_one<WORDS, R, MODE, 0>(b, mq, s);
+    case 1: return launch_one<WORDS, R, MODE, 1>(b, mq, s);
+    case 2: return launch_one<WORDS, R, MODE, 2>(b, mq, s);
+    case 3: return launch_one<WORDS, R, MODE, 3>(b, mq, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 template <int WORDS, int R>
-static cudaError_t launch_mode(const KnnBatch& b, int mode, int mq, cudaStream_t s) {
+static cudaError_t launch_mode(const KnnBatch& b, int mode, int var, int mq, cudaStream_t s) {
   switch (mode) {
-    case 0: return launch_one<WORDS, R, 0>(b, mq, s);
-    case 2: return launch_one<WORDS, R, 2>(b, mq, s);
-    case 3: return launch_one<WORDS, R, 3>(b, mq, s);
+    case 0: return launch_var<WORDS, R, 0>(b, var, mq, s);
+    case 2: return launch_var<WORDS, R, 2>(b, var, mq, s);
+    case 3: return launch_var<WORDS, R, 3>(b, var, mq, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
 // words: 8 or 16; R: queries per thread (1, 2 or 4; 4 only for 8 words).
 // max_qblocks: ceil(max nq / (32*R)) over the batch's problems.
-cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int max_qblocks,
-                        cudaStream_t stream) {
+cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int variant,
+                        int max_qblocks, cudaStream_t stream) {
   if (batch.num_problems <= 0 || max_qblocks <= 0) return cudaSuccess;
   if (words == 8) {
-    if (R == 1) return launch_mode<8, 1>(batch, mode, max_qblocks, stream);
-    if (R == 2) return launch_mode<8, 2>(batch, mode, max_qblocks, stream);
-    if (R == 4) return launch_mode<8, 4>(batch, mode, max_qblocks, stream);
+    if (R == 1) return launch_mode<8, 1>(batch, mode, variant, max_qblocks, stream);
+    if (R == 2) return launch_mode<8, 2>(batch, mode, variant, max_qblocks, stream);
+    if (R == 4) return launch_mode<8, 4>(batch, mode, variant, max_qblocks, stream);
   } else if (words == 16) {
-    if (R == 1) return launch_mode<16, 1>(batch, mode, max_qblocks, stream);
-    if (R == 2) return launch_mode<16, 2>(batch, mode, max_qblocks, stream);
+    if (R == 1) return launch_mode<16, 1>(batch, mode, variant, max_qblocks, stream);
+    if (R == 2) return launch_mode<16, 2>(batch, mode, variant, max_qblocks, stream);
   }
   return cudaErrorInvalidValue;
 }

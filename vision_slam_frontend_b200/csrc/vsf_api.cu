@@ -12,8 +12,8 @@
 #include "vsf_device.cuh"
 
 namespace vsf {
-cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int max_qblocks,
-                        cudaStream_t stream);
+cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int variant,
+                        int max_qblocks, cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
                          uint64_t seed, cudaStream_t stream);
 int probe_ops_per_step(int kind);
@@ -51,7 +51,7 @@ struct vsf_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
-  int popc_mode = 0, force_split = 0, force_R = 0;
+  int popc_mode = -1, force_split = 0, force_R = 0, variant = -1;   // -1 / 0 = library default
 
   int rows_pad = 0;    // max_features rounded up to 128
   int regions = 0;     // window + 2
@@ -196,35 +196,29 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       VSF_CUDA(c, cudaMemsetAsync(c->d_match_count + specs[i].region, 0, sizeof(int), c->stream));
     return VSF_OK;
   }
-  // queries per thread: the largest R that still gives every SM two CTAs
-  int R = c->force_R;
-  if (R == 0) {
-    R = 1;
-    const int cand[3] = {4, 2, 1};
-    for (int k = 0; k < 3; ++k) {
-      if (cand[k] == 4 && c->words != 8) continue;
-      long long qblocks = 0;
-      for (const ProblemSpec& s : specs) qblocks += (s.nq + 32 * cand[k] - 1) / (32 * cand[k]);
-      if (qblocks >= 2LL * c->sm_count) {
-        R = cand[k];
-        break;
-      }
-    }
-  }
-  if (c->words == 16 && R > 2) R = 2;
+  // Defaults from the round-1 sweep on B200 (profiles/): one query per thread keeps
+  // 40 registers/thread and the most resident warps, which is what the carry-save
+  // variant (5 POPC + 14 LOP3 per 256-bit comparison) needs to hide its longer
+  // dependency chains; it beats R = 2, 4 at every size measured.
+  const int R = c->force_R ? ((c->words == 16 && c->force_R > 2) ? 2 : c->force_R) : 1;
+  const int mode = c->popc_mode >= 0 ? c->popc_mode : 2;
+  const int variant = c->variant >= 0 ? c->variant : 3;
   long long qblocks = 0;
   for (const ProblemSpec& s : specs) qblocks += (s.nq + 32 * R - 1) / (32 * R);
-  // train splits: aim for ~3 CTAs per SM, keep >= 64 train rows per split
+  // Train splits: the work of one CTA is 32*R queries x (nt / S) train rows.  Aim for
+  // at least ~8 waves of CTAs (5 resident per SM) so the tail of the launch is short,
+  // but keep at least one full 256-row tile per split.
   int S = c->force_split;
   if (S == 0) {
-    S = int((3LL * c->sm_count + qblocks - 1) / std::max(1LL, qblocks));
-    S = std::min(S, std::max(1, max_nt / 64));
+    const long long target = 8LL * 5 * c->sm_count;
+    S = int((target + qblocks - 1) / std::max(1LL, qblocks));
+    S = std::min(S, std::max(1, max_nt / 256));
   }
   S = std::max(1, std::min(S, 32));
   while (S > 1 && size_t(row0) * S > c->partial_cap) --S;
   b.split = S;
   const int max_qblocks = (max_nq + 32 * R - 1) / (32 * R);
-  VSF_CUDA(c, launch_knn2(b, c->words, R, c->popc_mode, max_qblocks, c->stream));
+  VSF_CUDA(c, launch_knn2(b, c->words, R, mode, variant, max_qblocks, c->stream));
   return VSF_OK;
 }
 
@@ -384,16 +378,20 @@ extern "C" int vsf_synchronize(vsf_ctx* c) {
   return VSF_OK;
 }
 
-extern "C" int vsf_set_tuning(vsf_ctx* c, int popc_mode, int train_split, int queries_per_thread) {
+extern "C" int vsf_set_tuning(vsf_ctx* c, int popc_mode, int train_split, int queries_per_thread,
+                              int variant) {
   if (!c) return VSF_ERR_BAD_ARG;
-  if (!(popc_mode == 0 || popc_mode == 2 || popc_mode == 3)) return fail(c, VSF_ERR_BAD_ARG, "popc_mode must be 0, 2 or 3");
+  if (!(popc_mode == -1 || popc_mode == 0 || popc_mode == 2 || popc_mode == 3))
+    return fail(c, VSF_ERR_BAD_ARG, "popc_mode must be -1, 0, 2 or 3");
   if (train_split < 0 || train_split > 32) return fail(c, VSF_ERR_BAD_ARG, "train_split must be 0..32");
   if (!(queries_per_thread == 0 || queries_per_thread == 1 || queries_per_thread == 2 ||
         queries_per_thread == 4))
     return fail(c, VSF_ERR_BAD_ARG, "queries_per_thread must be 0, 1, 2 or 4");
+  if (variant < -1 || variant > 3) return fail(c, VSF_ERR_BAD_ARG, "variant must be -1..3");
   c->popc_mode = popc_mode;
   c->force_split = train_split;
   c->force_R = queries_per_thread;
+  c->variant = variant;
   return VSF_OK;
 }
 
