@@ -263,6 +263,7 @@ def run_b200(a):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("VSF_NCCL_DEBUG", "WARN")   # keep stdout = one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, W = a.features, a.window

@@ -19,7 +19,7 @@ FRONTEND_LIB = os.path.join(PKG, "libvsf_frontend.so")
 CUDA_SOURCES = ["knn2_kernel.cu", "stereo_kernels.cu", "sort_kernel.cu",
                 "aux_kernels.cu", "vsf_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-              "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp", "--use_fast_math=false"]
 
 
 def _nvcc() -> str:
@@ -60,7 +60,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
             rebuilt = True
         objs.append(o)
     if rebuilt or not os.path.exists(LIB):
-        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB + ".tmp"] + objs + ["-cudart", "static"]
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB + ".tmp"] + objs + ["-cudart", "static", "-Xcompiler", "-fopenmp"]
         subprocess.check_call(cmd)
         os.replace(LIB + ".tmp", LIB)
     return LIB

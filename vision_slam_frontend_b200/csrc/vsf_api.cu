@@ -6,6 +6,7 @@
 #include <cstring>
 #include <deque>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "stereo_args.cuh"
@@ -48,6 +49,7 @@ struct ProblemSpec {
 struct vsf_ctx {
   int device = 0, max_features = 0, desc_bytes = 0, row_bytes = 0, words = 0, window = 0;
   int sm_count = 0;
+  int host_threads = 1;   // for the host-side std::sort of sort_mode 1
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -293,6 +295,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   c->rows_pad = round_up(max_features, 128);
   c->regions = window + 2;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  c->host_threads = int(std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return VSF_ERR_CUDA;
@@ -589,18 +592,23 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
     }
     return VSF_OK;
   }
-  // sort_mode 1: the reference's own host sequence (src/slam_frontend.cc:289-296)
+  // sort_mode 1: the reference's own host sequence (src/slam_frontend.cc:289-296), one
+  // frame pair per host thread (each list is sorted by the same single-threaded
+  // std::sort the reference runs, so the order inside every list is unchanged).
   if ((rc = fetch_regions(c, nf, 0))) return rc;
   for (int j = 0; j < nf; ++j) {
-    vsf_dmatch* m = c->h_matches + size_t(j) * c->rows_pad;
-    const int cnt = c->h_counts[j];
-    std::sort(m, m + cnt, ByDistance());
-    const int good = int(float(size_t(cnt)) * best_percent);
+    const int good = int(float(size_t(c->h_counts[j])) * best_percent);
     if (good > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
     counts[j] = good;
     if (frame_ids) frame_ids[j] = c->slot_frame[c->live[j]];
+  }
+  const int nthreads = std::max(1, std::min(nf, c->host_threads));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (int j = 0; j < nf; ++j) {
+    vsf_dmatch* m = c->h_matches + size_t(j) * c->rows_pad;
+    std::sort(m, m + c->h_counts[j], ByDistance());
     vsf_feature_match* o = out + size_t(j) * cap_per_frame;
-    for (int i = 0; i < good; ++i) {
+    for (int i = 0; i < counts[j]; ++i) {
       o[i].feature_idx_initial = uint64_t(m[i].queryIdx);
       o[i].feature_idx_current = uint64_t(m[i].trainIdx);
     }
