@@ -94,6 +94,17 @@ int vsf_synchronize(vsf_ctx* ctx);
 int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
                    int queries_per_thread, int variant);
 
+/* Which hardware pipe computes the distance matrix of the kNN kernel.
+ * 0 = automatic (tensor cores for batches large enough to fill the GPU, POPC pipe
+ * otherwise), 1 = POPC pipe (XOR + POPC, csrc/knn2_kernel.cu), 2 = tensor cores,
+ * int8 operands (tcgen05.mma kind::i8 over +-1 expanded descriptor bits,
+ * csrc/knn2_tc_kernel.cu), 3 = tensor cores, e4m3 operands (kind::f8f6f4).
+ * The tensor-core engines need desc_bytes <= 32.  Every engine produces
+ * bit-identical results.  flags: bring-up knobs, pass 0. */
+int vsf_set_engine(vsf_ctx* ctx, int engine, int flags);
+/* Engine (1..3) used by the most recent kNN launch of this ctx. */
+int vsf_last_engine(const vsf_ctx* ctx);
+
 /* ---------------------------------------------- a1: BFMatcher::knnMatch k=2 */
 
 /* Replaces `matcher_->knnMatch(query.descriptors_, train.descriptors_,

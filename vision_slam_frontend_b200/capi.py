@@ -66,6 +66,8 @@ def load_library():
         "vsf_set_stream": ([vp, vp], i),
         "vsf_synchronize": ([vp], i),
         "vsf_set_tuning": ([vp, i, i, i, i], i),
+        "vsf_set_engine": ([vp, i, i], i),
+        "vsf_last_engine": ([vp], i),
         "vsf_knn2": ([vp, vp, i, sz, vp, i, sz, vp, vp], i),
         "vsf_get_matches": ([vp, vp, i, sz, vp, i, sz, d, vp, i, C.POINTER(i)], i),
         "vsf_window_push": ([vp, u64, vp, i, sz], i),
@@ -98,7 +100,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "vsf_create", "vsf_destroy", "vsf_last_error", "vsf_version", "vsf_set_stream",
-    "vsf_synchronize", "vsf_set_tuning", "vsf_knn2", "vsf_get_matches", "vsf_window_push",
+    "vsf_synchronize", "vsf_set_tuning", "vsf_set_engine", "vsf_last_engine", "vsf_knn2", "vsf_get_matches", "vsf_window_push",
     "vsf_window_commit", "vsf_window_clear", "vsf_window_size", "vsf_window_match",
     "vsf_window_feature_matches", "vsf_stereo_filter", "vsf_set_stereo_threshold",
     "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_observe_features",
@@ -169,6 +171,14 @@ class Context:
     def set_tuning(self, popc_mode=-1, train_split=0, queries_per_thread=0, variant=-1):
         self._check(self._L.vsf_set_tuning(self._h, popc_mode, train_split, queries_per_thread,
                                            variant))
+
+    def set_engine(self, engine: int = 0, flags: int = 0):
+        """0 auto, 1 POPC pipe, 2 tensor cores (int8), 3 tensor cores (e4m3)."""
+        self._check(self._L.vsf_set_engine(self._h, engine, flags))
+
+    @property
+    def last_engine(self) -> int:
+        return self._L.vsf_last_engine(self._h)
 
     # -- a1 / a2 -------------------------------------------------------------------
     def knn2(self, Q: np.ndarray, T: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

@@ -20,6 +20,7 @@
 //   Warps are merged through shared memory, train splits through global memory
 //   (last-arriver pattern), and the last CTA of a problem compacts the ratio
 //   survivors in ascending query order.
+#include "knn2_tail.cuh"
 #include "vsf_device.cuh"
 
 namespace vsf {
@@ -52,16 +53,13 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
   constexpr int QB = 32 * R;
   constexpr int ROW_BYTES = WORDS * 4;
   constexpr int TILE_ROWS = kTileBytes / ROW_BYTES;
-  constexpr int SCAN_CHUNK = 256;
   constexpr int RING = V::kRing;
-  constexpr int NWARPS = V::kThreads / 32;
 
   __shared__ __align__(128) uint8_t s_tile[RING][kTileBytes];
   __shared__ __align__(8) uint64_t s_full[RING];
   __shared__ __align__(8) uint64_t s_empty[RING];
   __shared__ uint32_t s_merge[kConsumerWarps][QB][2];
-  __shared__ uint32_t s_off[SCAN_CHUNK];
-  __shared__ int s_flag;
+  __shared__ TailSmem s_tail;
 
   const KnnProblem& P = batch.p[blockIdx.y];
   const int tid = threadIdx.x;
@@ -207,10 +205,10 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
       const unsigned prev = atomicAdd(&batch.qblock_arrivals[P.qb0 + qb], 1u);
       const int last = (prev == unsigned(S - 1));
       if (last) batch.qblock_arrivals[P.qb0 + qb] = 0u;  // self-reset for the next launch
-      s_flag = last;
+      s_tail.flag = last;
     }
     __syncthreads();
-    if (!s_flag) return;
+    if (!s_tail.flag) return;
     __threadfence();
     if (tid < QB) {
       k1 = k2 = kKeySentinel;
@@ -221,82 +219,8 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
     }
   }
 
-  // ---------------- finalize: unpack, ratio test ----------------
-  bool pass = false;
-  if (tid < QB && q0 + tid < nq) {
-    const int i0 = (k1 == kKeySentinel) ? -1 : int(k1 & kIdxMask);
-    const int i1 = (k2 == kKeySentinel) ? -1 : int(k2 & kIdxMask);
-    const int d0 = (k1 == kKeySentinel) ? -1 : int(k1 >> kIdxBits);
-    const int d1 = (k2 == kKeySentinel) ? -1 : int(k2 >> kIdxBits);
-    batch.knn_out[row] = make_uint4(uint32_t(i0), uint32_t(i1), uint32_t(d0), uint32_t(d1));
-    // `dist1 < nn_match_ratio * dist2` in double (src/slam_frontend.cc:533);
-    // fewer than 2 train rows: no match passes.
-    pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
-    __threadfence();
-  }
-  const int npass = __syncthreads_count(pass);
-  if (tid == 0) {
-    batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
-    __threadfence();
-    const unsigned prev = atomicAdd(&batch.problem_arrivals[blockIdx.y], 1u);
-    const int last = (prev == unsigned(nqb - 1));
-    if (last) batch.problem_arrivals[blockIdx.y] = 0u;
-    s_flag = last;
-  }
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-
-  // ---------------- tail: the problem's last CTA compacts survivors in query order -------------
-  uint32_t base = 0;
-  for (int c0 = 0; c0 < nqb; c0 += SCAN_CHUNK) {
-    const int cn = min(SCAN_CHUNK, nqb - c0);
-    if (warp == 0) {
-      // exclusive scan of the per-query-block survivor counts of this chunk
-      uint32_t run = base;
-      for (int i = lane; i < ((cn + 31) & ~31); i += 32) {
-        const uint32_t c = (i < cn) ? __ldcg(&batch.qblock_pass[P.qb0 + c0 + i]) : 0u;
-        uint32_t incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += n;
-        }
-        if (i < cn) s_off[i] = run + incl - c;
-        run += __shfl_sync(0xffffffffu, incl, 31);
-      }
-      if (lane == 0) s_flag = int(run);
-    }
-    __syncthreads();
-    for (int b = warp; b < cn; b += NWARPS) {
-      uint32_t off = s_off[b];
-#pragma unroll
-      for (int g = 0; g < R; ++g) {
-        const int q = (c0 + b) * QB + g * 32 + lane;
-        bool ok = false;
-        uint4 rec = make_uint4(0, 0, 0, 0);
-        if (q < nq) {
-          rec = __ldcg(&batch.knn_out[P.row0 + q]);
-          ok = (int(rec.y) >= 0) && (double(int(rec.z)) < batch.ratio * double(int(rec.w)));
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-          const uint32_t dst = off + __popc(bal & ((1u << lane) - 1u));
-          int4 m;
-          m.x = q;            // queryIdx
-          m.y = int(rec.x);   // trainIdx
-          m.z = 0;            // imgIdx
-          m.w = __float_as_int(float(int(rec.z)));  // distance
-          reinterpret_cast<int4*>(P.matches)[dst] = m;
-        }
-        off += __popc(bal);
-      }
-    }
-    __syncthreads();
-    base = uint32_t(s_flag);
-    __syncthreads();
-  }
-  if (tid == 0) *P.match_count = int(base);
+  // ---------------- finalize: unpack, ratio test, ordered compaction ----------------
+  finalize_and_compact<QB, V::kThreads>(batch, P, blockIdx.y, qb, nqb, nq, k1, k2, s_tail);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,112 @@
+// Inline-PTX wrappers for the Blackwell tensor-core path (tcgen05 / TMEM), sm_100a only.
+// Descriptor bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor"
+// tables (the same fields CUTLASS names in cute/arch/mma_sm100_desc.hpp).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsf {
+namespace tc {
+
+// ---- shared-memory matrix descriptor, K-major, no swizzle ----------------------------------
+// Canonical layout (16-byte units): ((8 rows, n groups), 2 K-chunks) : ((1, SBO), LBO)
+//   a "core matrix" is 8 rows x 16 bytes stored as 128 contiguous bytes;
+//   SBO = byte distance between consecutive 8-row groups (M/N direction),
+//   LBO = byte distance between the two 16-byte K-chunks one MMA (K = 32 bytes) consumes.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFFu);        // start address        bits [0,14)
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset  bits [16,30)
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset   bits [32,46)
+  d |= uint64_t(1) << 46;                           // descriptor version (Blackwell)
+  // base offset 0, lbo mode 0, layout type SWIZZLE_NONE (0) in bits [61,64)
+  return d;
+}
+
+// ---- instruction descriptor (dense, K-major A and B) ------------------------------------------
+//   c_format [4,6): 1 = F32, 2 = S32;  a_format [7,10), b_format [10,13):
+//   kind::f8f6f4: 0 = E4M3;  kind::i8: 0 = U8, 1 = S8;  n_dim [17,23) = N>>3;  m_dim [24,29) = M>>4
+__host__ __device__ constexpr uint32_t instr_desc(bool int8, int M, int N) {
+  return (uint32_t(int8 ? 2 : 1) << 4) | (uint32_t(int8 ? 1 : 0) << 7) | (uint32_t(int8 ? 1 : 0) << 10) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+template <bool I8>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if (I8) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// mbarrier arrive once every tcgen05 op issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
+               : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- TMEM allocation (one full warp executes these) -------------------------------------------
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_result))),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem_addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "n"(COLS) : "memory");
+}
+
+// ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns ------------------
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace tc
+}  // namespace vsf

@@ -15,6 +15,10 @@
 namespace vsf {
 cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int variant,
                         int max_qblocks, cudaStream_t stream);
+cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
+                                cudaStream_t stream);
+cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq,
+                           cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
                          uint64_t seed, cudaStream_t stream);
 int probe_ops_per_step(int kind);
@@ -54,6 +58,11 @@ struct vsf_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int popc_mode = -1, force_split = 0, force_R = 0, variant = -1;   // -1 / 0 = library default
+  int engine = 0;         // 0 auto, 1 POPC pipe, 2 tensor cores int8, 3 tensor cores e4m3
+  int engine_flags = 0;   // bit 0: exchange LBO/SBO (bring-up)
+  int last_engine = 0;    // engine the last kNN launch used
+  double tc_auto_min_cmp = 1e18;  // automatic mode: tensor cores from this many comparisons per batch
+  uint8_t* d_train_exp[kTcMaxTrains] = {nullptr, nullptr};  // +-1 expanded train images
 
   int rows_pad = 0;    // max_features rounded up to 128
   int regions = 0;     // window + 2
@@ -198,6 +207,75 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       VSF_CUDA(c, cudaMemsetAsync(c->d_match_count + specs[i].region, 0, sizeof(int), c->stream));
     return VSF_OK;
   }
+  // ---- engine choice.  The tensor-core engine needs 32-byte rows and at most kTcMaxTrains
+  // distinct train frames in the batch; automatic mode uses it once the batch is large enough
+  // to fill the machine (small batches are launch-bound and the POPC kernel has less fixed cost).
+  int engine = c->engine;
+  int train_of[kMaxProblems];
+  int n_trains = 0;
+  const ProblemSpec* train_spec[kTcMaxTrains];
+  bool tc_ok = (c->words == 8) && max_nt >= 1;
+  if (tc_ok) {
+    for (int i = 0; i < b.num_problems && tc_ok; ++i) {
+      int k = 0;
+      for (; k < n_trains; ++k)
+        if (train_spec[k]->t == specs[i].t && train_spec[k]->nt == specs[i].nt && train_spec[k]->nt_dev == specs[i].nt_dev) break;
+      if (k == n_trains) {
+        if (n_trains == kTcMaxTrains) { tc_ok = false; break; }
+        train_spec[n_trains++] = &specs[i];
+      }
+      train_of[i] = k;
+    }
+  }
+  if (engine == 0) engine = (tc_ok && double(total_q) * double(max_nt) >= c->tc_auto_min_cmp) ? 2 : 1;
+  if (engine >= 2 && !tc_ok) engine = 1;
+  c->last_engine = engine;
+
+  if (engine >= 2) {
+    const int int8 = engine == 2;
+    for (int k = 0; k < n_trains; ++k)
+      VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
+                                      c->d_train_exp[k], int8, c->stream));
+    TcBatch tb;
+    std::memset(&tb, 0, sizeof(tb));
+    long long qblocks = 0;
+    for (const ProblemSpec& s : specs) qblocks += (s.nq + kTcQ - 1) / kTcQ;
+    const int tiles = (max_nt + kTcTileRows - 1) / kTcTileRows;
+    // Train splits: maximise (machine fill of the last wave) x (tiles per unit vs ~1.5 tiles of
+    // fixed cost per unit: query expansion + pipeline fill/drain).
+    int S = c->force_split;
+    if (S == 0) {
+      double best = -1.0;
+      for (int cand = 1; cand <= std::min(tiles, 32); ++cand) {
+        const int tps = (tiles + cand - 1) / cand;
+        const long long units = qblocks * ((tiles + tps - 1) / tps);
+        const long long waves = (units + c->sm_count - 1) / c->sm_count;
+        const double eff = double(units) / double(waves * c->sm_count) * double(tps) / (double(tps) + 1.5);
+        if (eff > best + 1e-9) { best = eff; S = cand; }
+      }
+    }
+    S = std::max(1, std::min(S, std::min(tiles, 32)));
+    while (S > 1 && size_t(row0) * S > c->partial_cap) --S;
+    const int tps = (tiles + S - 1) / S;
+    S = (tiles + tps - 1) / tps;   // drop splits that would be empty
+    tb.split = S;
+    tb.rows_per_split = tps * kTcTileRows;
+    tb.swap_lbo_sbo = c->engine_flags & 1;
+    int units = 0;
+    for (int i = 0; i < b.num_problems; ++i) {
+      tb.t_exp[i] = c->d_train_exp[train_of[i]];
+      tb.unit_begin[i] = units;
+      units += ((specs[i].nq + kTcQ - 1) / kTcQ) * S;
+    }
+    tb.unit_begin[b.num_problems] = units;
+    tb.total_units = units;
+    b.split = S;
+    const int grid = std::max(1, std::min(units, c->sm_count));
+    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, grid, max_nq, c->stream));
+    return VSF_OK;
+  }
+
+  // ---- POPC engine
   // Defaults from the round-1 sweep on B200 (profiles/): one query per thread keeps
   // 40 registers/thread and the most resident warps, which is what the carry-save
   // variant (5 POPC + 14 LOP3 per 256-bit comparison) needs to hide its longer
@@ -238,7 +316,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
                  c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
                  c->d_chunk_keep, c->d_kept_left, c->d_kept_right, c->d_n_kept, c->d_thresh, c->d_X4,
-                 c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count};
+                 c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
   void* host[] = {c->h_desc[0], c->h_desc[1], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches,
@@ -338,6 +416,9 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC(c, c->d_sink, 64);
   VSF_ALLOC(c, c->d_fm, size_t(window) * N * sizeof(vsf_feature_match));
   VSF_ALLOC(c, c->d_fm_count, kMaxProblems * sizeof(int));
+  if (c->words == 8)
+    for (int k = 0; k < kTcMaxTrains; ++k)
+      VSF_ALLOC(c, c->d_train_exp[k], size_t(round_up(max_features, kTcTileRows)) * kTcRowBytes);
   {
     const float init[2] = {10000.0f, 10000.0f};  // stereo_ambig_constraint (src/slam_frontend.cc:353)
     cudaMemcpy(c->d_thresh, init, sizeof(init), cudaMemcpyHostToDevice);
@@ -397,6 +478,17 @@ extern "C" int vsf_set_tuning(vsf_ctx* c, int popc_mode, int train_split, int qu
   c->variant = variant;
   return VSF_OK;
 }
+
+extern "C" int vsf_set_engine(vsf_ctx* c, int engine, int flags) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (engine < 0 || engine > 3) return fail(c, VSF_ERR_BAD_ARG, "engine must be 0 (auto), 1 (POPC), 2 (tensor int8) or 3 (tensor e4m3)");
+  if (engine >= 2 && c->words != 8) return fail(c, VSF_ERR_BAD_ARG, "the tensor-core engine needs descriptors of at most 32 bytes");
+  c->engine = engine;
+  c->engine_flags = flags;
+  return VSF_OK;
+}
+
+extern "C" int vsf_last_engine(const vsf_ctx* c) { return c ? c->last_engine : 0; }
 
 extern "C" int vsf_device_sm_count(const vsf_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" int vsf_device_row_bytes(const vsf_ctx* c) { return c ? c->row_bytes : 0; }

@@ -53,6 +53,25 @@ struct KnnBatch {
   KnnProblem p[kMaxProblems];
 };
 
+// ---- tensor-core engine (knn2_tc_kernel.cu) -------------------------------------------------
+constexpr int kTcQ = 256;            // queries per work unit (two M=128 UMMA tiles)
+constexpr int kTcTileRows = 256;     // train rows per staged tile (N of one UMMA)
+constexpr int kTcBucket = 32;        // train rows per selection bucket (one tcgen05.ld.x32)
+constexpr int kTcStages = 2;         // train tiles in flight in shared memory
+constexpr int kTcRowBytes = 256;     // one 256-bit descriptor expanded to +-1 bytes
+constexpr int kTcABytes = kTcQ * kTcRowBytes;
+constexpr int kTcBBytes = kTcTileRows * kTcRowBytes;
+constexpr int kTcMaxTrains = 2;      // distinct train frames per batch that can be expanded
+
+struct TcBatch {
+  const uint8_t* t_exp[kMaxProblems];  // expanded train image of every problem
+  int unit_begin[kMaxProblems + 1];    // prefix sum of work units (query blocks x splits)
+  int split;                           // train splits per problem
+  int rows_per_split;                  // multiple of kTcTileRows
+  int total_units;
+  int swap_lbo_sbo;                    // bring-up knob: exchange the two descriptor strides
+};
+
 // ---- PTX helpers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
