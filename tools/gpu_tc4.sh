@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for e in 2 3; do timeout 300 python tools/tc_probe.py case $e 0 > gpurun_out/tc_parity_e$e.log 2>&1; grep -c "'bad_idx_rows': 0, 'bad_dist_rows': 0, 'matches_equal': True" gpurun_out/tc_parity_e$e.log; tail -1 gpurun_out/tc_parity_e$e.log; done
+for f in 0 4; do
+  N=5000 W=10 POSES=64 ENGINE=2 FLAGS=$f timeout 120 python tools/tc_time.py
+  N=20000 W=10 POSES=4 ENGINE=2 FLAGS=$f timeout 120 python tools/tc_time.py
+done 2>&1 | tee gpurun_out/tc_time.log
+for s in 1 2 3 4 5; do N=5000 W=10 POSES=64 ENGINE=2 SPLIT=$s timeout 120 python tools/tc_time.py; done 2>&1 | tee -a gpurun_out/tc_time.log
+N=2000 W=1 POSES=100 ENGINE=2 timeout 120 python tools/tc_time.py
+ENGINE=2 N=5000 W=10 LAUNCHES=3 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_tc_c4.csv python tools/ncu_target.py > /dev/null 2>&1
+grep -v "^==" gpurun_out/launches_tc_c4.csv | cut -d, -f5,15- | tail -4
+ENGINE=2 N=20000 W=10 LAUNCHES=2 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_tc_n20000.csv python tools/ncu_target.py > /dev/null 2>&1
+grep -v "^==" gpurun_out/launches_tc_n20000.csv | cut -d, -f5,15- | tail -4
+VSF_ENGINE=2 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3

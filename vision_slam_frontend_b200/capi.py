@@ -12,7 +12,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "libvsf_cuda.so")
+# VSF_LIB_PATH: development knob to load an alternative build of the same library (kernel variants)
+_LIB_PATH = os.environ.get("VSF_LIB_PATH") or os.path.join(_PKG, "libvsf_cuda.so")
 _LIB = None
 
 # cv::DMatch / cv::KeyPoint / slam_types::FeatureMatch layouts (include/vsf.h)

@@ -30,6 +30,8 @@
 //                         issuer (one elected thread), warps 0-7 = query expansion into smem +
 //                         TMEM epilogue.  Work unit = 256 queries x one train split.
 //   knn2_tc_refine_kernel exact top-2 inside the candidate buckets, ratio test, compaction.
+#include <utility>
+
 #include "knn2_tail.cuh"
 #include "tc_ptx.cuh"
 #include "vsf_device.cuh"
@@ -66,6 +68,8 @@ template <bool I8>
 __global__ void __launch_bounds__(256)
 expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __restrict__ nt_dev,
                     uint8_t* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int rows_pad = (nt_bound + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
   int nt = nt_bound;
   if (nt_dev) nt = min(nt, *nt_dev);
@@ -88,7 +92,9 @@ expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kTcEpiWarps = 8;
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcColSplit = 2;                      // epilogue warps per (accumulator half, lane quarter)
+constexpr int kTcEpiCols = kTcTileRows / kTcColSplit;  // columns of a tile one epilogue warp reduces
 constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;  // + TMA producer warp + MMA warp
 constexpr int kTcBarriers = 2 * kTcStages + 6;      // full/empty per stage, tfull/tempty/aready per half
 constexpr int kTcSmemBytes = kTcABytes + kTcStages * kTcBBytes + kTcBarriers * 8 + 16 + 128;
@@ -128,29 +134,6 @@ __device__ __forceinline__ TcUnit decode_unit(const KnnBatch& batch, const TcBat
 }
 
 template <bool I8>
-__device__ __forceinline__ int bucket_max(const uint32_t (&v)[32]) {
-  if (I8) {
-    int m[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      m[c] = int(v[8 * c]);
-#pragma unroll
-      for (int i = 1; i < 8; ++i) m[c] = max(m[c], int(v[8 * c + i]));
-    }
-    return max(max(m[0], m[1]), max(m[2], m[3]));
-  } else {
-    float m[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      m[c] = __uint_as_float(v[8 * c]);
-#pragma unroll
-      for (int i = 1; i < 8; ++i) m[c] = fmaxf(m[c], __uint_as_float(v[8 * c + i]));
-    }
-    return __float2int_rn(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])));
-  }
-}
-
-template <bool I8>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
   extern __shared__ uint8_t smem_raw[];
@@ -178,8 +161,8 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mbar_init(&tfull[h], 1);
-      mbar_init(&tempty[h], 4);
-      mbar_init(&aready[h], 4);
+      mbar_init(&tempty[h], 4 * kTcColSplit);
+      mbar_init(&aready[h], 4 * kTcColSplit);
     }
     mbar_fence_init();
   }
@@ -188,10 +171,13 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  // everything above overlapped the tail of the previous kernel in the stream
+  pdl_wait();
+  pdl_launch_dependents();
 
   // K-major, no swizzle: [K-chunk c][row][16 B]; chunk stride = rows * 16, 8-row group stride = 128
-  const uint32_t lbo = tc.swap_lbo_sbo ? 128u : uint32_t(kTcQ * 16);
-  const uint32_t sbo = tc.swap_lbo_sbo ? uint32_t(kTcQ * 16) : 128u;
+  const uint32_t lbo = uint32_t(kTcQ * 16);
+  const uint32_t sbo = 128u;
 
   if (warp == kTcEpiWarps) {
     // ------------------------------ TMA producer ------------------------------
@@ -246,32 +232,56 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     __syncwarp();
   } else {
     // ------------------------------ query expansion + epilogue ------------------------------
-    const int h = warp >> 2;                       // accumulator half = query rows 128h .. 128h+127
+    // 16 warps: warp = (column half ch) * 8 + (accumulator half h) * 4 + (TMEM lane quarter).
+    // Two warps per SM sub-partition work on the same accumulator while the tensor core fills
+    // the other one.  An accumulator is handed back to the tensor core as soon as it has been
+    // copied to registers (tcgen05.ld + wait), before it is reduced.
+    const int h = (warp >> 2) & 1;                 // accumulator half = query rows 128h .. 128h+127
+    const int ch = warp >> 3;                      // train columns 128ch .. 128ch+127 of every tile
     const int r = (warp & 3) * 32 + lane;          // TMEM lane = row inside the half
-    const uint32_t taddr = tmem_base + (uint32_t((warp & 3) * 32) << 16) + uint32_t(h) * kTcTileRows;
+    const uint32_t taddr = tmem_base + (uint32_t((warp & 3) * 32) << 16) + uint32_t(h * kTcTileRows + ch * kTcEpiCols);
+    constexpr int NB = kTcEpiCols / kTcBucket;     // buckets per warp per tile
+    constexpr int TB = kTcTileRows / kTcBucket;    // buckets per tile
     uint32_t acc_use = 0;
-    for (int u = blockIdx.x; u < tc.total_units; u += gridDim.x) {
-      const TcUnit U = decode_unit(batch, tc, u);
-      if (U.skip) continue;
+
+    // the query words of the next unit are fetched one unit ahead
+    auto load_query = [&](const TcUnit& V) -> uint4 {
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      const int q = V.q0 + h * 128 + r;
+      if (!V.skip && V.ntiles > 0 && q < V.nq)
+        w = __ldg(reinterpret_cast<const uint4*>(batch.p[V.problem].q + size_t(q) * 8) + ch);
+      return w;
+    };
+    int u = blockIdx.x;
+    TcUnit U;
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (u < tc.total_units) {
+      U = decode_unit(batch, tc, u);
+      w = load_query(U);
+    }
+    while (u < tc.total_units) {
+      const int un = u + int(gridDim.x);
+      TcUnit Un;
+      uint4 wn = make_uint4(0u, 0u, 0u, 0u);
       const KnnProblem& P = batch.p[U.problem];
       const int q = U.q0 + h * 128 + r;
-      uint2* part = reinterpret_cast<uint2*>(batch.partial) + (size_t(P.row0 + q) * tc.split + U.z);
-      if (U.ntiles == 0) {
-        if (q < U.nq) *part = make_uint2(uint32_t(kTcKeySentinel), uint32_t(kTcKeySentinel));
+      uint2* part = reinterpret_cast<uint2*>(batch.partial) +
+                    (size_t(P.row0 + q) * (tc.split * kTcColSplit) + U.z * kTcColSplit + ch);
+      if (U.skip || U.ntiles == 0) {
+        if (!U.skip && q < U.nq) *part = make_uint2(uint32_t(kTcKeySentinel), uint32_t(kTcKeySentinel));
+        if (un < tc.total_units) {
+          Un = decode_unit(batch, tc, un);
+          wn = load_query(Un);
+        }
+        U = Un; w = wn; u = un;
         continue;
       }
-      // expand this thread's query row into the A image
+      // expand half of this thread's query row (K-chunks 8ch .. 8ch+7) into the A image
       {
-        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
-        if (q < U.nq) {
-          const uint4* src = reinterpret_cast<const uint4*>(P.q + size_t(q) * 8);
-          w0 = __ldg(src);
-          w1 = __ldg(src + 1);
-        }
-        const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        uint8_t* dst = sA + size_t(h * 128 + r) * 16;
+        const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+        uint8_t* dst = sA + size_t(h * 128 + r) * 16 + size_t(ch * 8) * (kTcQ * 16);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 8; ++c) {
           const uint32_t b16 = (words[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
           *reinterpret_cast<uint4*>(dst + size_t(c) * (kTcQ * 16)) = expand16<I8>(b16);
         }
@@ -279,35 +289,95 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
         __syncwarp();
         if (lane == 0) mbar_arrive(&aready[h]);
       }
+      if (un < tc.total_units) {
+        Un = decode_unit(batch, tc, un);
+        wn = load_query(Un);
+      }
       int m1 = kTcKeySentinel, m2 = kTcKeySentinel;
-      const int bucket0 = U.t_begin / kTcBucket;
+      const int bucket0 = U.t_begin / kTcBucket + ch * NB;
       for (int k = 0; k < U.ntiles; ++k, ++acc_use) {
         mbar_wait(&tfull[h], acc_use & 1u);
         tc::fence_after_sync();
-        const int tile_row0 = U.t_begin + k * kTcTileRows;
-#pragma unroll 2
-        for (int j = 0; j < kTcTileRows / kTcBucket; ++j) {
-          uint32_t v[32];
-          tc::tmem_ld_32x32(taddr + uint32_t(j * kTcBucket), v);
-          tc::tmem_ld_wait();
-          const int brow0 = tile_row0 + j * kTcBucket;
-          const int valid = U.t_end - brow0;       // train rows of this bucket that exist
-          if (valid <= 0) continue;                // warp-uniform
-          if (valid < kTcBucket) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i >= valid) v[i] = I8 ? uint32_t(kTcKeySentinel) : 0xFF800000u;  // INT_MIN / -inf
-          }
-          const int bm = bucket_max<I8>(v);
-          const int key = bm * (1 << kBucketIdBits) + (kBucketIdMask - (bucket0 + k * (kTcTileRows / kTcBucket) + j));
+        const int row0 = U.t_begin + k * kTcTileRows + ch * kTcEpiCols;   // first train row of my columns
+        const int kbase = kBucketIdMask - (bucket0 + k * TB);
+        auto push = [&](int bm, int j) {
+          const int key = bm * (1 << kBucketIdBits) + (kbase - j);
           m2 = max(m2, min(m1, key));
           m1 = max(m1, key);
+        };
+        auto release = [&]() {
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[h]);
+        };
+        const bool full_tile = row0 + kTcEpiCols <= U.t_end;   // warp-uniform
+        if (tc.flags & 4) {
+          release();
+        } else if (I8) {
+          // int32 accumulators hold |dot| <= 256: read them as packed int16 pairs
+          // (tcgen05.ld ... .pack::16b), 2 columns per register, VIMNMX(3).S16x2 reduction
+          constexpr int RPB = kTcBucket / 2;        // registers per bucket
+          uint32_t v[2][32];
+          tc::tmem_ld_32x32_pack16(taddr, v[0]);
+          tc::tmem_ld_32x32_pack16(taddr + 64u, v[1]);
+          tc::tmem_ld_wait();
+          release();
+          if (!(tc.flags & 2)) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              uint32_t* b = &v[(j * RPB) / 32][(j * RPB) % 32];
+              if (!full_tile) {
+                const int valid = U.t_end - (row0 + j * kTcBucket);   // warp-uniform
+                if (valid <= 0) continue;
+                if (valid < kTcBucket) {
+#pragma unroll
+                  for (int i = 0; i < RPB; ++i) {
+                    if (2 * i >= valid) b[i] = 0x80008000u;
+                    else if (2 * i + 1 >= valid) b[i] = (b[i] & 0xFFFFu) | 0x80000000u;
+                  }
+                }
+              }
+              uint32_t mm = b[0];
+#pragma unroll
+              for (int i = 1; i < RPB; ++i) mm = __vmaxs2(mm, b[i]);
+              push(max(int(short(mm & 0xFFFFu)), int(mm) >> 16), j);
+            }
+          }
+        } else {
+          // fp32 accumulators: four loads of 32 columns, the next one in flight while one is reduced
+          constexpr int BPL = 32 / kTcBucket;       // buckets per load
+          uint32_t v[2][32];
+          tc::tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+          for (int l = 0; l < kTcEpiCols / 32; ++l) {
+            tc::tmem_ld_wait();
+            if (l + 1 < kTcEpiCols / 32) tc::tmem_ld_32x32(taddr + uint32_t((l + 1) * 32), v[(l + 1) & 1]);
+            else release();
+            if (!(tc.flags & 2)) {
+#pragma unroll
+              for (int jj = 0; jj < BPL; ++jj) {
+                const int j = l * BPL + jj;
+                uint32_t* b = &v[l & 1][jj * kTcBucket];
+                if (!full_tile) {
+                  const int valid = U.t_end - (row0 + j * kTcBucket);
+                  if (valid <= 0) continue;
+                  if (valid < kTcBucket) {
+#pragma unroll
+                    for (int i = 0; i < kTcBucket; ++i)
+                      if (i >= valid) b[i] = 0xFF800000u;   // -inf
+                  }
+                }
+                float mm = __uint_as_float(b[0]);
+#pragma unroll
+                for (int i = 1; i < kTcBucket; ++i) mm = fmaxf(mm, __uint_as_float(b[i]));
+                push(__float2int_rn(mm), j);
+              }
+            }
+          }
         }
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[h]);
       }
       if (q < U.nq) *part = make_uint2(uint32_t(m1), uint32_t(m2));
+      U = Un; w = wn; u = un;
     }
   }
 
@@ -320,15 +390,28 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
 }
 
 // ---------------------------------------------------------------------------------------------
-// Refine: one thread per query.  Merge the per-split top-2 buckets, recompute exact Hamming
-// distances inside them (packed keys, lowest train index wins ties), then the shared tail.
-constexpr int kRefineQB = 128;
+// Refine.  Two lanes per query: the even lane rescans the query's best bucket, the odd lane the
+// second-best one (after merging the per-split candidates), with exact Hamming distances on the
+// integer pipe and packed (distance, trainIdx) keys, lowest train index winning ties.  The
+// candidate rows of a warp's 32 (query, bucket) pairs are staged through shared memory with
+// coalesced 16-byte loads (a bucket is kTcBucket * 32 contiguous bytes), 8 rows per pair per
+// pass, so each lane then reads its own rows without bank conflicts.  The pair is merged with
+// one shuffle and the even lane applies the ratio test (src/slam_frontend.cc:529-536).
+constexpr int kRefineQB = 64;                                // queries per refine CTA
+constexpr int kCompactQB = 128;                              // queries per compaction CTA
+constexpr int kRefineThreads = 2 * kRefineQB;
+constexpr int kRefineRows = 8;                               // rows per pair per pass
+constexpr int kRefinePitch = kRefineRows * 32 + 16;          // bytes per pair in the stage (+16: bank skew)
+static_assert(kTcBucket % kRefineRows == 0, "bucket must be a multiple of the refine pass");
 
-__global__ void __launch_bounds__(kRefineQB)
+__global__ void __launch_bounds__(kRefineThreads)
 knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
-  __shared__ TailSmem s_tail;
+  __shared__ __align__(16) uint8_t s_stage[kRefineThreads / 32][32 * kRefinePitch];
   const KnnProblem& P = batch.p[blockIdx.y];
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   int nq = P.nq, nt = P.nt;
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
   if (P.nt_dev) nt = min(nt, *P.nt_dev);
@@ -339,14 +422,16 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   const int qb = blockIdx.x;
   const int q0 = qb * kRefineQB;
   if (q0 >= nq) return;
-  const int nqb = (nq + kRefineQB - 1) / kRefineQB;
-  const int q = q0 + tid;
+  const int q = q0 + (tid >> 1);
+  const int c = tid & 1;                       // 0: best bucket, 1: second-best bucket
 
-  uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
+  int key = kTcKeySentinel;
+  uint32_t qw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   if (q < nq) {
     int b1 = kTcKeySentinel, b2 = kTcKeySentinel;
-    const uint2* part = reinterpret_cast<const uint2*>(batch.partial) + size_t(P.row0 + q) * tc.split;
-    for (int z = 0; z < tc.split; ++z) {
+    const int np = tc.split * kTcColSplit;
+    const uint2* part = reinterpret_cast<const uint2*>(batch.partial) + size_t(P.row0 + q) * np;
+    for (int z = 0; z < np; ++z) {
       const uint2 p = __ldcg(part + z);
       const int a1 = int(p.x), a2 = int(p.y);
       // merge two descending pairs
@@ -354,49 +439,149 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       b2 = max(lo, max(b2, a2));
       b1 = hi;
     }
-    uint32_t qw[8];
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(P.q + size_t(q) * 8);
-      const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
-      qw[0] = w0.x; qw[1] = w0.y; qw[2] = w0.z; qw[3] = w0.w;
-      qw[4] = w1.x; qw[5] = w1.y; qw[6] = w1.z; qw[7] = w1.w;
-    }
+    key = c ? b2 : b1;
+    const uint4* src = reinterpret_cast<const uint4*>(P.q + size_t(q) * 8);
+    const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
+    qw[0] = w0.x; qw[1] = w0.y; qw[2] = w0.z; qw[3] = w0.w;
+    qw[4] = w1.x; qw[5] = w1.y; qw[6] = w1.z; qw[7] = w1.w;
+  }
+  // first train row of this lane's candidate bucket, -1 = none
+  const int my_row0 = (key == kTcKeySentinel) ? -1 : (kBucketIdMask - (key & kBucketIdMask)) * kTcBucket;
+  uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
+  uint8_t* stage = s_stage[warp];
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int key = c ? b2 : b1;
-      if (key == kTcKeySentinel) continue;
-      const int bucket = kBucketIdMask - (key & kBucketIdMask);
-      const int r0 = bucket * kTcBucket;
-      const int r1 = min(nt, r0 + kTcBucket);
-      for (int row = r0; row < r1; ++row) {
-        const uint4* tp = reinterpret_cast<const uint4*>(P.t + size_t(row) * 8);
-        const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+  for (int r0 = 0; r0 < kTcBucket; r0 += kRefineRows) {
+    // stage: 32 pairs x 8 rows x 32 B = 512 pieces of 16 B, 16 per lane
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int g = i * 2 + (lane >> 4);                  // pair (lane) whose rows this piece belongs to
+      const int piece = lane & 15;                        // 16-byte piece of the 256-byte run
+      const int base = __shfl_sync(0xffffffffu, my_row0, g);
+      const int row = base + r0 + (piece >> 1);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (base >= 0 && row < nt) v = __ldg(reinterpret_cast<const uint4*>(P.t + size_t(row) * 8) + (piece & 1));
+      *reinterpret_cast<uint4*>(stage + g * kRefinePitch + piece * 16) = v;
+    }
+    __syncwarp();
+    if (my_row0 >= 0) {
+      const uint4* mine = reinterpret_cast<const uint4*>(stage + lane * kRefinePitch);
+#pragma unroll
+      for (int k = 0; k < kRefineRows; ++k) {
+        const int row = my_row0 + r0 + k;
+        const uint4 t0 = mine[2 * k], t1 = mine[2 * k + 1];
         const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
         const uint32_t d = hamming256<2>(qw, tw);
-        top2_insert(k1, k2, (d << kIdxBits) + uint32_t(row));
+        if (row < nt) top2_insert(k1, k2, (d << kIdxBits) + uint32_t(row));
       }
     }
+    __syncwarp();
   }
-  finalize_and_compact<kRefineQB, kRefineQB>(batch, P, blockIdx.y, qb, nqb, nq, k1, k2, s_tail);
+  // merge the pair (both lanes end up with the query's exact top-2)
+  {
+    const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, 1), o2 = __shfl_xor_sync(0xffffffffu, k2, 1);
+    top2_merge(k1, k2, o1, o2);
+  }
+  // unpack + ratio test; survivors are compacted by knn2_compact_kernel
+  bool pass = false;
+  if (q < nq && c == 0) {
+    const int i0 = (k1 == kKeySentinel) ? -1 : int(k1 & kIdxMask);
+    const int i1 = (k2 == kKeySentinel) ? -1 : int(k2 & kIdxMask);
+    const int d0 = (k1 == kKeySentinel) ? -1 : int(k1 >> kIdxBits);
+    const int d1 = (k2 == kKeySentinel) ? -1 : int(k2 >> kIdxBits);
+    batch.knn_out[P.row0 + q] = make_uint4(uint32_t(i0), uint32_t(i1), uint32_t(d0), uint32_t(d1));
+    pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
+  }
+  const int npass = __syncthreads_count(pass);
+  if (tid == 0) batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
+}
+
+// Ordered compaction of the ratio survivors, one CTA per block of 128 queries: the CTA's
+// output offset is the sum of the survivor counts of the query blocks before it, so the list
+// comes out in ascending queryIdx order (what Frontend::GetMatches returns) with no serial pass.
+__global__ void __launch_bounds__(kCompactQB)
+knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
+  __shared__ unsigned s_red[kCompactQB / 32];
+  __shared__ unsigned s_woff[kCompactQB / 32];
+  const KnnProblem& P = batch.p[blockIdx.y];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  pdl_wait();
+  pdl_launch_dependents();
+  int nq = P.nq;
+  if (P.nq_dev) nq = min(nq, *P.nq_dev);
+  if (nq <= 0) return;                       // the refine kernel wrote match_count = 0
+  const int qb = blockIdx.x;
+  const int q0 = qb * kCompactQB;
+  if (q0 >= nq) return;
+  const int nqb = (nq + kCompactQB - 1) / kCompactQB;
+  unsigned sum = 0;
+  for (int i = tid; i < qb * (kCompactQB / kRefineQB); i += kCompactQB) sum += __ldcg(&batch.qblock_pass[P.qb0 + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_red[warp] = sum;
+  const int q = q0 + tid;
+  bool ok = false;
+  uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+  if (q < nq) {
+    rec = __ldcg(&batch.knn_out[P.row0 + q]);
+    ok = (int(rec.y) >= 0) && (double(int(rec.z)) < batch.ratio * double(int(rec.w)));
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) s_woff[warp] = __popc(bal);
+  __syncthreads();
+  unsigned off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kCompactQB / 32; ++w) {
+    off += s_red[w];
+    if (w < warp) off += s_woff[w];
+    total += s_woff[w];
+  }
+  if (ok) {
+    int4 m;
+    m.x = q;                                  // queryIdx
+    m.y = int(rec.x);                         // trainIdx
+    m.z = 0;                                  // imgIdx
+    m.w = __float_as_int(float(int(rec.z)));  // distance
+    reinterpret_cast<int4*>(P.matches)[off + __popc(bal & ((1u << lane) - 1u))] = m;
+  }
+  if (qb == nqb - 1 && tid == 0) {
+    unsigned base = 0;
+#pragma unroll
+    for (int w = 0; w < kCompactQB / 32; ++w) base += s_red[w];
+    *P.match_count = int(base + total);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
-                                cudaStream_t stream) {
+                                int pdl, cudaStream_t stream) {
   if (nt_bound <= 0) return cudaSuccess;
   const int rows_pad = (nt_bound + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
   const int threads = rows_pad * 4;
   const int blocks = (threads + 255) / 256;
-  if (int8)
-    expand_train_kernel<true><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t*>(t), nt_bound, nt_dev,
-                                                          static_cast<uint8_t*>(out));
-  else
-    expand_train_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t*>(t), nt_bound, nt_dev,
-                                                           static_cast<uint8_t*>(out));
-  return cudaGetLastError();
+  const uint32_t* tp = static_cast<const uint32_t*>(t);
+  uint8_t* op = static_cast<uint8_t*>(out);
+  return int8 ? launch_pdl(expand_train_kernel<true>, dim3(blocks), dim3(256), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op)
+              : launch_pdl(expand_train_kernel<false>, dim3(blocks), dim3(256), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op);
 }
 
-cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq,
+cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq, int pdl,
                            cudaStream_t stream) {
   if (batch.num_problems <= 0 || tc.total_units <= 0) return cudaSuccess;
   cudaError_t e;
@@ -404,14 +589,14 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
   e = int8 ? cudaFuncSetAttribute(knn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes)
            : cudaFuncSetAttribute(knn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
   if (e != cudaSuccess) return e;
-  if (int8)
-    knn2_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, stream>>>(batch, tc);
-  else
-    knn2_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, stream>>>(batch, tc);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const bool p = pdl != 0;
+  e = int8 ? launch_pdl(knn2_tc_kernel<true>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc)
+           : launch_pdl(knn2_tc_kernel<false>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
+  if (e != cudaSuccess) return e;
   dim3 rgrid((max_nq + kRefineQB - 1) / kRefineQB, batch.num_problems);
-  knn2_tc_refine_kernel<<<rgrid, kRefineQB, 0, stream>>>(batch, tc);
-  return cudaGetLastError();
+  dim3 cgrid((max_nq + kCompactQB - 1) / kCompactQB, batch.num_problems);
+  if ((e = launch_pdl(knn2_tc_refine_kernel, rgrid, dim3(kRefineThreads), 0, stream, p, batch, tc)) != cudaSuccess) return e;
+  return launch_pdl(knn2_compact_kernel, cgrid, dim3(kCompactQB), 0, stream, p, batch);
 }
 
 }  // namespace vsf

@@ -3,6 +3,7 @@
 // every entry point reports VSF_ERR_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -16,8 +17,8 @@ namespace vsf {
 cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int variant,
                         int max_qblocks, cudaStream_t stream);
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
-                                cudaStream_t stream);
-cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq,
+                                int pdl, cudaStream_t stream);
+cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq, int pdl,
                            cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
                          uint64_t seed, cudaStream_t stream);
@@ -59,7 +60,7 @@ struct vsf_ctx {
   std::string err;
   int popc_mode = -1, force_split = 0, force_R = 0, variant = -1;   // -1 / 0 = library default
   int engine = 0;         // 0 auto, 1 POPC pipe, 2 tensor cores int8, 3 tensor cores e4m3
-  int engine_flags = 0;   // bit 0: exchange LBO/SBO (bring-up)
+  int engine_flags = 0;   // timing experiments only (TcBatch::flags)
   int last_engine = 0;    // engine the last kNN launch used
   double tc_auto_min_cmp = 1e18;  // automatic mode: tensor cores from this many comparisons per batch
   uint8_t* d_train_exp[kTcMaxTrains] = {nullptr, nullptr};  // +-1 expanded train images
@@ -233,9 +234,10 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
 
   if (engine >= 2) {
     const int int8 = engine == 2;
+    const int pdl = (c->engine_flags & 8) ? 0 : 1;   // flag 8: ordinary launches (A/B timing)
     for (int k = 0; k < n_trains; ++k)
       VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
-                                      c->d_train_exp[k], int8, c->stream));
+                                      c->d_train_exp[k], int8, pdl, c->stream));
     TcBatch tb;
     std::memset(&tb, 0, sizeof(tb));
     long long qblocks = 0;
@@ -255,12 +257,12 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       }
     }
     S = std::max(1, std::min(S, std::min(tiles, 32)));
-    while (S > 1 && size_t(row0) * S > c->partial_cap) --S;
+    while (S > 1 && size_t(row0) * S * 2 > c->partial_cap) --S;   // x2: column halves of the epilogue
     const int tps = (tiles + S - 1) / S;
     S = (tiles + tps - 1) / tps;   // drop splits that would be empty
     tb.split = S;
     tb.rows_per_split = tps * kTcTileRows;
-    tb.swap_lbo_sbo = c->engine_flags & 1;
+    tb.flags = c->engine_flags;
     int units = 0;
     for (int i = 0; i < b.num_problems; ++i) {
       tb.t_exp[i] = c->d_train_exp[train_of[i]];
@@ -271,7 +273,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     tb.total_units = units;
     b.split = S;
     const int grid = std::max(1, std::min(units, c->sm_count));
-    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, grid, max_nq, c->stream));
+    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, grid, max_nq, pdl, c->stream));
     return VSF_OK;
   }
 
@@ -393,7 +395,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC(c, c->d_xy_left_c, N * sizeof(float2));
   VSF_ALLOC(c, c->d_xy_right_c, N * sizeof(float2));
   VSF_ALLOC(c, c->d_knn_out, rows_cap * sizeof(uint4));
-  c->partial_cap = rows_cap * 2 + 262144;
+  c->partial_cap = rows_cap * 16 + 262144;
   VSF_ALLOC(c, c->d_partial, c->partial_cap * sizeof(uint2));
   const size_t qb_cap = rows_cap / 32 + kMaxProblems * 4;
   VSF_ALLOC(c, c->d_qblock_arrivals, qb_cap * sizeof(unsigned));
@@ -436,6 +438,10 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC_HOST(c, c->h_tri_io, N * 8 * sizeof(float));
   VSF_ALLOC_HOST(c, c->h_scalar, 16 * sizeof(float));
   VSF_ALLOC_HOST(c, c->h_fm, size_t(window) * N * sizeof(vsf_feature_match));
+  if (const char* e = std::getenv("VSF_ENGINE")) {   // test / bench override of the automatic choice
+    const int v = std::atoi(e);
+    if (v >= 0 && v <= 3 && (v < 2 || c->words == 8)) c->engine = v;
+  }
   c->slot_count.assign(window + 1, 0);
   c->slot_frame.assign(window + 1, 0);
   c->staging_slot = 0;

@@ -56,7 +56,10 @@ struct KnnBatch {
 // ---- tensor-core engine (knn2_tc_kernel.cu) -------------------------------------------------
 constexpr int kTcQ = 256;            // queries per work unit (two M=128 UMMA tiles)
 constexpr int kTcTileRows = 256;     // train rows per staged tile (N of one UMMA)
-constexpr int kTcBucket = 32;        // train rows per selection bucket (one tcgen05.ld.x32)
+#ifndef VSF_TC_BUCKET
+#define VSF_TC_BUCKET 16
+#endif
+constexpr int kTcBucket = VSF_TC_BUCKET;  // train rows per selection bucket (8, 16 or 32)
 constexpr int kTcStages = 2;         // train tiles in flight in shared memory
 constexpr int kTcRowBytes = 256;     // one 256-bit descriptor expanded to +-1 bytes
 constexpr int kTcABytes = kTcQ * kTcRowBytes;
@@ -69,7 +72,7 @@ struct TcBatch {
   int split;                           // train splits per problem
   int rows_per_split;                  // multiple of kTcTileRows
   int total_units;
-  int swap_lbo_sbo;                    // bring-up knob: exchange the two descriptor strides
+  int flags;                           // bring-up knobs (timing experiments; results invalid): 2 = skip the bucket reduction, 4 = skip the TMEM loads
 };
 
 // ---- PTX helpers -------------------------------------------------------------
@@ -117,6 +120,15 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
           "r"(smem_u32(smem_dst)),
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; pdl_wait() blocks
+// until the predecessor has completed and its writes are visible, pdl_launch_dependents() lets
+// the successor start its own prologue.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
