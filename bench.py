@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--split", type=int, default=0)
     ap.add_argument("--qpt", type=int, default=0)
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--engine", type=int, default=0,
+                    help="0 auto (tensor cores on this workload), 1 POPC pipe, 2 tensor int8, 3 tensor e4m3")
     return ap.parse_args()
 
 
@@ -278,6 +280,7 @@ def run_b200(a):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_tuning(a.popc_mode, a.split, a.qpt, a.variant)
+    ctx.set_engine(a.engine, 0)
 
     # ---- device-resident sequence: this rank's pose range, larger than L2 ----------------
     frame_bytes = n * 32
@@ -316,6 +319,17 @@ def run_b200(a):
         barrier()
     ms = e0.elapsed_time(e1)
     counts = ctx.fetch_window(W, with_matches=False)
+    engine = ctx.last_engine
+    # ---- per-kernel durations (CUDA events on the ctx stream around every kernel of a launch;
+    # a separate pass because the events serialise kernels that otherwise overlap via PDL)
+    ctx.set_profile(True)
+    kt = np.zeros(4)
+    KP = min(K, 200)
+    for t in range(KP):
+        launch_step(WU + t)
+        kt += np.array(ctx.last_kernel_times())
+    ctx.set_profile(False)
+    kt /= KP
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -351,22 +365,50 @@ def run_b200(a):
         achieved_gbs = alg_bytes / per_launch_s / 1e9
         cmp_rate_1gpu = cmp_per_step / per_launch_s
         popc_peak_cmp = popc_rate / 8.0                    # 8 POPC per 256-bit comparison
+        main_s = float(kt[1]) * 1e-3                       # dominant kernel, average launch duration
+        tensor = engine >= 2
+        if tensor:
+            # one comparison = one 256-term dot product of +-1 bytes = 256 MACs = 512 ops
+            ops = 512.0 * cmp_per_step
+            bf16 = float(peaks.get("bf16_tflops", 1590.0))
+            roofline = {
+                "bound": "tensor", "achieved": ops / main_s / 1e12, "peak": 2.0 * bf16, "unit": "TFLOP/s",
+                "frac": ops / main_s / 1e12 / (2.0 * bf16), "traffic": None,
+                "kernel": "vsf::knn2_tc_kernel<int8>" if engine == 2 else "vsf::knn2_tc_kernel<e4m3>",
+                "kernel_ms": float(kt[1]),
+                "peak_source": "2 x bf16_tflops (burst) of %s: 8-bit operands run the tensor pipe at twice the "
+                               "bf16 rate; ops are int8 multiply-accumulates counted as 2 (TOP/s)" % peak_src,
+                "algorithmic_ops_per_launch": ops,
+                "nominal_peak": 4500.0,
+                "frac_of_nominal": ops / main_s / 1e12 / 4500.0,
+                "other_kernels_ms": {"expand_train": float(kt[0]), "refine": float(kt[2]), "compact": float(kt[3])},
+                "note": "512 ops per 256-bit comparison x comparisons per launch / CUDA-event duration of the "
+                        "tensor-core kernel; the refine (exact POPC re-scan of <= 32 train rows per query) and "
+                        "the compaction are separate, small kernels listed in other_kernels_ms",
+            }
+        else:
+            roofline = {
+                "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "POPC engine: integer-pipe bound by design (arithmetic intensity N/32 comparisons "
+                        "per byte), HBM is idle at roofline; see roofline_int",
+            }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": WU, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "i8" if engine == 2 else ("f8e4m3" if engine == 3 else "u32"),
+            "data": "synthetic",
             "config": dict(workload_config(a, world),
                            l2="sequence buffer %.0f MB > %d MB L2, each frame first read from HBM; "
                               "L2 flushed before the timed region"
                               % (n_poses * frame_bytes / 2 ** 20, L2_BYTES // 2 ** 20)),
             "matched_frame_pairs_per_s": world * K * W / (ms_max * 1e-3),
-            "roofline": {
-                "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "kernel is integer-pipe (POPC) bound by design: arithmetic intensity is "
-                        "N/32 comparisons per byte, HBM is idle at roofline; see roofline_int",
-            },
+            "engine": {1: "popc", 2: "tensor_int8", 3: "tensor_e4m3"}.get(engine, str(engine)),
+            "roofline": roofline,
+            "roofline_hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved_gbs / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
+                             "note": "whole step; the path is compute-bound, HBM is idle by design"},
             "roofline_int": {
                 "bound": "int_pipe_popc", "achieved": cmp_rate_1gpu, "unit": "cmp/s per GPU",
                 "peak": popc_peak_cmp, "frac": cmp_rate_1gpu / popc_peak_cmp,
@@ -374,9 +416,15 @@ def run_b200(a):
                 "popc_ops_per_s": popc_rate, "lop3_ops_per_s": lop3_rate,
                 "popc_lop3_mixed_ops_per_s": mixed_rate,
                 "nominal_peak": 2 * ctx.sm_count * 1.965e9,
+                "note": "north-star denominator: the integer-pipe roofline of the naive 8-POPC comparison; the "
+                        "tensor-core engine is not bound by it (frac > 1)",
             },
-            "gpu_launches": K,
-            "kernel": "vsf::knn2_kernel<8,R,MODE> (one launch per step)",
+            "gpu_launches": K * (4 if tensor else 1),
+            "kernel": ("expand_train_kernel + knn2_tc_kernel + knn2_tc_refine_kernel + knn2_compact_kernel "
+                       "(4 launches per step, programmatic dependent launch)") if tensor
+                      else "vsf::knn2_kernel<8,R,MODE> (one launch per step)",
+            "kernel_ms": {"expand_train": float(kt[0]), "main": float(kt[1]), "refine": float(kt[2]),
+                          "compact": float(kt[3])},
             "last_step_survivors": [int(c) for c in counts],
             "clocks": clocks.summary(),
         }

@@ -105,6 +105,16 @@ int vsf_set_engine(vsf_ctx* ctx, int engine, int flags);
 /* Engine (1..3) used by the most recent kNN launch of this ctx. */
 int vsf_last_engine(const vsf_ctx* ctx);
 
+/* Per-kernel timing of the kNN launch sequence, for roofline accounting.  While enabled,
+ * CUDA events are recorded on the ctx stream around each kernel of every kNN launch (this
+ * removes the programmatic overlap between them, so leave it off for throughput runs).
+ * vsf_last_kernel_times waits for the most recent launch and returns 4 durations in ms:
+ * [0] train expansion, [1] the distance/selection kernel (knn2_tc_kernel or knn2_kernel),
+ * [2] refine, [3] ordered compaction ([0], [2], [3] are 0 for the POPC engine, whose single
+ * kernel does everything). */
+int vsf_set_profile(vsf_ctx* ctx, int enabled);
+int vsf_last_kernel_times(vsf_ctx* ctx, float* ms4);
+
 /* ---------------------------------------------- a1: BFMatcher::knnMatch k=2 */
 
 /* Replaces `matcher_->knnMatch(query.descriptors_, train.descriptors_,

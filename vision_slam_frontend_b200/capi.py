@@ -69,6 +69,8 @@ def load_library():
         "vsf_set_tuning": ([vp, i, i, i, i], i),
         "vsf_set_engine": ([vp, i, i], i),
         "vsf_last_engine": ([vp], i),
+        "vsf_set_profile": ([vp, i], i),
+        "vsf_last_kernel_times": ([vp, C.POINTER(f)], i),
         "vsf_knn2": ([vp, vp, i, sz, vp, i, sz, vp, vp], i),
         "vsf_get_matches": ([vp, vp, i, sz, vp, i, sz, d, vp, i, C.POINTER(i)], i),
         "vsf_window_push": ([vp, u64, vp, i, sz], i),
@@ -101,7 +103,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "vsf_create", "vsf_destroy", "vsf_last_error", "vsf_version", "vsf_set_stream",
-    "vsf_synchronize", "vsf_set_tuning", "vsf_set_engine", "vsf_last_engine", "vsf_knn2", "vsf_get_matches", "vsf_window_push",
+    "vsf_synchronize", "vsf_set_tuning", "vsf_set_engine", "vsf_last_engine", "vsf_set_profile",
+    "vsf_last_kernel_times", "vsf_knn2", "vsf_get_matches", "vsf_window_push",
     "vsf_window_commit", "vsf_window_clear", "vsf_window_size", "vsf_window_match",
     "vsf_window_feature_matches", "vsf_stereo_filter", "vsf_set_stereo_threshold",
     "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_observe_features",
@@ -180,6 +183,15 @@ class Context:
     @property
     def last_engine(self) -> int:
         return self._L.vsf_last_engine(self._h)
+
+    def set_profile(self, enabled: bool):
+        self._check(self._L.vsf_set_profile(self._h, int(bool(enabled))))
+
+    def last_kernel_times(self):
+        """[expand, distance/selection kernel, refine, compaction] durations in ms."""
+        ms = (C.c_float * 4)()
+        self._check(self._L.vsf_last_kernel_times(self._h, ms))
+        return [float(v) for v in ms]
 
     # -- a1 / a2 -------------------------------------------------------------------
     def knn2(self, Q: np.ndarray, T: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

@@ -71,7 +71,10 @@ knn2_kernel(const __grid_constant__ KnnBatch batch) {
   if (P.nt_dev) nt = min(nt, *P.nt_dev);
 
   if (nq <= 0) {
-    if (blockIdx.x == 0 && blockIdx.z == 0 && tid == 0) *P.match_count = 0;
+    if (blockIdx.x == 0 && blockIdx.z == 0 && tid == 0) {
+      *P.match_count = 0;
+      if (batch.host_counts) batch.host_counts[P.region] = 0;
+    }
     return;
   }
   const int qb = blockIdx.x;

@@ -56,6 +56,9 @@ __device__ __forceinline__ void finalize_and_compact(const KnnBatch& batch, cons
   __threadfence();
 
   // the problem's last CTA compacts survivors in query order
+  int4* hostm = batch.host_matches
+                    ? reinterpret_cast<int4*>(batch.host_matches + size_t(P.region) * batch.host_region_stride)
+                    : nullptr;
   uint32_t base = 0;
   for (int c0 = 0; c0 < nqb; c0 += kScanChunk) {
     const int cn = min(kScanChunk, nqb - c0);
@@ -96,6 +99,7 @@ __device__ __forceinline__ void finalize_and_compact(const KnnBatch& batch, cons
           m.z = 0;            // imgIdx
           m.w = __float_as_int(float(int(rec.z)));  // distance
           reinterpret_cast<int4*>(P.matches)[dst] = m;
+          if (hostm) hostm[dst] = m;
         }
         off += __popc(bal);
       }
@@ -104,7 +108,10 @@ __device__ __forceinline__ void finalize_and_compact(const KnnBatch& batch, cons
     base = uint32_t(sm.flag);
     __syncthreads();
   }
-  if (tid == 0) *P.match_count = int(base);
+  if (tid == 0) {
+    *P.match_count = int(base);
+    if (batch.host_counts) batch.host_counts[P.region] = int(base);
+  }
 }
 
 }  // namespace vsf

@@ -416,7 +416,10 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
   if (P.nt_dev) nt = min(nt, *P.nt_dev);
   if (nq <= 0) {
-    if (blockIdx.x == 0 && tid == 0) *P.match_count = 0;
+    if (blockIdx.x == 0 && tid == 0) {
+      *P.match_count = 0;
+      if (batch.host_counts) batch.host_counts[P.region] = 0;
+    }
     return;
   }
   const int qb = blockIdx.x;
@@ -542,13 +545,17 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
     m.y = int(rec.x);                         // trainIdx
     m.z = 0;                                  // imgIdx
     m.w = __float_as_int(float(int(rec.z)));  // distance
-    reinterpret_cast<int4*>(P.matches)[off + __popc(bal & ((1u << lane) - 1u))] = m;
+    const unsigned dst = off + __popc(bal & ((1u << lane) - 1u));
+    reinterpret_cast<int4*>(P.matches)[dst] = m;
+    if (batch.host_matches)
+      reinterpret_cast<int4*>(batch.host_matches + size_t(P.region) * batch.host_region_stride)[dst] = m;
   }
   if (qb == nqb - 1 && tid == 0) {
     unsigned base = 0;
 #pragma unroll
     for (int w = 0; w < kCompactQB / 32; ++w) base += s_red[w];
     *P.match_count = int(base + total);
+    if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
   }
 }
 
@@ -581,8 +588,11 @@ cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, 
               : launch_pdl(expand_train_kernel<false>, dim3(blocks), dim3(256), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op);
 }
 
+// ev (optional, 4 events): recorded before the main kernel, after it, after the refine and
+// after the compaction kernel (per-kernel timing for bench.py's roofline; an event between two
+// kernels removes their programmatic overlap, so it is only used in dedicated timing passes).
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq, int pdl,
-                           cudaStream_t stream) {
+                           cudaEvent_t* ev, cudaStream_t stream) {
   if (batch.num_problems <= 0 || tc.total_units <= 0) return cudaSuccess;
   cudaError_t e;
   // per-device attribute; setting it is a cheap host-side call
@@ -590,13 +600,18 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
            : cudaFuncSetAttribute(knn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
   if (e != cudaSuccess) return e;
   const bool p = pdl != 0;
+  if (ev) cudaEventRecord(ev[0], stream);
   e = int8 ? launch_pdl(knn2_tc_kernel<true>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc)
            : launch_pdl(knn2_tc_kernel<false>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
   if (e != cudaSuccess) return e;
+  if (ev) cudaEventRecord(ev[1], stream);
   dim3 rgrid((max_nq + kRefineQB - 1) / kRefineQB, batch.num_problems);
   dim3 cgrid((max_nq + kCompactQB - 1) / kCompactQB, batch.num_problems);
   if ((e = launch_pdl(knn2_tc_refine_kernel, rgrid, dim3(kRefineThreads), 0, stream, p, batch, tc)) != cudaSuccess) return e;
-  return launch_pdl(knn2_compact_kernel, cgrid, dim3(kCompactQB), 0, stream, p, batch);
+  if (ev) cudaEventRecord(ev[2], stream);
+  e = launch_pdl(knn2_compact_kernel, cgrid, dim3(kCompactQB), 0, stream, p, batch);
+  if (ev) cudaEventRecord(ev[3], stream);
+  return e;
 }
 
 }  // namespace vsf

@@ -19,7 +19,7 @@ cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int v
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
                                 int pdl, cudaStream_t stream);
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq, int pdl,
-                           cudaStream_t stream);
+                           cudaEvent_t* ev, cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
                          uint64_t seed, cudaStream_t stream);
 int probe_ops_per_step(int kind);
@@ -57,12 +57,15 @@ struct vsf_ctx {
   int host_threads = 1;   // for the host-side std::sort of sort_mode 1
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-kernel timing (vsf_set_profile)
+  int profile = 0;
+  bool pev_valid = false;
   std::string err;
   int popc_mode = -1, force_split = 0, force_R = 0, variant = -1;   // -1 / 0 = library default
   int engine = 0;         // 0 auto, 1 POPC pipe, 2 tensor cores int8, 3 tensor cores e4m3
   int engine_flags = 0;   // timing experiments only (TcBatch::flags)
   int last_engine = 0;    // engine the last kNN launch used
-  double tc_auto_min_cmp = 1e18;  // automatic mode: tensor cores from this many comparisons per batch
+  double tc_auto_min_cmp = 1e7;  // automatic mode: tensor cores from this many comparisons per batch
   uint8_t* d_train_exp[kTcMaxTrains] = {nullptr, nullptr};  // +-1 expanded train images
 
   int rows_pad = 0;    // max_features rounded up to 128
@@ -91,7 +94,10 @@ struct vsf_ctx {
   uint8_t* h_desc[2] = {nullptr, nullptr};
   float2* h_xy[2] = {nullptr, nullptr};
   int* h_counts = nullptr;         // kMaxProblems + 8
-  vsf_dmatch* h_matches = nullptr;  // regions * rows_pad
+  vsf_dmatch* h_matches = nullptr;  // regions * rows_pad, mapped: kernels mirror match lists into it
+  int* h_region_counts = nullptr;   // kMaxProblems, mapped: survivor count of every region
+  vsf_dmatch* dm_matches = nullptr; // device-side addresses of the two mapped buffers
+  int* dm_region_counts = nullptr;
   int* h_kept[2] = {nullptr, nullptr};
   float* h_resid = nullptr;
   float4* h_X4 = nullptr;
@@ -167,7 +173,8 @@ static int upload_xy(vsf_ctx* c, int which, const vsf_keypoint* kp, int n, float
 }
 
 // Build the batch, choose (R, split) and launch kernel 1.
-static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio) {
+// mirror: also store the match lists / counts into the mapped host buffers (host-API calls)
+static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio, bool mirror = false) {
   if (specs.empty()) return VSF_OK;
   if (int(specs.size()) > kMaxProblems) return fail(c, VSF_ERR_CAPACITY, "too many problems in one batch");
   KnnBatch b;
@@ -179,6 +186,11 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   b.qblock_arrivals = c->d_qblock_arrivals;
   b.qblock_pass = c->d_qblock_pass;
   b.problem_arrivals = c->d_problem_arrivals;
+  if (mirror) {
+    b.host_matches = c->dm_matches;
+    b.host_counts = c->dm_region_counts;
+    b.host_region_stride = c->rows_pad;
+  }
   int row0 = 0, qb0 = 0, max_nq = 0, max_nt = 0;
   long long total_q = 0;
   for (int i = 0; i < b.num_problems; ++i) {
@@ -196,6 +208,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     p.match_count = c->d_match_count + s.region;
     p.row0 = row0;
     p.qb0 = qb0;
+    p.region = s.region;
     row0 += round_up(std::max(s.nq, 1), 128);
     qb0 += round_up(std::max(s.nq, 1), 128) / 32;
     max_nq = std::max(max_nq, s.nq);
@@ -204,8 +217,10 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   }
   if (max_nq == 0) {
     // nothing to match: every problem reports zero survivors
-    for (int i = 0; i < b.num_problems; ++i)
+    for (int i = 0; i < b.num_problems; ++i) {
       VSF_CUDA(c, cudaMemsetAsync(c->d_match_count + specs[i].region, 0, sizeof(int), c->stream));
+      if (mirror) c->h_region_counts[specs[i].region] = 0;   // no kernel will write it
+    }
     return VSF_OK;
   }
   // ---- engine choice.  The tensor-core engine needs 32-byte rows and at most kTcMaxTrains
@@ -235,6 +250,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   if (engine >= 2) {
     const int int8 = engine == 2;
     const int pdl = (c->engine_flags & 8) ? 0 : 1;   // flag 8: ordinary launches (A/B timing)
+    if (c->profile) VSF_CUDA(c, cudaEventRecord(c->pev[0], c->stream));
     for (int k = 0; k < n_trains; ++k)
       VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
                                       c->d_train_exp[k], int8, pdl, c->stream));
@@ -273,7 +289,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     tb.total_units = units;
     b.split = S;
     const int grid = std::max(1, std::min(units, c->sm_count));
-    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, grid, max_nq, pdl, c->stream));
+    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, grid, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
+    c->pev_valid = c->profile != 0;
     return VSF_OK;
   }
 
@@ -300,7 +317,15 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   while (S > 1 && size_t(row0) * S > c->partial_cap) --S;
   b.split = S;
   const int max_qblocks = (max_nq + 32 * R - 1) / (32 * R);
+  if (c->profile) {
+    VSF_CUDA(c, cudaEventRecord(c->pev[0], c->stream));
+    VSF_CUDA(c, cudaEventRecord(c->pev[1], c->stream));
+  }
   VSF_CUDA(c, launch_knn2(b, c->words, R, mode, variant, max_qblocks, c->stream));
+  if (c->profile) {
+    for (int k = 2; k < 5; ++k) VSF_CUDA(c, cudaEventRecord(c->pev[k], c->stream));
+    c->pev_valid = true;
+  }
   return VSF_OK;
 }
 
@@ -321,13 +346,15 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
                  c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
-  void* host[] = {c->h_desc[0], c->h_desc[1], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches,
+  void* host[] = {c->h_desc[0], c->h_desc[1], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches, c->h_region_counts,
                   c->h_kept[0], c->h_kept[1], c->h_resid, c->h_X4, c->h_knn, c->h_tri_io,
                   c->h_scalar, c->h_fm};
   for (void* p : host)
     if (p) cudaFreeHost(p);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (cudaEvent_t e : c->pev)
+    if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -383,6 +410,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   c->stream = c->own_stream;
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  for (cudaEvent_t& e : c->pev) cudaEventCreate(&e);
 
   const size_t N = size_t(c->rows_pad);
   const size_t rows_cap = size_t(c->regions) * N;
@@ -431,7 +459,18 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
     VSF_ALLOC_HOST(c, c->h_kept[k], N * sizeof(int));
   }
   VSF_ALLOC_HOST(c, c->h_counts, (kMaxProblems + 8) * sizeof(int));
-  VSF_ALLOC_HOST(c, c->h_matches, rows_cap * sizeof(vsf_dmatch));
+  {
+    // mapped pinned memory: the compaction tails store survivors straight into it (zero-copy)
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_matches), rows_cap * sizeof(vsf_dmatch), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&c->h_region_counts), kMaxProblems * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->dm_matches), c->h_matches, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->dm_region_counts), c->h_region_counts, 0) != cudaSuccess) {
+      std::fprintf(stderr, "vsf_create: mapped pinned allocation failed\n");
+      vsf_destroy(c);
+      return VSF_ERR_CUDA;
+    }
+    std::memset(c->h_region_counts, 0, kMaxProblems * sizeof(int));
+  }
   VSF_ALLOC_HOST(c, c->h_resid, N * sizeof(float));
   VSF_ALLOC_HOST(c, c->h_X4, N * sizeof(float4));
   VSF_ALLOC_HOST(c, c->h_knn, N * sizeof(uint4));
@@ -496,6 +535,22 @@ extern "C" int vsf_set_engine(vsf_ctx* c, int engine, int flags) {
 
 extern "C" int vsf_last_engine(const vsf_ctx* c) { return c ? c->last_engine : 0; }
 
+extern "C" int vsf_set_profile(vsf_ctx* c, int enabled) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  c->profile = enabled ? 1 : 0;
+  c->pev_valid = false;
+  return VSF_OK;
+}
+
+extern "C" int vsf_last_kernel_times(vsf_ctx* c, float* ms4) {
+  if (!c || !ms4) return VSF_ERR_BAD_ARG;
+  if (!c->pev_valid) return fail(c, VSF_ERR_STATE, "no profiled kNN launch (call vsf_set_profile(ctx, 1) first)");
+  cudaSetDevice(c->device);
+  VSF_CUDA(c, cudaEventSynchronize(c->pev[4]));
+  for (int k = 0; k < 4; ++k) VSF_CUDA(c, cudaEventElapsedTime(&ms4[k], c->pev[k], c->pev[k + 1]));
+  return VSF_OK;
+}
+
 extern "C" int vsf_device_sm_count(const vsf_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" int vsf_device_row_bytes(const vsf_ctx* c) { return c ? c->row_bytes : 0; }
 
@@ -511,14 +566,14 @@ static int check_pair(vsf_ctx* c, const uint8_t* q, int nq, size_t qs, const uin
 }
 
 static int knn_pair(vsf_ctx* c, const uint8_t* q, int nq, size_t qs, const uint8_t* t, int nt, size_t ts,
-                    double ratio) {
+                    double ratio, bool mirror = false) {
   cudaSetDevice(c->device);
   int rc;
   if ((rc = upload_desc(c, 0, q, nq, qs, c->d_raw_left))) return rc;
   if ((rc = upload_desc(c, 1, t, nt, ts, c->d_raw_right))) return rc;
   std::vector<ProblemSpec> specs(1);
   specs[0] = ProblemSpec{c->d_raw_left, nq, nullptr, c->d_raw_right, nt, nullptr, c->window + 1};
-  return run_knn(c, specs, ratio);
+  return run_knn(c, specs, ratio, mirror);
 }
 
 extern "C" int vsf_knn2(vsf_ctx* c, const uint8_t* q, int nq, size_t q_stride, const uint8_t* t, int nt,
@@ -547,18 +602,12 @@ extern "C" int vsf_get_matches(vsf_ctx* c, const uint8_t* q, int nq, size_t q_st
   if (!n_out || cap < 0 || (cap > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
   *n_out = 0;
   if (nq == 0) return VSF_OK;
-  if ((rc = knn_pair(c, q, nq, q_stride, t, nt, t_stride, ratio))) return rc;
+  if ((rc = knn_pair(c, q, nq, q_stride, t, nt, t_stride, ratio, true))) return rc;
   const int region = c->window + 1;
-  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_match_count + region, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
-  const int n = c->h_counts[0];
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));   // survivors + count are already in mapped host memory
+  const int n = c->h_region_counts[region];
   if (n > cap) return fail(c, VSF_ERR_CAPACITY, "output capacity too small");
-  if (n > 0) {
-    VSF_CUDA(c, cudaMemcpyAsync(c->h_matches, c->region_ptr(region), size_t(n) * sizeof(vsf_dmatch),
-                                cudaMemcpyDeviceToHost, c->stream));
-    VSF_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::memcpy(out, c->h_matches, size_t(n) * sizeof(vsf_dmatch));
-  }
+  if (n > 0) std::memcpy(out, c->h_matches + size_t(region) * c->rows_pad, size_t(n) * sizeof(vsf_dmatch));
   *n_out = n;
   return VSF_OK;
 }
@@ -593,7 +642,7 @@ extern "C" int vsf_window_commit(vsf_ctx* c, uint64_t frame_id, int n) {
   return VSF_OK;
 }
 
-static int window_launch(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio) {
+static int window_launch(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio, bool mirror) {
   if (n < 0 || (n > 0 && !desc) || (n > 0 && stride < size_t(c->desc_bytes))) return fail(c, VSF_ERR_BAD_ARG, "bad frame");
   if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
   cudaSetDevice(c->device);
@@ -603,7 +652,15 @@ static int window_launch(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, 
   int j = 0;
   for (int s : c->live)
     specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, c->slot_ptr(c->staging_slot), n, nullptr, j++});
-  return run_knn(c, specs, ratio);
+  return run_knn(c, specs, ratio, mirror);
+}
+
+// host-API launches mirror their match lists into mapped host memory: one synchronisation and the
+// counts (h_counts[j]) / lists (h_matches + region * rows_pad) are there
+static int sync_mirrored(vsf_ctx* c, int n_regions, int first_region) {
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int j = 0; j < n_regions; ++j) c->h_counts[j] = c->h_region_counts[first_region + j];
+  return VSF_OK;
 }
 
 // counts first, then exactly the survivors of every region
@@ -628,10 +685,10 @@ extern "C" int vsf_window_match(vsf_ctx* c, const uint8_t* desc, int n, size_t s
                                 int* n_frames) {
   if (!c) return VSF_ERR_BAD_ARG;
   if (!n_frames || !counts || cap_per_frame < 0 || (cap_per_frame > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
-  int rc = window_launch(c, desc, n, stride, ratio);
+  int rc = window_launch(c, desc, n, stride, ratio, true);
   if (rc) return rc;
   const int nf = int(c->live.size());
-  if ((rc = fetch_regions(c, nf, 0))) return rc;
+  if ((rc = sync_mirrored(c, nf, 0))) return rc;
   *n_frames = nf;
   for (int j = 0; j < nf; ++j) {
     const int cnt = c->h_counts[j];
@@ -655,7 +712,7 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
   if (!c) return VSF_ERR_BAD_ARG;
   if (!n_frames || !counts || cap_per_frame < 0 || (cap_per_frame > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
   if (sort_mode != 0 && sort_mode != 1) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 or 1");
-  int rc = window_launch(c, desc, n, stride, ratio);
+  int rc = window_launch(c, desc, n, stride, ratio, sort_mode == 1);
   if (rc) return rc;
   const int nf = int(c->live.size());
   *n_frames = nf;
@@ -693,7 +750,7 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
   // sort_mode 1: the reference's own host sequence (src/slam_frontend.cc:289-296), one
   // frame pair per host thread (each list is sorted by the same single-threaded
   // std::sort the reference runs, so the order inside every list is unchanged).
-  if ((rc = fetch_regions(c, nf, 0))) return rc;
+  if ((rc = sync_mirrored(c, nf, 0))) return rc;
   for (int j = 0; j < nf; ++j) {
     const int good = int(float(size_t(c->h_counts[j])) * best_percent);
     if (good > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
@@ -857,31 +914,25 @@ extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_key
     specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, cur, nl, c->d_n_kept, j++});
   const int tri_region = c->window;
   specs.push_back(ProblemSpec{c->d_right_c, nl, c->d_n_kept, cur, nl, c->d_n_kept, tri_region});
-  if ((rc = run_knn(c, specs, ratio))) return rc;
+  if ((rc = run_knn(c, specs, ratio, true))) return rc;
   VSF_CUDA(c, launch_triangulate_matches(P_left, P_right, c->region_ptr(tri_region),
                                          c->d_match_count + tri_region, nl, c->d_xy_left_c,
                                          c->d_xy_right_c, c->d_X4, c->stream));
-  // results: counts first, then exactly-sized copies
-  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_match_count, (c->window + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  // match lists and their counts arrive in mapped host memory with the kernels; the rest is
+  // sized by two scalars, so: scalars, sync, exactly-sized copies, sync
   VSF_CUDA(c, cudaMemcpyAsync(c->h_counts + kMaxProblems, c->d_n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_thresh + c->thresh_cur, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k <= c->window; ++k) c->h_counts[k] = c->h_region_counts[k];
   const int M = c->h_counts[kMaxProblems];
   const int n_tri = c->h_counts[tri_region];
   if (M > 0) {
     VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[0], c->d_kept_left, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[1], c->d_kept_right, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }
-  for (int k = 0; k < nf; ++k)
-    if (c->h_counts[k] > 0)
-      VSF_CUDA(c, cudaMemcpyAsync(c->h_matches + size_t(k) * c->rows_pad, c->region_ptr(k),
-                                  size_t(c->h_counts[k]) * sizeof(vsf_dmatch), cudaMemcpyDeviceToHost, c->stream));
-  if (n_tri > 0) {
-    VSF_CUDA(c, cudaMemcpyAsync(c->h_matches + size_t(tri_region) * c->rows_pad, c->region_ptr(tri_region),
-                                size_t(n_tri) * sizeof(vsf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+  if (n_tri > 0)
     VSF_CUDA(c, cudaMemcpyAsync(c->h_X4, c->d_X4, size_t(n_tri) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  }
-  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (M > 0 || n_tri > 0) VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   out->n_kept = M;
   out->stereo_threshold_next = c->h_scalar[0];
   out->n_frames = nf;

@@ -39,6 +39,7 @@ struct KnnProblem {
   int nq, nt;
   int row0;                // first row of this problem in knn_out / partial
   int qb0;                 // first slot of this problem in the per-query-block counters
+  int region;              // index of `matches` among the ctx's match regions (host mirror slot)
 };
 
 struct KnnBatch {
@@ -50,6 +51,13 @@ struct KnnBatch {
   unsigned* qblock_arrivals;  // [qblocks]   self-resetting counters
   unsigned* qblock_pass;      // [qblocks]   ratio survivors per query block
   unsigned* problem_arrivals; // [problems]  self-resetting counters
+  // Optional zero-copy mirror: when host_matches != nullptr the survivors and their count are
+  // also stored straight into mapped pinned host memory (region r at host_matches +
+  // r * host_region_stride, count at host_counts[r]), so a host-API call needs one stream
+  // synchronisation and no device-to-host copy.
+  vsf_dmatch* host_matches;
+  int* host_counts;
+  int host_region_stride;
   KnnProblem p[kMaxProblems];
 };
 
