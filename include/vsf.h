@@ -179,6 +179,37 @@ int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
                                vsf_feature_match* out, int cap_per_frame,
                                int* n_frames);
 
+/* Pipelined form of vsf_window_feature_matches + vsf_window_commit for a frame
+ * stream (the bag loop of src/slam_frontend_main.cc:236-328 feeding
+ * ObserveImage): vsf_window_submit enqueues the upload of the frame, the match
+ * of every resident past frame against it (src/slam_frontend.cc:424-434), the
+ * device sort when sort_mode == 0, then evicts / pushes the frame into the
+ * window (:467-470) and returns WITHOUT waiting for the device.  The match
+ * lists of frame t do not feed frame t+1 (only its descriptors do), so up to
+ * VSF_PIPELINE_DEPTH frames may be in flight: the host sorts and consumes the
+ * lists of frame t while the device matches frame t+1.  desc is copied to
+ * pinned staging before the call returns.
+ * vsf_window_collect waits for the OLDEST submitted frame and returns exactly
+ * what vsf_window_feature_matches would have returned for it (same argument
+ * meaning; *frame_id = the id given at submit; sort_mode / best_percent are the
+ * ones given at submit).  VSF_ERR_STATE: submit with VSF_PIPELINE_DEPTH frames
+ * in flight, or collect with none. */
+#define VSF_PIPELINE_DEPTH 4
+int vsf_window_submit(vsf_ctx* ctx, uint64_t frame_id, const uint8_t* desc, int n,
+                      size_t stride, double nn_match_ratio, float best_percent,
+                      int sort_mode);
+int vsf_window_collect(vsf_ctx* ctx, uint64_t* frame_id, uint64_t* frame_ids,
+                       int* counts, vsf_feature_match* out, int cap_per_frame,
+                       int* n_frames);
+int vsf_window_in_flight(const vsf_ctx* ctx);
+
+/* Bytes that crossed PCIe for the most recent vsf_window_match /
+ * vsf_window_feature_matches / vsf_window_collect call: the uploaded descriptor
+ * rows, and the match records + counts the device stored into host memory
+ * (sort_mode 1 brings back every ratio survivor, sort_mode 0 only the kept
+ * FeatureMatches).  Bench accounting. */
+int vsf_window_last_transfer(const vsf_ctx* ctx, size_t* h2d_bytes, size_t* d2h_bytes);
+
 /* ------------------------- a5: stereo L->R match + RemoveAmbigStereo */
 
 /* Replaces `GetMatches(curr, right, ratio)` + Frontend::RemoveAmbigStereo

@@ -195,6 +195,58 @@ def test_window_feature_matches(sort_mode):
             live.append((p, D))
 
 
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("sort_mode", [0, 1])
+def test_window_pipelined_submit_collect(sort_mode, engine):
+    """vsf_window_submit / vsf_window_collect with several frames in flight return, frame by
+    frame, what the reference's loop (src/slam_frontend.cc:424-434, :467-470) produces."""
+    n, W = 1300, 3
+    frames = [synth.synth_pose(n - 53 * (p % 4), p, 130, 17) for p in range(9)]
+    frames[5] = frames[5][:0]                       # an empty frame in the middle of the stream
+    bp = restate.BEST_PERCENT
+    depth = 4                                       # VSF_PIPELINE_DEPTH
+    import vision_slam_frontend_b200 as vsf
+    with new_ctx(window=W) as ctx:
+        ctx.set_engine(engine, 0)
+        with pytest.raises(vsf.VsfError) as e:
+            ctx.window_collect()
+        assert e.value.code == 4                    # VSF_ERR_STATE: nothing in flight
+        live, expected, submitted, collected = [], [], 0, 0
+
+        def check_one():
+            fid, got = ctx.window_collect()
+            efid, elive, D = expected.pop(0)
+            assert fid == efid and len(got) == len(elive)
+            for (pfid, pairs), (pid, past) in zip(got, elive):
+                assert pfid == pid
+                m = native.get_matches(past, D, RATIO)
+                keep = restate.num_good_matches(len(m), bp)
+                assert len(pairs) == keep
+                order = restate.sort_order_stdsort(m) if sort_mode == 1 else restate.sort_order_stable(m)
+                exp = m[order][:keep]
+                np.testing.assert_array_equal(pairs[:, 0], exp["queryIdx"].astype(np.uint64))
+                np.testing.assert_array_equal(pairs[:, 1], exp["trainIdx"].astype(np.uint64))
+
+        for p, D in enumerate(frames):
+            if ctx.window_in_flight() == depth:
+                with pytest.raises(vsf.VsfError) as e:
+                    ctx.window_submit(100 + p, D, RATIO, float(bp), sort_mode)
+                assert e.value.code == 4            # full: collect first
+                check_one()
+                collected += 1
+            ctx.window_submit(100 + p, D, RATIO, float(bp), sort_mode)
+            submitted += 1
+            expected.append((100 + p, list(live), D))
+            if len(live) >= W:
+                live.pop(0)
+            live.append((100 + p, D))
+            assert ctx.window_size() == len(live)
+            assert ctx.window_in_flight() == submitted - collected
+        while expected:
+            check_one()
+        assert ctx.window_in_flight() == 0
+
+
 def test_window_c4_full_size(vsf_ctx):
     """BASELINE config 4's per-pose shape: 5000 features against 10 prior frames."""
     n, W = 5000, 10

@@ -79,6 +79,10 @@ def load_library():
         "vsf_window_size": ([vp], i),
         "vsf_window_match": ([vp, vp, i, sz, d, vp, vp, vp, i, C.POINTER(i)], i),
         "vsf_window_feature_matches": ([vp, vp, i, sz, d, f, i, vp, vp, vp, i, C.POINTER(i)], i),
+        "vsf_window_submit": ([vp, u64, vp, i, sz, d, f, i], i),
+        "vsf_window_collect": ([vp, C.POINTER(u64), vp, vp, vp, i, C.POINTER(i)], i),
+        "vsf_window_in_flight": ([vp], i),
+        "vsf_window_last_transfer": ([vp, C.POINTER(sz), C.POINTER(sz)], i),
         "vsf_stereo_filter": ([vp, vp, vp, i, sz, vp, vp, i, sz, vp, d, vp, vp,
                                C.POINTER(i), vp, vp, C.POINTER(i)], i),
         "vsf_set_stereo_threshold": ([vp, f], i),
@@ -106,7 +110,8 @@ EXPORTED_SYMBOLS = [
     "vsf_synchronize", "vsf_set_tuning", "vsf_set_engine", "vsf_last_engine", "vsf_set_profile",
     "vsf_last_kernel_times", "vsf_knn2", "vsf_get_matches", "vsf_window_push",
     "vsf_window_commit", "vsf_window_clear", "vsf_window_size", "vsf_window_match",
-    "vsf_window_feature_matches", "vsf_stereo_filter", "vsf_set_stereo_threshold",
+    "vsf_window_feature_matches", "vsf_window_submit", "vsf_window_collect",
+    "vsf_window_in_flight", "vsf_window_last_transfer", "vsf_stereo_filter", "vsf_set_stereo_threshold",
     "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_observe_features",
     "vsf_device_row_bytes", "vsf_window_match_device", "vsf_fetch_window",
     "vsf_synth_sequence_device", "vsf_probe_pipe", "vsf_device_sm_count",
@@ -255,6 +260,40 @@ class Context:
             res.append((int(fids[j]), np.stack([fm["feature_idx_initial"],
                                                 fm["feature_idx_current"]], 1).reshape(-1, 2)))
         return res
+
+    # pipelined form: submit frames ahead, collect their FeatureMatch lists in order
+    def window_submit(self, frame_id: int, D: np.ndarray, ratio: float, best_percent: float,
+                      sort_mode: int = 1):
+        D = _u8rows(D)
+        self._check(self._L.vsf_window_submit(self._h, frame_id, _ptr(D), len(D), D.strides[0],
+                                              float(ratio), float(best_percent), sort_mode))
+
+    def window_last_transfer(self):
+        """(h2d_bytes, d2h_bytes) of the most recent window call."""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._L.vsf_window_last_transfer(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def window_in_flight(self) -> int:
+        return self._L.vsf_window_in_flight(self._h)
+
+    def window_collect(self):
+        """-> (frame_id, [(past_frame_id, (m,2) uint64 [initial, current]), ...]) of the
+        oldest submitted frame."""
+        cap = self.max_features
+        fids = np.zeros(self.window, np.uint64)
+        counts = np.zeros(self.window, np.int32)
+        out = np.zeros((self.window, cap), FEATURE_MATCH_DTYPE)
+        nf = C.c_int(0)
+        fid = C.c_uint64(0)
+        self._check(self._L.vsf_window_collect(self._h, C.byref(fid), _ptr(fids), _ptr(counts),
+                                               _ptr(out), cap, C.byref(nf)))
+        res = []
+        for j in range(nf.value):
+            fm = out[j, :counts[j]]
+            res.append((int(fids[j]), np.stack([fm["feature_idx_initial"],
+                                                fm["feature_idx_current"]], 1).reshape(-1, 2)))
+        return int(fid.value), res
 
     # -- a5 ---------------------------------------------------------------------------
     def stereo_filter(self, kp_left, desc_left, kp_right, desc_right, F, ratio: float):

@@ -111,6 +111,32 @@ struct vsf_ctx {
   std::deque<int> live;   // slot indices, oldest first
   int staging_slot = 0;
   int last_n_frames = 0;  // of the last vsf_window_match_device
+  // where mirrored launches store their match lists / counts (the ctx's own mapped buffers, or
+  // those of a pipelined submission)
+  vsf_dmatch* mir_dm = nullptr;
+  int* mir_dcounts = nullptr;
+  int* mir_hcounts = nullptr;
+  // pipelined window matching (vsf_window_submit / vsf_window_collect): buffers allocated on
+  // first use, one set per frame in flight
+  struct Flight {
+    cudaEvent_t done = nullptr;
+    uint8_t* h_desc = nullptr;          // pinned staging of the submitted frame
+    vsf_dmatch* h_matches = nullptr;    // mapped: [window][rows_pad] ratio survivors (sort_mode 1)
+    vsf_feature_match* h_fm = nullptr;  // mapped: [window][rows_pad] sorted + cut (sort_mode 0)
+    int* h_counts = nullptr;            // mapped: [kMaxProblems]
+    vsf_dmatch* dm_matches = nullptr;   // device-side aliases
+    vsf_feature_match* dm_fm = nullptr;
+    int* dm_counts = nullptr;
+    int nf = 0, sort_mode = 1;
+    float best_percent = 1.f;
+    uint64_t frame_id = 0;
+    uint64_t fids[kMaxProblems];
+    size_t h2d_bytes = 0;
+  };
+  Flight flights[VSF_PIPELINE_DEPTH];
+  size_t last_h2d = 0, last_d2h = 0;   // PCIe bytes of the most recent window call (vsf_window_last_transfer)
+  bool flights_ready = false;
+  int flight_head = 0, flight_count = 0;   // FIFO: oldest = flights[flight_head]
 
   uint8_t* slot_ptr(int s) const { return d_ring + size_t(s) * rows_pad * row_bytes; }
   vsf_dmatch* region_ptr(int r) const { return d_matches + size_t(r) * rows_pad; }
@@ -147,10 +173,9 @@ static void commit_staging(vsf_ctx* c, uint64_t frame_id, int count) {
 
 // Pack caller rows (stride apart, desc_bytes wide) into pinned staging padded to
 // row_bytes, then one async H2D copy.
-static int upload_desc(vsf_ctx* c, int which, const uint8_t* src, int n, size_t stride,
+static int upload_desc(vsf_ctx* c, uint8_t* h, const uint8_t* src, int n, size_t stride,
                        uint8_t* d_dst) {
   if (n == 0) return VSF_OK;
-  uint8_t* h = c->h_desc[which];
   if (stride == size_t(c->row_bytes) && c->desc_bytes == c->row_bytes) {
     std::memcpy(h, src, size_t(n) * c->row_bytes);
   } else {
@@ -162,6 +187,11 @@ static int upload_desc(vsf_ctx* c, int which, const uint8_t* src, int n, size_t 
   }
   VSF_CUDA(c, cudaMemcpyAsync(d_dst, h, size_t(n) * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
   return VSF_OK;
+}
+
+static int upload_desc(vsf_ctx* c, int which, const uint8_t* src, int n, size_t stride,
+                       uint8_t* d_dst) {
+  return upload_desc(c, c->h_desc[which], src, n, stride, d_dst);
 }
 
 static int upload_xy(vsf_ctx* c, int which, const vsf_keypoint* kp, int n, float2* d_dst) {
@@ -187,8 +217,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   b.qblock_pass = c->d_qblock_pass;
   b.problem_arrivals = c->d_problem_arrivals;
   if (mirror) {
-    b.host_matches = c->dm_matches;
-    b.host_counts = c->dm_region_counts;
+    b.host_matches = c->mir_dm;
+    b.host_counts = c->mir_dcounts;
     b.host_region_stride = c->rows_pad;
   }
   int row0 = 0, qb0 = 0, max_nq = 0, max_nt = 0;
@@ -219,7 +249,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     // nothing to match: every problem reports zero survivors
     for (int i = 0; i < b.num_problems; ++i) {
       VSF_CUDA(c, cudaMemsetAsync(c->d_match_count + specs[i].region, 0, sizeof(int), c->stream));
-      if (mirror) c->h_region_counts[specs[i].region] = 0;   // no kernel will write it
+      if (mirror) c->mir_hcounts[specs[i].region] = 0;   // no kernel will write it
     }
     return VSF_OK;
   }
@@ -351,6 +381,12 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
                   c->h_scalar, c->h_fm};
   for (void* p : host)
     if (p) cudaFreeHost(p);
+  for (vsf_ctx::Flight& f : c->flights) {
+    void* fh[] = {f.h_desc, f.h_matches, f.h_fm, f.h_counts};
+    for (void* p : fh)
+      if (p) cudaFreeHost(p);
+    if (f.done) cudaEventDestroy(f.done);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (cudaEvent_t e : c->pev)
@@ -470,6 +506,9 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
       return VSF_ERR_CUDA;
     }
     std::memset(c->h_region_counts, 0, kMaxProblems * sizeof(int));
+    c->mir_dm = c->dm_matches;
+    c->mir_dcounts = c->dm_region_counts;
+    c->mir_hcounts = c->h_region_counts;
   }
   VSF_ALLOC_HOST(c, c->h_resid, N * sizeof(float));
   VSF_ALLOC_HOST(c, c->h_X4, N * sizeof(float4));
@@ -642,11 +681,12 @@ extern "C" int vsf_window_commit(vsf_ctx* c, uint64_t frame_id, int n) {
   return VSF_OK;
 }
 
-static int window_launch(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio, bool mirror) {
+static int window_launch(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio, bool mirror,
+                         uint8_t* h_staging = nullptr) {
   if (n < 0 || (n > 0 && !desc) || (n > 0 && stride < size_t(c->desc_bytes))) return fail(c, VSF_ERR_BAD_ARG, "bad frame");
   if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
   cudaSetDevice(c->device);
-  int rc = upload_desc(c, 0, desc, n, stride, c->slot_ptr(c->staging_slot));
+  int rc = upload_desc(c, h_staging ? h_staging : c->h_desc[0], desc, n, stride, c->slot_ptr(c->staging_slot));
   if (rc) return rc;
   std::vector<ProblemSpec> specs;
   int j = 0;
@@ -690,13 +730,23 @@ extern "C" int vsf_window_match(vsf_ctx* c, const uint8_t* desc, int n, size_t s
   const int nf = int(c->live.size());
   if ((rc = sync_mirrored(c, nf, 0))) return rc;
   *n_frames = nf;
+  c->last_h2d = size_t(n) * c->row_bytes;
+  c->last_d2h = 0;
   for (int j = 0; j < nf; ++j) {
     const int cnt = c->h_counts[j];
+    c->last_d2h += size_t(cnt) * sizeof(vsf_dmatch) + sizeof(int);
     if (cnt > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
     counts[j] = cnt;
     if (frame_ids) frame_ids[j] = c->slot_frame[c->live[j]];
     if (cnt) std::memcpy(out + size_t(j) * cap_per_frame, c->h_matches + size_t(j) * c->rows_pad, size_t(cnt) * sizeof(vsf_dmatch));
   }
+  return VSF_OK;
+}
+
+extern "C" int vsf_window_last_transfer(const vsf_ctx* c, size_t* h2d_bytes, size_t* d2h_bytes) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (h2d_bytes) *h2d_bytes = c->last_h2d;
+  if (d2h_bytes) *d2h_bytes = c->last_d2h;
   return VSF_OK;
 }
 
@@ -738,8 +788,11 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
                                       cudaMemcpyDeviceToHost, c->stream));
       VSF_CUDA(c, cudaStreamSynchronize(c->stream));
     }
+    c->last_h2d = size_t(n) * c->row_bytes;
+    c->last_d2h = 0;
     for (int j = 0; j < nf; ++j) {
       const int cnt = c->h_counts[j];
+      c->last_d2h += size_t(cnt) * sizeof(vsf_feature_match) + sizeof(int);
       if (cnt > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
       counts[j] = cnt;
       if (frame_ids) frame_ids[j] = c->slot_frame[c->live[j]];
@@ -751,7 +804,10 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
   // frame pair per host thread (each list is sorted by the same single-threaded
   // std::sort the reference runs, so the order inside every list is unchanged).
   if ((rc = sync_mirrored(c, nf, 0))) return rc;
+  c->last_h2d = size_t(n) * c->row_bytes;
+  c->last_d2h = 0;
   for (int j = 0; j < nf; ++j) {
+    c->last_d2h += size_t(c->h_counts[j]) * sizeof(vsf_dmatch) + sizeof(int);   // the whole survivor list is mirrored
     const int good = int(float(size_t(c->h_counts[j])) * best_percent);
     if (good > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
     counts[j] = good;
@@ -762,6 +818,114 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
   for (int j = 0; j < nf; ++j) {
     vsf_dmatch* m = c->h_matches + size_t(j) * c->rows_pad;
     std::sort(m, m + c->h_counts[j], ByDistance());
+    vsf_feature_match* o = out + size_t(j) * cap_per_frame;
+    for (int i = 0; i < counts[j]; ++i) {
+      o[i].feature_idx_initial = uint64_t(m[i].queryIdx);
+      o[i].feature_idx_current = uint64_t(m[i].trainIdx);
+    }
+  }
+  return VSF_OK;
+}
+
+// ------------------------------------------------- pipelined window matching (a3/a4, frame stream)
+
+static int flights_init(vsf_ctx* c) {
+  if (c->flights_ready) return VSF_OK;
+  cudaSetDevice(c->device);
+  const size_t N = size_t(c->rows_pad);
+  for (vsf_ctx::Flight& f : c->flights) {
+    VSF_CUDA(c, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_desc), N * c->row_bytes));
+    VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_matches), size_t(c->window) * N * sizeof(vsf_dmatch), cudaHostAllocMapped));
+    VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_fm), size_t(c->window) * N * sizeof(vsf_feature_match), cudaHostAllocMapped));
+    VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_counts), kMaxProblems * sizeof(int), cudaHostAllocMapped));
+    VSF_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&f.dm_matches), f.h_matches, 0));
+    VSF_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&f.dm_fm), f.h_fm, 0));
+    VSF_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&f.dm_counts), f.h_counts, 0));
+    std::memset(f.h_counts, 0, kMaxProblems * sizeof(int));
+  }
+  c->flights_ready = true;
+  return VSF_OK;
+}
+
+extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_count : 0; }
+
+extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* desc, int n, size_t stride,
+                                 double ratio, float best_percent, int sort_mode) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (sort_mode != 0 && sort_mode != 1) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 or 1");
+  if (c->flight_count >= VSF_PIPELINE_DEPTH)
+    return fail(c, VSF_ERR_STATE, "VSF_PIPELINE_DEPTH frames already in flight: call vsf_window_collect first");
+  int rc = flights_init(c);
+  if (rc) return rc;
+  vsf_ctx::Flight& f = c->flights[(c->flight_head + c->flight_count) % VSF_PIPELINE_DEPTH];
+  const int nf = int(c->live.size());
+  f.nf = nf;
+  f.sort_mode = sort_mode;
+  f.best_percent = best_percent;
+  f.frame_id = frame_id;
+  f.h2d_bytes = size_t(std::max(n, 0)) * c->row_bytes;
+  for (int j = 0; j < nf; ++j) f.fids[j] = c->slot_frame[c->live[j]];
+  // the kernels of this submission mirror into the flight's own mapped buffers
+  c->mir_dm = f.dm_matches;
+  c->mir_dcounts = f.dm_counts;
+  c->mir_hcounts = f.h_counts;
+  rc = window_launch(c, desc, n, stride, ratio, sort_mode == 1, f.h_desc);
+  c->mir_dm = c->dm_matches;
+  c->mir_dcounts = c->dm_region_counts;
+  c->mir_hcounts = c->h_region_counts;
+  if (rc) return rc;
+  if (sort_mode == 0 && nf > 0) {
+    // stable device sort + cut, written straight into the flight's mapped host buffers
+    const vsf_dmatch* mp[kMaxProblems];
+    const int* cp[kMaxProblems];
+    for (int j = 0; j < nf; ++j) {
+      mp[j] = c->region_ptr(j);
+      cp[j] = c->d_match_count + j;
+    }
+    VSF_CUDA(c, launch_sort_cut(mp, cp, nf, best_percent, f.dm_fm, c->rows_pad, f.dm_counts, c->max_features, c->stream));
+  }
+  VSF_CUDA(c, cudaEventRecord(f.done, c->stream));
+  commit_staging(c, frame_id, n);   // eviction + push (src/slam_frontend.cc:467-470)
+  ++c->flight_count;
+  return VSF_OK;
+}
+
+extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* frame_ids, int* counts,
+                                  vsf_feature_match* out, int cap_per_frame, int* n_frames) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!n_frames || !counts || cap_per_frame < 0 || (cap_per_frame > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
+  if (c->flight_count == 0) return fail(c, VSF_ERR_STATE, "no submitted frame to collect");
+  cudaSetDevice(c->device);
+  vsf_ctx::Flight& f = c->flights[c->flight_head];
+  VSF_CUDA(c, cudaEventSynchronize(f.done));
+  // the flight is consumed whatever happens next
+  c->flight_head = (c->flight_head + 1) % VSF_PIPELINE_DEPTH;
+  --c->flight_count;
+  const int nf = f.nf;
+  *n_frames = nf;
+  if (frame_id) *frame_id = f.frame_id;
+  c->last_h2d = f.h2d_bytes;
+  c->last_d2h = 0;
+  for (int j = 0; j < nf; ++j) {
+    c->last_d2h += size_t(f.h_counts[j]) * 16 + sizeof(int);   // vsf_dmatch and vsf_feature_match are both 16 B
+    // sort_mode 0: the kernel already stored int(count * best_percent); sort_mode 1: the cut of
+    // src/slam_frontend.cc:290 in float, like the reference
+    const int keep = f.sort_mode == 0 ? f.h_counts[j] : int(float(size_t(f.h_counts[j])) * f.best_percent);
+    if (keep > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
+    counts[j] = keep;
+    if (frame_ids) frame_ids[j] = f.fids[j];
+  }
+  if (f.sort_mode == 0) {
+    for (int j = 0; j < nf; ++j)
+      if (counts[j]) std::memcpy(out + size_t(j) * cap_per_frame, f.h_fm + size_t(j) * c->rows_pad, size_t(counts[j]) * sizeof(vsf_feature_match));
+    return VSF_OK;
+  }
+  const int nthreads = std::max(1, std::min(nf, c->host_threads));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (int j = 0; j < nf; ++j) {
+    vsf_dmatch* m = f.h_matches + size_t(j) * c->rows_pad;
+    std::sort(m, m + f.h_counts[j], ByDistance());   // the reference's own call (src/slam_frontend.cc:289)
     vsf_feature_match* o = out + size_t(j) * cap_per_frame;
     for (int i = 0; i < counts[j]; ++i) {
       o[i].feature_idx_initial = uint64_t(m[i].queryIdx);
