@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-lag", type=int, default=2,
+    ap.add_argument("--e2e-lag", type=int, default=3,
                     help="frames submitted ahead of the one being collected in the pipelined e2e leg (1..3)")
     ap.add_argument("--popc-mode", type=int, default=-1)
     ap.add_argument("--split", type=int, default=0)
@@ -283,6 +283,9 @@ def run_b200(a):
     ctx.set_stream(stream.cuda_stream)
     ctx.set_tuning(a.popc_mode, a.split, a.qpt, a.variant)
     ctx.set_engine(a.engine, 0)
+    # host threads for the reference's std::sort (e2e leg): the ranks of one box share its cores
+    host_threads = max(2, min(16, (os.cpu_count() or 16) // world))
+    ctx.set_host_threads(host_threads)
 
     # ---- device-resident sequence: this rank's pose range, larger than L2 ----------------
     frame_bytes = n * 32
@@ -472,11 +475,13 @@ def measure_e2e(a, ctx, seq, n, W, K, WU, world, dist, torch):
         if rc:
             raise RuntimeError(L.vsf_last_error(ctx._h).decode())
 
-    def timed(step, drain=None):
+    def timed(step, drain=None, after_warmup=None):
         for t in range(WU):
             step(t)
         if drain:
             drain()
+        if after_warmup:
+            after_warmup()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -526,18 +531,28 @@ def measure_e2e(a, ctx, seq, n, W, K, WU, world, dist, torch):
 
         def step(t):
             D = hp[W + t]
-            check(L.vsf_window_submit(ctx._h, W + t, D.ctypes.data, n, 32, RATIO, BEST_PERCENT, sort_mode))
+            t0 = time.perf_counter()
+            check(L.vsf_window_submit(ctx._h, W + t, D.ctypes.data, n, 32, RATIO, BEST_PERCENT, sort_mode,
+                                      1))   # VSF_SUBMIT_PINNED_DESC: hp is page-locked
+            t1 = time.perf_counter()
             if L.vsf_window_in_flight(ctx._h) > lag:
                 collect()
+            acc["submit_s"] = acc.get("submit_s", 0.0) + (t1 - t0)
+            acc["collect_s"] = acc.get("collect_s", 0.0) + (time.perf_counter() - t1)
 
         def drain():
             while L.vsf_window_in_flight(ctx._h) > 0:
                 collect()
 
-        el = timed(step, drain)
-        assert acc["collected"] == Ke + WU
+        def reset():
+            acc.update(d2h=0, collected=0, submit_s=0.0, collect_s=0.0)
+
+        el = timed(step, drain, reset)
+        assert acc["collected"] == Ke
         res[key] = {"value": world * Ke * W * n * n / el, "ms_per_step": 1e3 * el / Ke,
-                    "d2h_bytes_per_step": acc["d2h"] / (Ke + WU), "frames_in_flight": lag + 1}
+                    "d2h_bytes_per_step": acc["d2h"] / Ke, "frames_in_flight": lag + 1,
+                    "host_submit_us_per_step": 1e6 * acc["submit_s"] / Ke,
+                    "host_collect_us_per_step": 1e6 * acc["collect_s"] / Ke}
 
     # headline e2e: pipelined, bit-identical order (host std::sort, like the reference)
     head = res["pipelined_exact_stdsort"]
@@ -548,6 +563,7 @@ def measure_e2e(a, ctx, seq, n, W, K, WU, world, dist, torch):
                    "bit-identical order), pinned host buffers; every step's H2D, kernels, D2H, sort + cut "
                    "inside the timed region" % (lag + 1),
             "matched_frame_pairs_per_s": head["value"] / (n * n),
+            "host_threads": max(2, min(16, (os.cpu_count() or 16) // world)),
             "variants": res}
 
 

@@ -187,21 +187,32 @@ int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
  * window (:467-470) and returns WITHOUT waiting for the device.  The match
  * lists of frame t do not feed frame t+1 (only its descriptors do), so up to
  * VSF_PIPELINE_DEPTH frames may be in flight: the host sorts and consumes the
- * lists of frame t while the device matches frame t+1.  desc is copied to
- * pinned staging before the call returns.
+ * lists of frame t while the device matches frame t+1 (sort_mode 1: on the
+ * library's worker threads, the lists of all frames in flight concurrently).
+ * desc is copied to pinned staging before the call returns, unless flags has
+ * VSF_SUBMIT_PINNED_DESC: the caller then promises that desc is page-locked
+ * (cudaHostAlloc / cudaHostRegister), holds 32- or 64-byte rows back to back,
+ * and stays unchanged until the frame has been collected; the copy engine
+ * reads it in place.  Uploads, kernels and downloads run on three streams:
+ * frame t+1 is uploaded and frame t-1 downloaded while frame t is matched.
  * vsf_window_collect waits for the OLDEST submitted frame and returns exactly
  * what vsf_window_feature_matches would have returned for it (same argument
  * meaning; *frame_id = the id given at submit; sort_mode / best_percent are the
  * ones given at submit).  VSF_ERR_STATE: submit with VSF_PIPELINE_DEPTH frames
  * in flight, or collect with none. */
 #define VSF_PIPELINE_DEPTH 4
+#define VSF_SUBMIT_PINNED_DESC 1
 int vsf_window_submit(vsf_ctx* ctx, uint64_t frame_id, const uint8_t* desc, int n,
                       size_t stride, double nn_match_ratio, float best_percent,
-                      int sort_mode);
+                      int sort_mode, int flags);
 int vsf_window_collect(vsf_ctx* ctx, uint64_t* frame_id, uint64_t* frame_ids,
                        int* counts, vsf_feature_match* out, int cap_per_frame,
                        int* n_frames);
 int vsf_window_in_flight(const vsf_ctx* ctx);
+/* Host threads the library may use for the reference's std::sort of sort_mode 1
+ * (default: min(16, hardware threads)); set it to cores / ranks when several
+ * ranks share one host.  Call before the first vsf_window_submit. */
+int vsf_set_host_threads(vsf_ctx* ctx, int n);
 
 /* Bytes that crossed PCIe for the most recent vsf_window_match /
  * vsf_window_feature_matches / vsf_window_collect call: the uploaded descriptor

@@ -195,14 +195,19 @@ def test_window_feature_matches(sort_mode):
             live.append((p, D))
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("sort_mode", [0, 1])
-def test_window_pipelined_submit_collect(sort_mode, engine):
+def test_window_pipelined_submit_collect(sort_mode, engine, pinned):
     """vsf_window_submit / vsf_window_collect with several frames in flight return, frame by
     frame, what the reference's loop (src/slam_frontend.cc:424-434, :467-470) produces."""
     n, W = 1300, 3
     frames = [synth.synth_pose(n - 53 * (p % 4), p, 130, 17) for p in range(9)]
     frames[5] = frames[5][:0]                       # an empty frame in the middle of the stream
+    if pinned:                                      # VSF_SUBMIT_PINNED_DESC: page-locked rows, read in place
+        import torch
+        keep_alive = [torch.from_numpy(np.ascontiguousarray(D)).pin_memory() for D in frames]
+        frames = [t.numpy() for t in keep_alive]
     bp = restate.BEST_PERCENT
     depth = 4                                       # VSF_PIPELINE_DEPTH
     import vision_slam_frontend_b200 as vsf
@@ -230,11 +235,11 @@ def test_window_pipelined_submit_collect(sort_mode, engine):
         for p, D in enumerate(frames):
             if ctx.window_in_flight() == depth:
                 with pytest.raises(vsf.VsfError) as e:
-                    ctx.window_submit(100 + p, D, RATIO, float(bp), sort_mode)
+                    ctx.window_submit(100 + p, D, RATIO, float(bp), sort_mode, pinned)
                 assert e.value.code == 4            # full: collect first
                 check_one()
                 collected += 1
-            ctx.window_submit(100 + p, D, RATIO, float(bp), sort_mode)
+            ctx.window_submit(100 + p, D, RATIO, float(bp), sort_mode, pinned)
             submitted += 1
             expected.append((100 + p, list(live), D))
             if len(live) >= W:

@@ -79,9 +79,10 @@ def load_library():
         "vsf_window_size": ([vp], i),
         "vsf_window_match": ([vp, vp, i, sz, d, vp, vp, vp, i, C.POINTER(i)], i),
         "vsf_window_feature_matches": ([vp, vp, i, sz, d, f, i, vp, vp, vp, i, C.POINTER(i)], i),
-        "vsf_window_submit": ([vp, u64, vp, i, sz, d, f, i], i),
+        "vsf_window_submit": ([vp, u64, vp, i, sz, d, f, i, i], i),
         "vsf_window_collect": ([vp, C.POINTER(u64), vp, vp, vp, i, C.POINTER(i)], i),
         "vsf_window_in_flight": ([vp], i),
+        "vsf_set_host_threads": ([vp, i], i),
         "vsf_window_last_transfer": ([vp, C.POINTER(sz), C.POINTER(sz)], i),
         "vsf_stereo_filter": ([vp, vp, vp, i, sz, vp, vp, i, sz, vp, d, vp, vp,
                                C.POINTER(i), vp, vp, C.POINTER(i)], i),
@@ -111,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "vsf_last_kernel_times", "vsf_knn2", "vsf_get_matches", "vsf_window_push",
     "vsf_window_commit", "vsf_window_clear", "vsf_window_size", "vsf_window_match",
     "vsf_window_feature_matches", "vsf_window_submit", "vsf_window_collect",
-    "vsf_window_in_flight", "vsf_window_last_transfer", "vsf_stereo_filter", "vsf_set_stereo_threshold",
+    "vsf_window_in_flight", "vsf_set_host_threads", "vsf_window_last_transfer", "vsf_stereo_filter", "vsf_set_stereo_threshold",
     "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_observe_features",
     "vsf_device_row_bytes", "vsf_window_match_device", "vsf_fetch_window",
     "vsf_synth_sequence_device", "vsf_probe_pipe", "vsf_device_sm_count",
@@ -263,16 +264,22 @@ class Context:
 
     # pipelined form: submit frames ahead, collect their FeatureMatch lists in order
     def window_submit(self, frame_id: int, D: np.ndarray, ratio: float, best_percent: float,
-                      sort_mode: int = 1):
+                      sort_mode: int = 1, pinned: bool = False):
+        """pinned=True: D is page-locked, row-contiguous at the device row width and stays
+        untouched until the frame is collected (VSF_SUBMIT_PINNED_DESC)."""
         D = _u8rows(D)
         self._check(self._L.vsf_window_submit(self._h, frame_id, _ptr(D), len(D), D.strides[0],
-                                              float(ratio), float(best_percent), sort_mode))
+                                              float(ratio), float(best_percent), sort_mode,
+                                              1 if pinned else 0))
 
     def window_last_transfer(self):
         """(h2d_bytes, d2h_bytes) of the most recent window call."""
         a, b = C.c_size_t(0), C.c_size_t(0)
         self._check(self._L.vsf_window_last_transfer(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def set_host_threads(self, n: int):
+        self._check(self._L.vsf_set_host_threads(self._h, n))
 
     def window_in_flight(self) -> int:
         return self._L.vsf_window_in_flight(self._h)

@@ -2,10 +2,13 @@
 // staging and the launch sequences.  No CPU fallback anywhere: if CUDA is unavailable
 // every entry point reports VSF_ERR_CUDA.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -105,11 +108,15 @@ struct vsf_ctx {
   float* h_tri_io = nullptr;
   float* h_scalar = nullptr;
   vsf_feature_match* h_fm = nullptr;
+  uint32_t* h_keys = nullptr;   // plain host scratch for the host sort (allocated on first use)
   // sliding window (frame_list_) state
   std::vector<int> slot_count;
   std::vector<uint64_t> slot_frame;
   std::deque<int> live;   // slot indices, oldest first
+  std::deque<int> free_slots;   // FIFO: a slot evicted at frame t is reused for frame t+2, so the
+                                // upload of frame t+1 never touches rows the kernels of frame t read
   int staging_slot = 0;
+  int ring_slots = 0;     // window + 2
   int last_n_frames = 0;  // of the last vsf_window_match_device
   // where mirrored launches store their match lists / counts (the ctx's own mapped buffers, or
   // those of a pipelined submission)
@@ -119,27 +126,56 @@ struct vsf_ctx {
   // pipelined window matching (vsf_window_submit / vsf_window_collect): buffers allocated on
   // first use, one set per frame in flight
   struct Flight {
-    cudaEvent_t done = nullptr;
+    cudaEvent_t ev_up = nullptr;        // upload stream: the frame's rows are in the ring
+    cudaEvent_t ev_chain = nullptr;     // main stream: the kernels of this frame have finished
+    cudaEvent_t done = nullptr;         // download stream: the lists are in host memory
     uint8_t* h_desc = nullptr;          // pinned staging of the submitted frame
-    vsf_dmatch* h_matches = nullptr;    // mapped: [window][rows_pad] ratio survivors (sort_mode 1)
-    vsf_feature_match* h_fm = nullptr;  // mapped: [window][rows_pad] sorted + cut (sort_mode 0)
-    int* h_counts = nullptr;            // mapped: [kMaxProblems]
-    vsf_dmatch* dm_matches = nullptr;   // device-side aliases
-    vsf_feature_match* dm_fm = nullptr;
-    int* dm_counts = nullptr;
+    vsf_dmatch* d_matches = nullptr;    // device: [window][rows_pad] ratio survivors of this frame
+    vsf_feature_match* d_fm = nullptr;  // device: [window][rows_pad] sorted + cut (sort_mode 0)
+    vsf_dmatch* h_matches = nullptr;    // pinned copy of d_matches (sort_mode 1)
+    vsf_feature_match* h_fm = nullptr;  // pinned copy of d_fm (sort_mode 0) / output of the host sort
+    int* h_counts = nullptr;            // mapped: [kMaxProblems], written by the kernels
+    int* dm_counts = nullptr;           // its device-side alias
+    size_t d2h_bytes = 0;
     int nf = 0, sort_mode = 1;
     float best_percent = 1.f;
     uint64_t frame_id = 0;
     uint64_t fids[kMaxProblems];
     size_t h2d_bytes = 0;
+    // host-side finish of sort_mode 1 (worker threads): per past frame the kept count, pending
+    // = lists not finished yet (+1 while the device is still running)
+    uint32_t* keys = nullptr;           // [window][rows_pad] packed (distance, position) sort keys
+    int keep[kMaxProblems];
+    std::atomic<int> pending{0};
+    int cuda_error = 0;
   };
+  struct SortTask {
+    Flight* f;
+    int list;   // sort + cut that past frame's list
+  };
+  // One dispatcher thread waits for each submitted frame's download and turns its lists into
+  // tasks for the workers.  Three separate locks so that the caller's thread (submit / collect)
+  // never queues behind the workers: disp_* (caller -> dispatcher), pool_* (dispatcher ->
+  // workers), done_* (workers -> caller).
+  std::vector<std::thread> workers;
+  std::thread dispatcher;
+  std::mutex disp_mu, pool_mu, done_mu;
+  std::condition_variable disp_cv, pool_cv, done_cv;
+  std::deque<Flight*> disp_q;
+  std::deque<SortTask> pool_q;
+  bool pool_stop = false;
   Flight flights[VSF_PIPELINE_DEPTH];
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;   // copy engines of the pipelined path
+  cudaEvent_t ev_main = nullptr;
+  bool main_dirty = false;   // non-pipelined kernels launched since the last submit may still read the ring
+  std::vector<cudaEvent_t> slot_last_chain;   // per ring slot: ev_chain of the last pipelined frame that read it
   size_t last_h2d = 0, last_d2h = 0;   // PCIe bytes of the most recent window call (vsf_window_last_transfer)
   bool flights_ready = false;
   int flight_head = 0, flight_count = 0;   // FIFO: oldest = flights[flight_head]
 
+  vsf_dmatch* match_base = nullptr;   // d_matches, or the device buffer of a pipelined submission
   uint8_t* slot_ptr(int s) const { return d_ring + size_t(s) * rows_pad * row_bytes; }
-  vsf_dmatch* region_ptr(int r) const { return d_matches + size_t(r) * rows_pad; }
+  vsf_dmatch* region_ptr(int r) const { return match_base + size_t(r) * rows_pad; }
 };
 
 #define VSF_CUDA(ctx, expr)                                                             \
@@ -156,19 +192,24 @@ static int fail(vsf_ctx* ctx, int code, const char* msg) {
   return code;
 }
 
-static int pick_free_slot(const vsf_ctx* c) {
-  for (int s = 0; s <= c->window; ++s)
-    if (std::find(c->live.begin(), c->live.end(), s) == c->live.end()) return s;
-  return 0;
+static void reset_ring(vsf_ctx* c) {
+  c->live.clear();
+  c->free_slots.clear();
+  c->staging_slot = 0;
+  for (int s = 1; s < c->ring_slots; ++s) c->free_slots.push_back(s);
 }
 
 // frame_list_ eviction + push (src/slam_frontend.cc:467-470)
 static void commit_staging(vsf_ctx* c, uint64_t frame_id, int count) {
-  if (int(c->live.size()) >= c->window) c->live.pop_front();
+  if (int(c->live.size()) >= c->window) {
+    c->free_slots.push_back(c->live.front());
+    c->live.pop_front();
+  }
   c->slot_count[c->staging_slot] = count;
   c->slot_frame[c->staging_slot] = frame_id;
   c->live.push_back(c->staging_slot);
-  c->staging_slot = pick_free_slot(c);
+  c->staging_slot = c->free_slots.front();
+  c->free_slots.pop_front();
 }
 
 // Pack caller rows (stride apart, desc_bytes wide) into pinned staging padded to
@@ -206,6 +247,7 @@ static int upload_xy(vsf_ctx* c, int which, const vsf_keypoint* kp, int n, float
 // mirror: also store the match lists / counts into the mapped host buffers (host-API calls)
 static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio, bool mirror = false) {
   if (specs.empty()) return VSF_OK;
+  c->main_dirty = true;
   if (int(specs.size()) > kMaxProblems) return fail(c, VSF_ERR_CAPACITY, "too many problems in one batch");
   KnnBatch b;
   std::memset(&b, 0, sizeof(b));
@@ -369,6 +411,18 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  if (!c->workers.empty()) {
+    {
+      std::lock_guard<std::mutex> lk(c->disp_mu);
+      std::lock_guard<std::mutex> lk2(c->pool_mu);
+      c->pool_stop = true;
+    }
+    c->disp_cv.notify_all();
+    if (c->dispatcher.joinable()) c->dispatcher.join();   // drains its queue into the pool first
+    c->pool_cv.notify_all();
+    for (std::thread& t : c->workers) t.join();
+  }
+  std::free(c->h_keys);
   void* dev[] = {c->d_ring, c->d_raw_left, c->d_raw_right, c->d_right_c, c->d_xy_left, c->d_xy_right,
                  c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
@@ -381,12 +435,21 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
                   c->h_scalar, c->h_fm};
   for (void* p : host)
     if (p) cudaFreeHost(p);
+  if (c->up_stream) cudaStreamSynchronize(c->up_stream);
+  if (c->down_stream) cudaStreamSynchronize(c->down_stream);
   for (vsf_ctx::Flight& f : c->flights) {
     void* fh[] = {f.h_desc, f.h_matches, f.h_fm, f.h_counts};
     for (void* p : fh)
       if (p) cudaFreeHost(p);
-    if (f.done) cudaEventDestroy(f.done);
+    if (f.d_matches) cudaFree(f.d_matches);
+    if (f.d_fm) cudaFree(f.d_fm);
+    for (cudaEvent_t e : {f.ev_up, f.ev_chain, f.done})
+      if (e) cudaEventDestroy(e);
+    std::free(f.keys);
   }
+  if (c->ev_main) cudaEventDestroy(c->ev_main);
+  if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  if (c->down_stream) cudaStreamDestroy(c->down_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (cudaEvent_t e : c->pev)
@@ -450,7 +513,8 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
 
   const size_t N = size_t(c->rows_pad);
   const size_t rows_cap = size_t(c->regions) * N;
-  VSF_ALLOC(c, c->d_ring, size_t(window + 1) * N * c->row_bytes);
+  c->ring_slots = window + 2;
+  VSF_ALLOC(c, c->d_ring, size_t(c->ring_slots) * N * c->row_bytes);
   VSF_ALLOC(c, c->d_raw_left, N * c->row_bytes);
   VSF_ALLOC(c, c->d_raw_right, N * c->row_bytes);
   VSF_ALLOC(c, c->d_right_c, N * c->row_bytes);
@@ -469,6 +533,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   cudaMemset(c->d_qblock_pass, 0, qb_cap * sizeof(unsigned));
   cudaMemset(c->d_problem_arrivals, 0, kMaxProblems * sizeof(unsigned));
   VSF_ALLOC(c, c->d_matches, rows_cap * sizeof(vsf_dmatch));
+  c->match_base = c->d_matches;
   VSF_ALLOC(c, c->d_match_count, kMaxProblems * sizeof(int));
   cudaMemset(c->d_match_count, 0, kMaxProblems * sizeof(int));
   VSF_ALLOC(c, c->d_resid, N * sizeof(float));
@@ -520,9 +585,10 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
     const int v = std::atoi(e);
     if (v >= 0 && v <= 3 && (v < 2 || c->words == 8)) c->engine = v;
   }
-  c->slot_count.assign(window + 1, 0);
-  c->slot_frame.assign(window + 1, 0);
-  c->staging_slot = 0;
+  c->slot_count.assign(c->ring_slots, 0);
+  c->slot_frame.assign(c->ring_slots, 0);
+  c->slot_last_chain.assign(c->ring_slots, nullptr);
+  reset_ring(c);
   if (cudaDeviceSynchronize() != cudaSuccess) {
     vsf_destroy(c);
     return VSF_ERR_CUDA;
@@ -535,6 +601,8 @@ extern "C" int vsf_set_stream(vsf_ctx* c, void* cuda_stream) {
   if (!c) return VSF_ERR_BAD_ARG;
   cudaSetDevice(c->device);
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->up_stream));
+  if (c->down_stream) VSF_CUDA(c, cudaStreamSynchronize(c->down_stream));
   c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
   return VSF_OK;
 }
@@ -543,6 +611,8 @@ extern "C" int vsf_synchronize(vsf_ctx* c) {
   if (!c) return VSF_ERR_BAD_ARG;
   cudaSetDevice(c->device);
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->up_stream));
+  if (c->down_stream) VSF_CUDA(c, cudaStreamSynchronize(c->down_stream));
   return VSF_OK;
 }
 
@@ -657,8 +727,7 @@ extern "C" int vsf_window_size(const vsf_ctx* c) { return c ? int(c->live.size()
 
 extern "C" int vsf_window_clear(vsf_ctx* c) {
   if (!c) return VSF_ERR_BAD_ARG;
-  c->live.clear();
-  c->staging_slot = 0;
+  reset_ring(c);
   return VSF_OK;
 }
 
@@ -751,9 +820,29 @@ extern "C" int vsf_window_last_transfer(const vsf_ctx* c, size_t* h2d_bytes, siz
 }
 
 namespace {
-struct ByDistance {  // cv::DMatch::operator<
-  bool operator()(const vsf_dmatch& a, const vsf_dmatch& b) const { return a.distance < b.distance; }
+// The tail of Frontend::GetFeatureMatches on the host (src/slam_frontend.cc:289-296):
+// std::sort(matches) with cv::DMatch::operator< (distance only), keep the first
+// int(size * best_percent), emit FeatureMatch(queryIdx, trainIdx).  std::sort is not stable, so
+// the order inside equal-distance groups is whatever libstdc++'s introsort does; that sequence
+// of moves depends only on the comparison results and the element count, never on the element
+// type, so sorting 4-byte (distance << 22 | position) keys with a distance-only comparator
+// yields exactly the permutation the reference gets on its 16-byte DMatch records, at a
+// fraction of the memory traffic.  Returns the kept count.
+struct ByKeyDistance {
+  bool operator()(uint32_t a, uint32_t b) const { return (a >> kIdxBits) < (b >> kIdxBits); }
 };
+int sort_cut_list(const vsf_dmatch* m, int n, float best_percent, uint32_t* keys, vsf_feature_match* out, int cap) {
+  const int keep = int(float(size_t(n)) * best_percent);   // float multiply, truncation (:290)
+  if (keep > cap) return -1;
+  for (int i = 0; i < n; ++i) keys[i] = (uint32_t(int(m[i].distance)) << kIdxBits) | uint32_t(i);
+  std::sort(keys, keys + n, ByKeyDistance());
+  for (int i = 0; i < keep; ++i) {
+    const vsf_dmatch& d = m[keys[i] & kIdxMask];
+    out[i].feature_idx_initial = uint64_t(d.queryIdx);
+    out[i].feature_idx_current = uint64_t(d.trainIdx);
+  }
+  return keep;
+}
 }  // namespace
 
 extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, double ratio,
@@ -813,37 +902,103 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
     counts[j] = good;
     if (frame_ids) frame_ids[j] = c->slot_frame[c->live[j]];
   }
+  if (!c->h_keys) c->h_keys = static_cast<uint32_t*>(std::malloc(size_t(c->window) * c->rows_pad * sizeof(uint32_t)));
+  if (!c->h_keys) return fail(c, VSF_ERR_CUDA, "out of host memory");
   const int nthreads = std::max(1, std::min(nf, c->host_threads));
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-  for (int j = 0; j < nf; ++j) {
-    vsf_dmatch* m = c->h_matches + size_t(j) * c->rows_pad;
-    std::sort(m, m + c->h_counts[j], ByDistance());
-    vsf_feature_match* o = out + size_t(j) * cap_per_frame;
-    for (int i = 0; i < counts[j]; ++i) {
-      o[i].feature_idx_initial = uint64_t(m[i].queryIdx);
-      o[i].feature_idx_current = uint64_t(m[i].trainIdx);
-    }
-  }
+  for (int j = 0; j < nf; ++j)
+    sort_cut_list(c->h_matches + size_t(j) * c->rows_pad, c->h_counts[j], best_percent,
+                  c->h_keys + size_t(j) * c->rows_pad, out + size_t(j) * cap_per_frame, cap_per_frame);
   return VSF_OK;
 }
 
 // ------------------------------------------------- pipelined window matching (a3/a4, frame stream)
 
+static void pool_finish_one(vsf_ctx* c, vsf_ctx::Flight* f) {
+  if (f->pending.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+    std::lock_guard<std::mutex> lk(c->done_mu);
+    c->done_cv.notify_all();
+  }
+}
+
+static void pool_worker(vsf_ctx* c) {
+  for (;;) {
+    vsf_ctx::SortTask t;
+    {
+      std::unique_lock<std::mutex> lk(c->pool_mu);
+      c->pool_cv.wait(lk, [c] { return c->pool_stop || !c->pool_q.empty(); });
+      if (c->pool_q.empty()) return;   // stop requested and nothing left
+      t = c->pool_q.front();
+      c->pool_q.pop_front();
+    }
+    vsf_ctx::Flight* f = t.f;
+    const size_t off = size_t(t.list) * c->rows_pad;
+    f->keep[t.list] = sort_cut_list(f->h_matches + off, f->h_counts[t.list], f->best_percent, f->keys + off,
+                                    f->h_fm + off, c->rows_pad);
+    pool_finish_one(c, f);
+  }
+}
+
+static void pool_dispatcher(vsf_ctx* c) {
+  cudaSetDevice(c->device);
+  for (;;) {
+    vsf_ctx::Flight* f;
+    {
+      std::unique_lock<std::mutex> lk(c->disp_mu);
+      c->disp_cv.wait(lk, [c] { return c->pool_stop || !c->disp_q.empty(); });
+      if (c->disp_q.empty()) return;
+      f = c->disp_q.front();
+      c->disp_q.pop_front();
+    }
+    // once the event completes the survivors + counts of the frame are in host memory; every
+    // past frame's list then becomes one task, longest first (they bound the finish time)
+    const cudaError_t e = cudaEventSynchronize(f->done);
+    if (e != cudaSuccess) f->cuda_error = int(e);
+    const int nf = (e == cudaSuccess) ? f->nf : 0;
+    if (nf > 0) {
+      int order[kMaxProblems];
+      for (int j = 0; j < nf; ++j) order[j] = j;
+      std::sort(order, order + nf, [f](int a, int b) { return f->h_counts[a] > f->h_counts[b]; });
+      f->pending.fetch_add(nf, std::memory_order_acq_rel);
+      {
+        std::lock_guard<std::mutex> lk(c->pool_mu);
+        for (int k = 0; k < nf; ++k) c->pool_q.push_back(vsf_ctx::SortTask{f, order[k]});
+      }
+      c->pool_cv.notify_all();
+    }
+    pool_finish_one(c, f);   // the device-wait token taken at submit
+  }
+}
+
 static int flights_init(vsf_ctx* c) {
   if (c->flights_ready) return VSF_OK;
   cudaSetDevice(c->device);
   const size_t N = size_t(c->rows_pad);
+  const size_t list_bytes = size_t(c->window) * N * 16;   // vsf_dmatch and vsf_feature_match: 16 B
+  VSF_CUDA(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  VSF_CUDA(c, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+  VSF_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
   for (vsf_ctx::Flight& f : c->flights) {
+    VSF_CUDA(c, cudaEventCreateWithFlags(&f.ev_up, cudaEventDisableTiming));
+    VSF_CUDA(c, cudaEventCreateWithFlags(&f.ev_chain, cudaEventDisableTiming));
     VSF_CUDA(c, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_desc), N * c->row_bytes));
-    VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_matches), size_t(c->window) * N * sizeof(vsf_dmatch), cudaHostAllocMapped));
-    VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_fm), size_t(c->window) * N * sizeof(vsf_feature_match), cudaHostAllocMapped));
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_matches), list_bytes));
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_fm), list_bytes));
+    VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_matches), list_bytes));
+    VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_fm), list_bytes));
     VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_counts), kMaxProblems * sizeof(int), cudaHostAllocMapped));
-    VSF_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&f.dm_matches), f.h_matches, 0));
-    VSF_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&f.dm_fm), f.h_fm, 0));
     VSF_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&f.dm_counts), f.h_counts, 0));
     std::memset(f.h_counts, 0, kMaxProblems * sizeof(int));
+    f.keys = static_cast<uint32_t*>(std::malloc(size_t(c->window) * N * sizeof(uint32_t)));
+    if (!f.keys) return fail(c, VSF_ERR_CUDA, "out of host memory");
   }
+  // worker threads for the host-side finish of sort_mode 1: lists of different frames in flight
+  // are sorted concurrently, so the host keeps up with the device
+  // (the caller's thread and the dispatcher keep a core each)
+  const int nworkers = std::max(1, c->host_threads - 2);
+  for (int i = 0; i < nworkers; ++i) c->workers.emplace_back(pool_worker, c);
+  c->dispatcher = std::thread(pool_dispatcher, c);
   c->flights_ready = true;
   return VSF_OK;
 }
@@ -851,43 +1006,115 @@ static int flights_init(vsf_ctx* c) {
 extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_count : 0; }
 
 extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* desc, int n, size_t stride,
-                                 double ratio, float best_percent, int sort_mode) {
+                                 double ratio, float best_percent, int sort_mode, int flags) {
   if (!c) return VSF_ERR_BAD_ARG;
   if (sort_mode != 0 && sort_mode != 1) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 or 1");
+  if (n < 0 || (n > 0 && !desc) || (n > 0 && stride < size_t(c->desc_bytes))) return fail(c, VSF_ERR_BAD_ARG, "bad frame");
+  if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
   if (c->flight_count >= VSF_PIPELINE_DEPTH)
     return fail(c, VSF_ERR_STATE, "VSF_PIPELINE_DEPTH frames already in flight: call vsf_window_collect first");
   int rc = flights_init(c);
   if (rc) return rc;
+  cudaSetDevice(c->device);
   vsf_ctx::Flight& f = c->flights[(c->flight_head + c->flight_count) % VSF_PIPELINE_DEPTH];
   const int nf = int(c->live.size());
   f.nf = nf;
   f.sort_mode = sort_mode;
   f.best_percent = best_percent;
   f.frame_id = frame_id;
-  f.h2d_bytes = size_t(std::max(n, 0)) * c->row_bytes;
-  for (int j = 0; j < nf; ++j) f.fids[j] = c->slot_frame[c->live[j]];
-  // the kernels of this submission mirror into the flight's own mapped buffers
-  c->mir_dm = f.dm_matches;
+  f.h2d_bytes = size_t(n) * c->row_bytes;
+  int max_cnt = 0;
+  for (int j = 0; j < nf; ++j) {
+    f.fids[j] = c->slot_frame[c->live[j]];
+    max_cnt = std::max(max_cnt, c->slot_count[c->live[j]]);
+  }
+  // ---- upload stream: the frame's rows go into the free ring slot while the main stream is
+  // still matching the previous frame.  The slot was last read by the frame before that one.
+  const int S = c->staging_slot;
+  if (c->main_dirty) {   // kernels launched outside the pipeline may still be reading the ring
+    VSF_CUDA(c, cudaEventRecord(c->ev_main, c->stream));
+    VSF_CUDA(c, cudaStreamWaitEvent(c->up_stream, c->ev_main, 0));
+  }
+  if (c->slot_last_chain[S]) VSF_CUDA(c, cudaStreamWaitEvent(c->up_stream, c->slot_last_chain[S], 0));
+  if (n > 0) {
+    const uint8_t* src = f.h_desc;
+    if ((flags & VSF_SUBMIT_PINNED_DESC) && stride == size_t(c->row_bytes) && c->desc_bytes == c->row_bytes) {
+      src = desc;   // page-locked and already in the device layout: no staging copy
+    } else if (stride == size_t(c->row_bytes) && c->desc_bytes == c->row_bytes) {
+      std::memcpy(f.h_desc, desc, size_t(n) * c->row_bytes);
+    } else {
+      for (int i = 0; i < n; ++i) {
+        std::memcpy(f.h_desc + size_t(i) * c->row_bytes, desc + size_t(i) * stride, c->desc_bytes);
+        if (c->desc_bytes < c->row_bytes)
+          std::memset(f.h_desc + size_t(i) * c->row_bytes + c->desc_bytes, 0, c->row_bytes - c->desc_bytes);
+      }
+    }
+    VSF_CUDA(c, cudaMemcpyAsync(c->slot_ptr(S), src, size_t(n) * c->row_bytes, cudaMemcpyHostToDevice, c->up_stream));
+  }
+  VSF_CUDA(c, cudaEventRecord(f.ev_up, c->up_stream));
+  VSF_CUDA(c, cudaStreamWaitEvent(c->stream, f.ev_up, 0));
+  // ---- main stream: every resident past frame (query side) against this frame (train side);
+  // the survivors go to the flight's own device buffer, the counts straight to mapped host memory
+  std::vector<ProblemSpec> specs;
+  for (int j = 0; j < nf; ++j) {
+    const int s = c->live[j];
+    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, c->slot_ptr(S), n, nullptr, j});
+  }
+  c->match_base = f.d_matches;
+  c->mir_dm = nullptr;
   c->mir_dcounts = f.dm_counts;
   c->mir_hcounts = f.h_counts;
-  rc = window_launch(c, desc, n, stride, ratio, sort_mode == 1, f.h_desc);
-  c->mir_dm = c->dm_matches;
-  c->mir_dcounts = c->dm_region_counts;
-  c->mir_hcounts = c->h_region_counts;
-  if (rc) return rc;
-  if (sort_mode == 0 && nf > 0) {
-    // stable device sort + cut, written straight into the flight's mapped host buffers
+  rc = run_knn(c, specs, ratio, sort_mode == 1);
+  if (rc == VSF_OK && sort_mode == 0 && nf > 0) {
+    // stable device sort + cut; the kept counts go to the flight's mapped counters
     const vsf_dmatch* mp[kMaxProblems];
     const int* cp[kMaxProblems];
     for (int j = 0; j < nf; ++j) {
       mp[j] = c->region_ptr(j);
       cp[j] = c->d_match_count + j;
     }
-    VSF_CUDA(c, launch_sort_cut(mp, cp, nf, best_percent, f.dm_fm, c->rows_pad, f.dm_counts, c->max_features, c->stream));
+    const cudaError_t e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, c->max_features, c->stream);
+    if (e != cudaSuccess) {
+      c->err = std::string("launch_sort_cut: ") + cudaGetErrorString(e);
+      rc = VSF_ERR_CUDA;
+    }
   }
-  VSF_CUDA(c, cudaEventRecord(f.done, c->stream));
+  c->match_base = c->d_matches;
+  c->mir_dm = c->dm_matches;
+  c->mir_dcounts = c->dm_region_counts;
+  c->mir_hcounts = c->h_region_counts;
+  if (rc) return rc;
+  c->main_dirty = false;
+  VSF_CUDA(c, cudaEventRecord(f.ev_chain, c->stream));
+  for (int j = 0; j < nf; ++j) c->slot_last_chain[c->live[j]] = f.ev_chain;
+  c->slot_last_chain[S] = f.ev_chain;
+  // ---- download stream: the lists leave through the copy engine while the main stream goes on
+  // with the next frame.  Their lengths are only known on the device, so each list is copied up
+  // to its bound (a past frame's row count, cut by best_percent for the sorted lists).
+  VSF_CUDA(c, cudaStreamWaitEvent(c->down_stream, f.ev_chain, 0));
+  f.d2h_bytes = size_t(nf) * sizeof(int);
+  if (nf > 0 && max_cnt > 0) {
+    const size_t pitch = size_t(c->rows_pad) * 16;
+    const int rows = sort_mode == 1 ? max_cnt : std::min(max_cnt, int(float(size_t(max_cnt)) * best_percent) + 1);
+    if (rows > 0) {
+      VSF_CUDA(c, cudaMemcpy2DAsync(sort_mode == 1 ? static_cast<void*>(f.h_matches) : static_cast<void*>(f.h_fm), pitch,
+                                    sort_mode == 1 ? static_cast<const void*>(f.d_matches) : static_cast<const void*>(f.d_fm), pitch,
+                                    size_t(rows) * 16, size_t(nf), cudaMemcpyDeviceToHost, c->down_stream));
+      f.d2h_bytes += size_t(rows) * 16 * size_t(nf);
+    }
+  }
+  VSF_CUDA(c, cudaEventRecord(f.done, c->down_stream));
   commit_staging(c, frame_id, n);   // eviction + push (src/slam_frontend.cc:467-470)
   ++c->flight_count;
+  f.cuda_error = 0;
+  if (sort_mode == 1) {
+    f.pending.store(1, std::memory_order_release);   // the device-wait token
+    {
+      std::lock_guard<std::mutex> lk(c->disp_mu);
+      c->disp_q.push_back(&f);
+    }
+    c->disp_cv.notify_one();
+  }
   return VSF_OK;
 }
 
@@ -898,40 +1125,39 @@ extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* fram
   if (c->flight_count == 0) return fail(c, VSF_ERR_STATE, "no submitted frame to collect");
   cudaSetDevice(c->device);
   vsf_ctx::Flight& f = c->flights[c->flight_head];
-  VSF_CUDA(c, cudaEventSynchronize(f.done));
+  cudaError_t werr = cudaSuccess;
+  if (f.sort_mode == 1) {
+    std::unique_lock<std::mutex> lk(c->done_mu);
+    c->done_cv.wait(lk, [&f] { return f.pending.load(std::memory_order_acquire) == 0; });
+    werr = cudaError_t(f.cuda_error);
+  } else {
+    werr = cudaEventSynchronize(f.done);
+  }
   // the flight is consumed whatever happens next
   c->flight_head = (c->flight_head + 1) % VSF_PIPELINE_DEPTH;
   --c->flight_count;
+  VSF_CUDA(c, werr);
   const int nf = f.nf;
   *n_frames = nf;
   if (frame_id) *frame_id = f.frame_id;
   c->last_h2d = f.h2d_bytes;
-  c->last_d2h = 0;
+  c->last_d2h = f.d2h_bytes;
   for (int j = 0; j < nf; ++j) {
-    c->last_d2h += size_t(f.h_counts[j]) * 16 + sizeof(int);   // vsf_dmatch and vsf_feature_match are both 16 B
-    // sort_mode 0: the kernel already stored int(count * best_percent); sort_mode 1: the cut of
-    // src/slam_frontend.cc:290 in float, like the reference
-    const int keep = f.sort_mode == 0 ? f.h_counts[j] : int(float(size_t(f.h_counts[j])) * f.best_percent);
+    const int keep = f.sort_mode == 0 ? f.h_counts[j] : f.keep[j];
     if (keep > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
     counts[j] = keep;
     if (frame_ids) frame_ids[j] = f.fids[j];
   }
-  if (f.sort_mode == 0) {
-    for (int j = 0; j < nf; ++j)
-      if (counts[j]) std::memcpy(out + size_t(j) * cap_per_frame, f.h_fm + size_t(j) * c->rows_pad, size_t(counts[j]) * sizeof(vsf_feature_match));
-    return VSF_OK;
-  }
-  const int nthreads = std::max(1, std::min(nf, c->host_threads));
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-  for (int j = 0; j < nf; ++j) {
-    vsf_dmatch* m = f.h_matches + size_t(j) * c->rows_pad;
-    std::sort(m, m + f.h_counts[j], ByDistance());   // the reference's own call (src/slam_frontend.cc:289)
-    vsf_feature_match* o = out + size_t(j) * cap_per_frame;
-    for (int i = 0; i < counts[j]; ++i) {
-      o[i].feature_idx_initial = uint64_t(m[i].queryIdx);
-      o[i].feature_idx_current = uint64_t(m[i].trainIdx);
-    }
-  }
+  for (int j = 0; j < nf; ++j)
+    if (counts[j]) std::memcpy(out + size_t(j) * cap_per_frame, f.h_fm + size_t(j) * c->rows_pad, size_t(counts[j]) * sizeof(vsf_feature_match));
+  return VSF_OK;
+}
+
+extern "C" int vsf_set_host_threads(vsf_ctx* c, int n) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (n < 1 || n > 256) return fail(c, VSF_ERR_BAD_ARG, "host thread count must be 1..256");
+  if (c->flights_ready) return fail(c, VSF_ERR_STATE, "worker threads already started (call before the first vsf_window_submit)");
+  c->host_threads = n;
   return VSF_OK;
 }
 
