@@ -372,13 +372,23 @@ def run_b200(a):
         popc_peak_cmp = popc_rate / 8.0                    # 8 POPC per 256-bit comparison
         main_s = float(kt[1]) * 1e-3                       # dominant kernel, average launch duration
         tensor = engine >= 2
+        # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        traffic, traffic_src = None, None
+        if n == 5000 and W == 10:
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                te = tj["tensor_int8" if engine == 2 else ("popc" if engine == 1 else "none")]
+                traffic, traffic_src = te["traffic_bytes"], te["source"]
+            except Exception:
+                pass
         if tensor:
             # one comparison = one 256-term dot product of +-1 bytes = 256 MACs = 512 ops
             ops = 512.0 * cmp_per_step
             bf16 = float(peaks.get("bf16_tflops", 1590.0))
             roofline = {
                 "bound": "tensor", "achieved": ops / main_s / 1e12, "peak": 2.0 * bf16, "unit": "TFLOP/s",
-                "frac": ops / main_s / 1e12 / (2.0 * bf16), "traffic": None,
+                "frac": ops / main_s / 1e12 / (2.0 * bf16), "traffic": traffic, "traffic_unit": "bytes/launch",
+                "traffic_source": traffic_src,
                 "kernel": "vsf::knn2_tc_kernel<int8>" if engine == 2 else "vsf::knn2_tc_kernel<e4m3>",
                 "kernel_ms": float(kt[1]),
                 "peak_source": "2 x bf16_tflops (burst) of %s: 8-bit operands run the tensor pipe at twice the "
@@ -394,7 +404,8 @@ def run_b200(a):
         else:
             roofline = {
                 "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_unit": "bytes/launch",
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "POPC engine: integer-pipe bound by design (arithmetic intensity N/32 comparisons "
                         "per byte), HBM is idle at roofline; see roofline_int",
