@@ -324,6 +324,16 @@ int vsf_probe_pipe(vsf_ctx* ctx, int kind, int iters, double* ops_per_second);
 
 int vsf_device_sm_count(const vsf_ctx* ctx);
 
+/* Bring-up aid: per-CTA timeline of the last tensor-engine launch made with engine flag 16
+ * (vsf_set_engine(ctx, 2, 16)): 16 values per CTA, layout documented in
+ * csrc/knn2_tc_kernel.cu.  Waits for the ctx stream. */
+int vsf_debug_tc_trace(vsf_ctx* ctx, long long* out, int max_ctas, int* n_ctas);
+/* Bring-up aid: kernel-level timeline of the tensor-engine launches made since
+ * vsf_set_engine(ctx, engine, 32): per launch 10 values = earliest start / latest end
+ * (globaltimer ns) of the expansion, distance, refine and compaction kernels, then of the
+ * refine after its wait.  At most 256 launches are kept. */
+int vsf_debug_kernel_trace(vsf_ctx* ctx, long long* out, int max_records, int* n_records);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,10 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("VSF_TC_TRACE"):
+        # per-CTA timeline stamps inside knn2_tc_kernel (tools/tc_timeline.py); costs ~6 % of the
+        # kernel even when switched off at run time, so never part of a normal build
+        flags.append("-DVSF_TC_TRACE")
     objs = []
     rebuilt = False
     for src in CUDA_SOURCES:

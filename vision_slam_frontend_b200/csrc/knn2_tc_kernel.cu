@@ -13,23 +13,26 @@
 //
 // Selection without packing an index into every element: the epilogue reads its query's row
 // of the accumulator (tcgen05.ld, one TMEM lane per query) and keeps only the MAXIMUM dot of
-// every bucket of 32 consecutive train rows (3-input VIMNMX3 / FMNMX3: 16 instructions per 32
-// comparisons), then the top-2 BUCKETS per query ordered by (max dot desc, bucket asc).  The
-// best neighbour (lowest distance, lowest train index on ties) is always inside the best
-// bucket, and the second neighbour is inside the best or the second-best bucket, so the
-// refine kernel recomputes exact Hamming distances for just those <= 64 train rows per query
-// on the integer pipe (XOR/POPC, lexicographic packed keys) and the result is bit-identical
-// to the POPC engine and to OpenCV.
+// every bucket of kTcBucket (16) consecutive train rows (3-input VIMNMX3 on packed int16 pairs),
+// then the top-2 BUCKETS per query ordered by (max dot desc, bucket asc).  The best neighbour
+// (lowest distance, lowest train index on ties) is always inside the best bucket, and the
+// second neighbour is inside the best or the second-best bucket, so the refine kernel
+// recomputes exact Hamming distances for just those <= 32 train rows per query on the integer
+// pipe (XOR/POPC, lexicographic packed keys) and the result is bit-identical to the POPC engine
+// and to OpenCV.
 //
-// Kernels (all on the ctx stream):
+// Kernels:
 //   expand_train_kernel   packed train rows -> +-1 bytes, written tile by tile in the exact
 //                         shared-memory image the UMMA descriptors expect (K-major, no swizzle:
 //                         [16 K-chunks][256 rows][16 B]), so one 64 KB 1-D TMA bulk copy
 //                         (cp.async.bulk, SASS UBLKCP) stages a tile.
-//   knn2_tc_kernel        persistent, warp-specialised: warp 8 = TMA producer, warp 9 = MMA
-//                         issuer (one elected thread), warps 0-7 = query expansion into smem +
-//                         TMEM epilogue.  Work unit = 256 queries x one train split.
-//   knn2_tc_refine_kernel exact top-2 inside the candidate buckets, ratio test, compaction.
+//   knn2_tc_kernel        persistent, warp-specialised, one CTA per SM: warps 0-15 = query
+//                         expansion into smem + TMEM epilogue, warp 16 = TMA producer, warp 17 =
+//                         MMA issuer (one elected thread).  The (256-query block, train tile)
+//                         slots of the launch are shared out as equal contiguous ranges (TcBatch).
+//   knn2_tc_refine_kernel exact top-2 inside the candidate buckets, ratio test.
+//   knn2_compact_kernel   ratio survivors in ascending queryIdx order.
+// launch_knn2_tc chains the four on one stream with programmatic dependent launch.
 #include <utility>
 
 #include "knn2_tail.cuh"
@@ -67,7 +70,8 @@ __device__ __forceinline__ uint4 expand16(uint32_t b16) {
 template <bool I8>
 __global__ void __launch_bounds__(256)
 expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __restrict__ nt_dev,
-                    uint8_t* __restrict__ out) {
+                    uint8_t* __restrict__ out, long long* kt) {
+  if (threadIdx.x == 0) ktrace_start(kt, 0);
   pdl_wait();
   pdl_launch_dependents();
   const int rows_pad = (nt_bound + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
@@ -76,7 +80,7 @@ expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __r
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = idx % rows_pad;
   const int cg = idx / rows_pad;  // 0..3: K-chunks 4*cg .. 4*cg+3  (words 2*cg, 2*cg+1)
-  if (cg >= 4) return;
+  if (cg >= 4) return;   // whole CTAs at most: blockDim divides rows_pad
   uint2 w = make_uint2(0u, 0u);
   const bool live = row < nt;
   if (live) w = __ldg(reinterpret_cast<const uint2*>(t + size_t(row) * 8) + cg);
@@ -89,6 +93,7 @@ expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __r
     uint4 v = live ? expand16<I8>(b16) : make_uint4(0u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(base + size_t(4 * cg + c) * (kTcTileRows * 16)) = v;
   }
+  if (threadIdx.x == 0) ktrace_end(kt, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -104,21 +109,44 @@ constexpr int kBucketIdMask = (1 << kBucketIdBits) - 1;
 constexpr int kTcKeySentinel = int(0x80000000u);    // INT_MIN: "no bucket"
 
 struct TcUnit {
-  int problem, qb, z;
+  int problem, qb, slot;
   int nq, nt;
   int q0;
   int t_begin, t_end, ntiles;
+  int len;     // tile slots of the CTA's range this segment uses up
   bool skip;   // no queries in this block
 };
 
-__device__ __forceinline__ TcUnit decode_unit(const KnnBatch& batch, const TcBatch& tc, int u) {
+// Walk over the segments of this CTA's slot range [x, end) (slots = pieces of
+// tc.tiles_per_piece train tiles, see TcBatch).  Only the first segment can start in the middle
+// of a query block (two divisions, done once, before the kernel waits for its stream
+// predecessor); every later one starts at piece 0 of the next block and is the block's first
+// segment, so stepping costs a few integer instructions.
+struct TcWalk {
+  long long x, end;
+  int gqb, t0, slot, p;
+};
+
+__device__ __forceinline__ TcWalk walk_begin(const TcBatch& tc) {
+  TcWalk w;
+  w.p = 0;
+  w.x = (long long)blockIdx.x * tc.total / tc.grid;
+  w.end = (long long)(blockIdx.x + 1) * tc.total / tc.grid;
+  const long long gqb = w.x / tc.pieces;
+  w.gqb = int(gqb);
+  w.t0 = int(w.x - gqb * tc.pieces);
+  w.slot = int(blockIdx.x) - tc_owner(gqb * tc.pieces, tc.total, tc.grid);
+  return w;
+}
+
+__device__ __forceinline__ TcUnit walk_unit(const KnnBatch& batch, const TcBatch& tc, const TcWalk& w) {
   TcUnit U;
-  int p = 0;
-  while (u >= tc.unit_begin[p + 1]) ++p;
+  U.len = int(min((long long)(tc.pieces - w.t0), w.end - w.x));
+  int p = w.p;
+  while (w.gqb >= tc.qb_begin[p + 1]) ++p;
   U.problem = p;
-  const int local = u - tc.unit_begin[p];
-  U.qb = local / tc.split;
-  U.z = local % tc.split;
+  U.qb = w.gqb - tc.qb_begin[p];
+  U.slot = w.slot;
   const KnnProblem& P = batch.p[p];
   int nq = P.nq, nt = P.nt;
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
@@ -127,11 +155,37 @@ __device__ __forceinline__ TcUnit decode_unit(const KnnBatch& batch, const TcBat
   U.nt = nt;
   U.q0 = U.qb * kTcQ;
   U.skip = U.q0 >= nq;
-  U.t_begin = min(nt, U.z * tc.rows_per_split);
-  U.t_end = min(nt, U.t_begin + tc.rows_per_split);
+  // pieces -> train rows (the last piece of a block may be short)
+  const int tile0 = min(tc.tiles, w.t0 * tc.tiles_per_piece);
+  const int tile1 = min(tc.tiles, (w.t0 + U.len) * tc.tiles_per_piece);
+  U.t_begin = min(nt, tile0 * kTcTileRows);
+  U.t_end = min(nt, tile1 * kTcTileRows);
   U.ntiles = (U.t_end - U.t_begin + kTcTileRows - 1) / kTcTileRows;
   return U;
 }
+
+__device__ __forceinline__ void walk_next(TcWalk& w, const TcUnit& U) {
+  w.x += U.len;
+  w.gqb += 1;
+  w.t0 = 0;
+  w.slot = 0;
+  w.p = U.problem;
+}
+__device__ __forceinline__ bool walk_more(const TcWalk& w) { return w.x < w.end; }
+
+// Timeline slots (flag 16, SM clock cycles unless noted): 0 globaltimer ns at entry, 1 entry,
+// 2 barriers/TMEM ready, 3 predecessor complete (griddepcontrol.wait returned), 4 first TMA issued,
+// 5 first query half expanded, 6 first train tile landed, 7 first MMA issued, 8 last MMA
+// committed, 9 last accumulator complete, 10 last partial keys written, 11 CTA done,
+// 12 cycles the MMA warp waited for expanded queries, 13 ... for train tiles, 14 segments,
+// 15 globaltimer ns at the end.
+__device__ __forceinline__ long long tc_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_TRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
+#define TC_TRACE_ONCE(slot) do { if (tr && tr[slot] == 0) tr[slot] = clock64(); } while (0)
 
 template <bool I8>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -151,6 +205,17 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  // (compiled out by default: even switched off at run time the stamps cost 6 % of the kernel)
+#ifdef VSF_TC_TRACE
+  long long* const tr = tc.trace ? tc.trace + size_t(blockIdx.x) * kTcTraceSlots : nullptr;
+#else
+  long long* const tr = nullptr;
+#endif
+  if (tr && tid == 0) {
+    tr[0] = tc_globaltimer();
+    tr[1] = clock64();
+  }
+  if (tid == 0) ktrace_start(batch.ktrace, 1);
 
   if (tid == 0) {
 #pragma unroll
@@ -171,9 +236,16 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
-  // everything above overlapped the tail of the previous kernel in the stream
-  pdl_wait();
-  pdl_launch_dependents();
+  // Everything above overlaps the tail of the previous kernel in the stream, and so does what
+  // each role does before its own griddepcontrol.wait below: decoding the first work unit and
+  // (epilogue warps) loading + expanding its queries.  Only the expanded train image comes from
+  // the stream predecessor (expand_train_kernel); the descriptors and device-side row counts
+  // were written by kernels before it, which had completed before the predecessor triggered
+  // this launch.
+  if (tid == 0) TC_TRACE(2);
+
+  // this CTA's contiguous range of (query block, train tile) slots
+  TcWalk wk = walk_begin(tc);
 
   // K-major, no swizzle: [K-chunk c][row][16 B]; chunk stride = rows * 16, 8-row group stride = 128
   const uint32_t lbo = uint32_t(kTcQ * 16);
@@ -181,39 +253,66 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
 
   if (warp == kTcEpiWarps) {
     // ------------------------------ TMA producer ------------------------------
+    TcUnit U;
+    if (lane == 0 && walk_more(wk)) U = walk_unit(batch, tc, wk);
+    pdl_wait();                 // the expanded train image is complete
+    pdl_launch_dependents();
     if (lane == 0) {
       uint32_t it = 0;
-      for (int u = blockIdx.x; u < tc.total_units; u += gridDim.x) {
-        const TcUnit U = decode_unit(batch, tc, u);
-        if (U.skip) continue;
-        const uint8_t* src = tc.t_exp[U.problem] + size_t(U.t_begin / kTcTileRows) * kTcBBytes;
-        for (int k = 0; k < U.ntiles; ++k, ++it) {
-          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], kTcBBytes);
-          tma_load_1d(sB + size_t(s) * kTcBBytes, src + size_t(k) * kTcBBytes, kTcBBytes, &full[s]);
+      while (walk_more(wk)) {
+        if (!U.skip) {
+          const uint8_t* src = tc.t_exp[U.problem] + size_t(U.t_begin / kTcTileRows) * kTcBBytes;
+          for (int k = 0; k < U.ntiles; ++k, ++it) {
+            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full[s], kTcBBytes);
+            tma_load_1d(sB + size_t(s) * kTcBBytes, src + size_t(k) * kTcBBytes, kTcBBytes, &full[s]);
+            if (it == 0) TC_TRACE(4);
+          }
         }
+        walk_next(wk, U);
+        if (walk_more(wk)) U = walk_unit(batch, tc, wk);
       }
     }
     __syncwarp();
   } else if (warp == kTcEpiWarps + 1) {
     // ------------------------------ MMA issuer ------------------------------
+    pdl_wait();
+    pdl_launch_dependents();
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::instr_desc(I8, 128, kTcTileRows);
       uint32_t it = 0, unit_it = 0, acc_use[2] = {0u, 0u};
+      long long wait_a = 0, wait_b = 0, nseg = 0;
       const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-      for (int u = blockIdx.x; u < tc.total_units; u += gridDim.x) {
-        const TcUnit U = decode_unit(batch, tc, u);
+      while (walk_more(wk)) {
+        const TcUnit U = walk_unit(batch, tc, wk);
+        walk_next(wk, U);
+        ++nseg;
         if (U.skip || U.ntiles == 0) continue;
         for (int k = 0; k < U.ntiles; ++k, ++it) {
           const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
-          mbar_wait(&full[s], ph);
+          // a ragged last tile only multiplies the train rows that exist (N a multiple of 16;
+          // the epilogue masks per row, the accumulator columns beyond N are never looked at)
+          const int valid = min(kTcTileRows, U.t_end - (U.t_begin + k * kTcTileRows));
+          const uint32_t idesc = tc::instr_desc(I8, 128, (valid + 15) & ~15);
+          if (tr) {
+            const long long t0 = clock64();
+            mbar_wait(&full[s], ph);
+            wait_b += clock64() - t0;
+            if (it == 0) tr[6] = clock64();
+          } else {
+            mbar_wait(&full[s], ph);
+          }
           tc::fence_after_sync();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            if (k == 0) mbar_wait(&aready[h], unit_it & 1u);
+            if (k == 0) {
+              const long long t0 = tr ? clock64() : 0;
+              mbar_wait(&aready[h], unit_it & 1u);
+              if (tr) wait_a += clock64() - t0;
+            }
             mbar_wait(&tempty[h], (acc_use[h] & 1u) ^ 1u);
             tc::fence_after_sync();
+            if (it == 0 && h == 0) TC_TRACE(7);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               // one MMA consumes K = 32 bytes = 2 chunks
@@ -227,6 +326,12 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
           tc::commit(&empty[s]);
         }
         ++unit_it;
+      }
+      if (tr) {
+        tr[8] = clock64();
+        tr[12] = wait_a;
+        tr[13] = wait_b;
+        tr[14] = nseg;
       }
     }
     __syncwarp();
@@ -252,45 +357,56 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
         w = __ldg(reinterpret_cast<const uint4*>(batch.p[V.problem].q + size_t(q) * 8) + ch);
       return w;
     };
-    int u = blockIdx.x;
+    // expand half of this thread's query row (K-chunks 8ch .. 8ch+7) into the A image
+    auto expand_query = [&](const uint4& qw) {
+      const uint32_t words[4] = {qw.x, qw.y, qw.z, qw.w};
+      uint8_t* dst = sA + size_t(h * 128 + r) * 16 + size_t(ch * 8) * (kTcQ * 16);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t b16 = (words[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+        *reinterpret_cast<uint4*>(dst + size_t(c) * (kTcQ * 16)) = expand16<I8>(b16);
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aready[h]);
+      if (tid == 0) TC_TRACE_ONCE(5);
+    };
     TcUnit U;
     uint4 w = make_uint4(0u, 0u, 0u, 0u);
-    if (u < tc.total_units) {
-      U = decode_unit(batch, tc, u);
+    bool expanded = false;   // the queries of unit U are already in the A image
+    if (walk_more(wk)) {
+      U = walk_unit(batch, tc, wk);
       w = load_query(U);
+      if (!(U.skip || U.ntiles == 0)) {
+        expand_query(w);
+        expanded = true;
+      }
     }
-    while (u < tc.total_units) {
-      const int un = u + int(gridDim.x);
+    pdl_wait();                 // partial keys of the previous launch have been consumed
+    pdl_launch_dependents();
+    if (tid == 0) TC_TRACE(3);
+    while (walk_more(wk)) {
+      walk_next(wk, U);                       // wk now stands on the unit after U
+      const bool more = walk_more(wk);
       TcUnit Un;
       uint4 wn = make_uint4(0u, 0u, 0u, 0u);
       const KnnProblem& P = batch.p[U.problem];
       const int q = U.q0 + h * 128 + r;
       uint2* part = reinterpret_cast<uint2*>(batch.partial) +
-                    (size_t(P.row0 + q) * (tc.split * kTcColSplit) + U.z * kTcColSplit + ch);
+                    (size_t(P.row0 + q) * (tc.slots * kTcColSplit) + U.slot * kTcColSplit + ch);
       if (U.skip || U.ntiles == 0) {
         if (!U.skip && q < U.nq) *part = make_uint2(uint32_t(kTcKeySentinel), uint32_t(kTcKeySentinel));
-        if (un < tc.total_units) {
-          Un = decode_unit(batch, tc, un);
+        if (more) {
+          Un = walk_unit(batch, tc, wk);
           wn = load_query(Un);
         }
-        U = Un; w = wn; u = un;
+        U = Un; w = wn;
         continue;
       }
-      // expand half of this thread's query row (K-chunks 8ch .. 8ch+7) into the A image
-      {
-        const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-        uint8_t* dst = sA + size_t(h * 128 + r) * 16 + size_t(ch * 8) * (kTcQ * 16);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t b16 = (words[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-          *reinterpret_cast<uint4*>(dst + size_t(c) * (kTcQ * 16)) = expand16<I8>(b16);
-        }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&aready[h]);
-      }
-      if (un < tc.total_units) {
-        Un = decode_unit(batch, tc, un);
+      if (!expanded) expand_query(w);
+      expanded = false;
+      if (more) {
+        Un = walk_unit(batch, tc, wk);
         wn = load_query(Un);
       }
       int m1 = kTcKeySentinel, m2 = kTcKeySentinel;
@@ -298,6 +414,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
       for (int k = 0; k < U.ntiles; ++k, ++acc_use) {
         mbar_wait(&tfull[h], acc_use & 1u);
         tc::fence_after_sync();
+        if (warp == kTcEpiWarps - 1 && lane == 0) TC_TRACE(9);   // overwritten by every tile: the last one stays
         const int row0 = U.t_begin + k * kTcTileRows + ch * kTcEpiCols;   // first train row of my columns
         const int kbase = kBucketIdMask - (bucket0 + k * TB);
         auto push = [&](int bm, int j) {
@@ -309,6 +426,13 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[h]);
+          // Last tile of the unit: every MMA that reads this half of the A image has completed
+          // (that is what tfull[h] said), so the next unit's queries can go in now and the tensor
+          // core restarts while this tile is still being reduced.
+          if (k == U.ntiles - 1 && more && !(Un.skip || Un.ntiles == 0)) {
+            expand_query(wn);
+            expanded = true;
+          }
         };
         const bool full_tile = row0 + kTcEpiCols <= U.t_end;   // warp-uniform
         if (tc.flags & 4) {
@@ -377,7 +501,8 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
         }
       }
       if (q < U.nq) *part = make_uint2(uint32_t(m1), uint32_t(m2));
-      U = Un; w = wn; u = un;
+      if (warp == kTcEpiWarps - 1 && lane == 0) TC_TRACE(10);
+      U = Un; w = wn;
     }
   }
 
@@ -386,6 +511,13 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
   if (warp == kTcEpiWarps + 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc<kTcTmemCols>(tmem_base);
+  }
+  if (tid == 0) {
+    ktrace_end(batch.ktrace, 1);
+    if (tr) {
+      tr[11] = clock64();
+      tr[15] = tc_globaltimer();
+    }
   }
 }
 
@@ -402,7 +534,8 @@ constexpr int kCompactQB = 128;                              // queries per comp
 constexpr int kRefineThreads = 2 * kRefineQB;
 constexpr int kRefineRows = 8;                               // rows per pair per pass
 constexpr int kRefinePitch = kRefineRows * 32 + 16;          // bytes per pair in the stage (+16: bank skew)
-static_assert(kTcBucket % kRefineRows == 0, "bucket must be a multiple of the refine pass");
+constexpr int kRefinePP = kRefineRows * 2;                   // 16-byte pieces of one pair's run of rows
+static_assert(kTcBucket % kRefineRows == 0 && 32 % kRefinePP == 0, "bucket must be a multiple of the refine pass");
 
 __global__ void __launch_bounds__(kRefineThreads)
 knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
@@ -410,11 +543,26 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   const KnnProblem& P = batch.p[blockIdx.y];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  pdl_wait();
-  pdl_launch_dependents();
+  if (tid == 0) ktrace_start(batch.ktrace, 2);
+  // The descriptors and row counts were written before the launch sequence began (see
+  // knn2_tc_kernel): the query words are fetched while the distance kernel is still finishing.
   int nq = P.nq, nt = P.nt;
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
   if (P.nt_dev) nt = min(nt, *P.nt_dev);
+  const int qb = blockIdx.x;
+  const int q0 = qb * kRefineQB;
+  const int q = q0 + (tid >> 1);
+  const int c = tid & 1;                       // 0: best bucket, 1: second-best bucket
+  uint32_t qw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  if (q < nq) {
+    const uint4* src = reinterpret_cast<const uint4*>(P.q + size_t(q) * 8);
+    const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
+    qw[0] = w0.x; qw[1] = w0.y; qw[2] = w0.z; qw[3] = w0.w;
+    qw[4] = w1.x; qw[5] = w1.y; qw[6] = w1.z; qw[7] = w1.w;
+  }
+  pdl_wait();                                  // the partial bucket keys are complete
+  if (tid == 0) ktrace_start(batch.ktrace, 4);
+  pdl_launch_dependents();
   if (nq <= 0) {
     if (blockIdx.x == 0 && tid == 0) {
       *P.match_count = 0;
@@ -422,18 +570,16 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     }
     return;
   }
-  const int qb = blockIdx.x;
-  const int q0 = qb * kRefineQB;
   if (q0 >= nq) return;
-  const int q = q0 + (tid >> 1);
-  const int c = tid & 1;                       // 0: best bucket, 1: second-best bucket
 
   int key = kTcKeySentinel;
-  uint32_t qw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   if (q < nq) {
     int b1 = kTcKeySentinel, b2 = kTcKeySentinel;
-    const int np = tc.split * kTcColSplit;
-    const uint2* part = reinterpret_cast<const uint2*>(batch.partial) + size_t(P.row0 + q) * np;
+    // the query block's tile slots were shared out to consecutive CTAs, one partial segment each
+    const int nseg = tc_block_segments(tc, tc.qb_begin[blockIdx.y] + q / kTcQ);
+    const int np = nseg * kTcColSplit;
+    const uint2* part = reinterpret_cast<const uint2*>(batch.partial) + size_t(P.row0 + q) * (tc.slots * kTcColSplit);
+#pragma unroll 4
     for (int z = 0; z < np; ++z) {
       const uint2 p = __ldcg(part + z);
       const int a1 = int(p.x), a2 = int(p.y);
@@ -443,10 +589,6 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       b1 = hi;
     }
     key = c ? b2 : b1;
-    const uint4* src = reinterpret_cast<const uint4*>(P.q + size_t(q) * 8);
-    const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
-    qw[0] = w0.x; qw[1] = w0.y; qw[2] = w0.z; qw[3] = w0.w;
-    qw[4] = w1.x; qw[5] = w1.y; qw[6] = w1.z; qw[7] = w1.w;
   }
   // first train row of this lane's candidate bucket, -1 = none
   const int my_row0 = (key == kTcKeySentinel) ? -1 : (kBucketIdMask - (key & kBucketIdMask)) * kTcBucket;
@@ -454,11 +596,11 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   uint8_t* stage = s_stage[warp];
 #pragma unroll 1
   for (int r0 = 0; r0 < kTcBucket; r0 += kRefineRows) {
-    // stage: 32 pairs x 8 rows x 32 B = 512 pieces of 16 B, 16 per lane
+    // stage: 32 pairs x 8 rows x 32 B in pieces of 16 B, 16 per lane
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int g = i * 2 + (lane >> 4);                  // pair (lane) whose rows this piece belongs to
-      const int piece = lane & 15;                        // 16-byte piece of the 256-byte run
+    for (int i = 0; i < kRefinePP; ++i) {
+      const int g = i * (32 / kRefinePP) + lane / kRefinePP;          // pair (lane) whose rows this piece belongs to
+      const int piece = lane % kRefinePP;                       // 16-byte piece of the pair's run of rows
       const int base = __shfl_sync(0xffffffffu, my_row0, g);
       const int row = base + r0 + (piece >> 1);
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -495,7 +637,10 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
   }
   const int npass = __syncthreads_count(pass);
-  if (tid == 0) batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
+  if (tid == 0) {
+    batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
+    ktrace_end(batch.ktrace, 2);
+  }
 }
 
 // Ordered compaction of the ratio survivors, one CTA per block of 128 queries: the CTA's
@@ -508,6 +653,7 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
   const KnnProblem& P = batch.p[blockIdx.y];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) ktrace_start(batch.ktrace, 3);
   pdl_wait();
   pdl_launch_dependents();
   int nq = P.nq;
@@ -557,6 +703,7 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
     *P.match_count = int(base + total);
     if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
   }
+  if (tid == 0) ktrace_end(batch.ktrace, 3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -577,23 +724,43 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
-                                int pdl, cudaStream_t stream) {
+                                int pdl, cudaStream_t stream, long long* ktrace) {
   if (nt_bound <= 0) return cudaSuccess;
   const int rows_pad = (nt_bound + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
+  // 128-thread CTAs: one warp per SM sub-partition at 18 registers per thread fits beside a
+  // resident CTA of knn2_tc_kernel (whose 5 warps x 96 registers leave 1024 registers free on
+  // two of the four sub-partitions), so the distance kernel of this launch can start its
+  // prologue (and expand its first queries) while the expansion is still running
+  constexpr int kExpandThreads = 128;
+  {
+    // ... and the same shared-memory carve-out as that kernel (the largest one): a kernel that
+    // prefers another L1 / shared split cannot share an SM with it, the SM is reconfigured only
+    // once it has drained
+    static int carveout_set_for = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (carveout_set_for != dev) {
+      cudaError_t e = cudaFuncSetAttribute(expand_train_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(expand_train_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+      carveout_set_for = dev;
+    }
+  }
   const int threads = rows_pad * 4;
-  const int blocks = (threads + 255) / 256;
+  const int blocks = (threads + kExpandThreads - 1) / kExpandThreads;
   const uint32_t* tp = static_cast<const uint32_t*>(t);
   uint8_t* op = static_cast<uint8_t*>(out);
-  return int8 ? launch_pdl(expand_train_kernel<true>, dim3(blocks), dim3(256), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op)
-              : launch_pdl(expand_train_kernel<false>, dim3(blocks), dim3(256), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op);
+  return int8 ? launch_pdl(expand_train_kernel<true>, dim3(blocks), dim3(kExpandThreads), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op, ktrace)
+              : launch_pdl(expand_train_kernel<false>, dim3(blocks), dim3(kExpandThreads), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op, ktrace);
 }
 
 // ev (optional, 4 events): recorded before the main kernel, after it, after the refine and
 // after the compaction kernel (per-kernel timing for bench.py's roofline; an event between two
 // kernels removes their programmatic overlap, so it is only used in dedicated timing passes).
-cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq, int pdl,
+cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
                            cudaEvent_t* ev, cudaStream_t stream) {
-  if (batch.num_problems <= 0 || tc.total_units <= 0) return cudaSuccess;
+  if (batch.num_problems <= 0 || tc.total <= 0) return cudaSuccess;
   cudaError_t e;
   // per-device attribute; setting it is a cheap host-side call
   e = int8 ? cudaFuncSetAttribute(knn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes)
@@ -601,8 +768,8 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
   if (e != cudaSuccess) return e;
   const bool p = pdl != 0;
   if (ev) cudaEventRecord(ev[0], stream);
-  e = int8 ? launch_pdl(knn2_tc_kernel<true>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc)
-           : launch_pdl(knn2_tc_kernel<false>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
+  e = int8 ? launch_pdl(knn2_tc_kernel<true>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc)
+           : launch_pdl(knn2_tc_kernel<false>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
   if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[1], stream);
   dim3 rgrid((max_nq + kRefineQB - 1) / kRefineQB, batch.num_problems);

@@ -20,8 +20,8 @@ namespace vsf {
 cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int variant,
                         int max_qblocks, cudaStream_t stream);
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
-                                int pdl, cudaStream_t stream);
-cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int grid, int max_nq, int pdl,
+                                int pdl, cudaStream_t stream, long long* ktrace);
+cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
                            cudaEvent_t* ev, cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
                          uint64_t seed, cudaStream_t stream);
@@ -41,6 +41,8 @@ cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* 
 
 
 using namespace vsf;
+
+constexpr int kKtracePoses = 256;   // launches kept by the kernel-level timeline (engine flag 32)
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -67,6 +69,9 @@ struct vsf_ctx {
   int popc_mode = -1, force_split = 0, force_R = 0, variant = -1;   // -1 / 0 = library default
   int engine = 0;         // 0 auto, 1 POPC pipe, 2 tensor cores int8, 3 tensor cores e4m3
   int engine_flags = 0;   // timing experiments only (TcBatch::flags)
+  long long* d_tc_trace = nullptr;   // engine flag 16: per-CTA timeline of knn2_tc_kernel
+  long long* d_ktrace = nullptr;     // engine flag 32: kernel-level timeline, kKtracePoses records of [5][2]
+  long long ktrace_n = 0;
   int last_engine = 0;    // engine the last kNN launch used
   double tc_auto_min_cmp = 1e7;  // automatic mode: tensor cores from this many comparisons per batch
   uint8_t* d_train_exp[kTcMaxTrains] = {nullptr, nullptr};  // +-1 expanded train images
@@ -323,45 +328,74 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     const int int8 = engine == 2;
     const int pdl = (c->engine_flags & 8) ? 0 : 1;   // flag 8: ordinary launches (A/B timing)
     if (c->profile) VSF_CUDA(c, cudaEventRecord(c->pev[0], c->stream));
+    long long* kt = nullptr;
+    if ((c->engine_flags & 32) && c->d_ktrace) {   // kernel-level timeline, one record per launch (ring)
+      kt = c->d_ktrace + size_t(c->ktrace_n % kKtracePoses) * 10;
+      ++c->ktrace_n;
+    }
+    b.ktrace = kt;
     for (int k = 0; k < n_trains; ++k)
       VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
-                                      c->d_train_exp[k], int8, pdl, c->stream));
+                                      c->d_train_exp[k], int8, pdl, c->stream, kt));
     TcBatch tb;
     std::memset(&tb, 0, sizeof(tb));
-    long long qblocks = 0;
-    for (const ProblemSpec& s : specs) qblocks += (s.nq + kTcQ - 1) / kTcQ;
-    const int tiles = (max_nt + kTcTileRows - 1) / kTcTileRows;
-    // Train splits: maximise (machine fill of the last wave) x (tiles per unit vs ~1.5 tiles of
-    // fixed cost per unit: query expansion + pipeline fill/drain).
-    int S = c->force_split;
-    if (S == 0) {
+    // Work = (256-query block, piece of train tiles) slots, shared out to the CTAs as equal
+    // contiguous ranges (see TcBatch).
+    int qblocks = 0;
+    for (int i = 0; i < b.num_problems; ++i) {
+      tb.t_exp[i] = c->d_train_exp[train_of[i]];
+      tb.qb_begin[i] = qblocks;
+      qblocks += (specs[i].nq + kTcQ - 1) / kTcQ;
+    }
+    tb.qb_begin[b.num_problems] = qblocks;
+    tb.tiles = (max_nt + kTcTileRows - 1) / kTcTileRows;
+    tb.flags = c->engine_flags;
+    if (c->engine_flags & 16) {   // per-CTA timeline for tools/tc_timeline.py
+      if (!c->d_tc_trace) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_tc_trace), size_t(c->sm_count) * kTcTraceSlots * sizeof(long long)));
+      VSF_CUDA(c, cudaMemsetAsync(c->d_tc_trace, 0, size_t(c->sm_count) * kTcTraceSlots * sizeof(long long), c->stream));
+      tb.trace = c->d_tc_trace;
+    }
+    // Granularity of the slots and number of CTAs (see TcBatch).
+    const int sm = c->sm_count;
+    const long long tile_slots = (long long)qblocks * tb.tiles;
+    int S = tb.tiles;                  // pieces per block; default: one tile per piece
+    long long G = 0;                   // 0: one CTA per SM (or per slot when there are fewer)
+    if (c->force_split > 0) {
+      // tuning knob (tests): about force_split pieces per block, one piece per CTA when they fit
+      S = std::min(c->force_split, tb.tiles);
+      if ((long long)qblocks * S <= sm) G = (long long)qblocks * S;
+    } else if (tile_slots < 4LL * sm && qblocks <= sm) {
+      // small launch: one piece of one block per CTA, as many pieces as fill the machine once
+      S = int(std::max<long long>(1, std::min<long long>(tb.tiles, sm / qblocks)));
+      G = (long long)qblocks * S;
+    } else if (tile_slots > 128LL * sm) {
+      // very large launch: a few long pieces per block; maximise (fill of the last round of
+      // pieces) x (piece length vs ~1.5 tiles of fixed cost per segment)
       double best = -1.0;
-      for (int cand = 1; cand <= std::min(tiles, 32); ++cand) {
-        const int tps = (tiles + cand - 1) / cand;
-        const long long units = qblocks * ((tiles + tps - 1) / tps);
-        const long long waves = (units + c->sm_count - 1) / c->sm_count;
-        const double eff = double(units) / double(waves * c->sm_count) * double(tps) / (double(tps) + 1.5);
+      for (int cand = 1; cand <= std::min(tb.tiles, 16); ++cand) {
+        const int tpp = (tb.tiles + cand - 1) / cand;
+        const long long P = (long long)qblocks * ((tb.tiles + tpp - 1) / tpp);
+        const long long rounds = (P + sm - 1) / sm;
+        const double eff = double(P) / double(rounds * sm) * double(tpp) / (double(tpp) + 1.5);
         if (eff > best + 1e-9) { best = eff; S = cand; }
       }
     }
-    S = std::max(1, std::min(S, std::min(tiles, 32)));
-    while (S > 1 && size_t(row0) * S * 2 > c->partial_cap) --S;   // x2: column halves of the epilogue
-    const int tps = (tiles + S - 1) / S;
-    S = (tiles + tps - 1) / tps;   // drop splits that would be empty
-    tb.split = S;
-    tb.rows_per_split = tps * kTcTileRows;
-    tb.flags = c->engine_flags;
-    int units = 0;
-    for (int i = 0; i < b.num_problems; ++i) {
-      tb.t_exp[i] = c->d_train_exp[train_of[i]];
-      tb.unit_begin[i] = units;
-      units += ((specs[i].nq + kTcQ - 1) / kTcQ) * S;
+    for (;;) {
+      S = std::max(1, std::min(S, tb.tiles));
+      tb.tiles_per_piece = (tb.tiles + S - 1) / S;
+      tb.pieces = (tb.tiles + tb.tiles_per_piece - 1) / tb.tiles_per_piece;   // drop pieces that would be empty
+      tb.total = (long long)qblocks * tb.pieces;
+      long long g = G > 0 ? std::min<long long>(G, tb.total) : std::min<long long>(sm, tb.total);
+      if (G > 0 && (long long)qblocks * tb.pieces <= sm) g = tb.total;          // one piece per CTA
+      // a block's `pieces` consecutive slots cross at most 1 + ceil((pieces - 1) / shortest range) ranges
+      const long long lmin = tb.total / g;
+      tb.slots = int(std::min<long long>(tb.pieces, 1 + (tb.pieces - 1 + lmin - 1) / lmin));
+      tb.grid = int(g);
+      if (S == 1 || size_t(row0) * tb.slots * 2 <= c->partial_cap) break;   // x2: column halves of the epilogue
+      S = (S + 1) / 2;                 // coarser pieces, fewer segments per block
     }
-    tb.unit_begin[b.num_problems] = units;
-    tb.total_units = units;
-    b.split = S;
-    const int grid = std::max(1, std::min(units, c->sm_count));
-    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, grid, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
+    b.split = tb.slots;
+    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
     c->pev_valid = c->profile != 0;
     return VSF_OK;
   }
@@ -427,7 +461,8 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
                  c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
                  c->d_chunk_keep, c->d_kept_left, c->d_kept_right, c->d_n_kept, c->d_thresh, c->d_X4,
-                 c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1]};
+                 c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1], c->d_tc_trace,
+                 c->d_ktrace};
   for (void* p : dev)
     if (p) cudaFree(p);
   void* host[] = {c->h_desc[0], c->h_desc[1], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches, c->h_region_counts,
@@ -639,6 +674,16 @@ extern "C" int vsf_set_engine(vsf_ctx* c, int engine, int flags) {
   if (engine >= 2 && c->words != 8) return fail(c, VSF_ERR_BAD_ARG, "the tensor-core engine needs descriptors of at most 32 bytes");
   c->engine = engine;
   c->engine_flags = flags;
+  if (flags & 32) {
+    // kernel-level timeline: starts = +inf, ends = 0
+    cudaSetDevice(c->device);
+    std::vector<long long> init(size_t(kKtracePoses) * 10);
+    for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0 : 0x7fffffffffffffffLL;
+    if (!c->d_ktrace) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_ktrace), init.size() * sizeof(long long)));
+    VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+    VSF_CUDA(c, cudaMemcpy(c->d_ktrace, init.data(), init.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    c->ktrace_n = 0;
+  }
   return VSF_OK;
 }
 
@@ -1381,6 +1426,28 @@ extern "C" int vsf_synth_sequence_device(vsf_ctx* c, void* d_out, int n, int fir
     return fail(c, VSF_ERR_BAD_ARG, "bad synth arguments (generator produces 32-byte rows)");
   cudaSetDevice(c->device);
   VSF_CUDA(c, launch_synth(static_cast<uint32_t*>(d_out), n, first_pose, n_poses, stride, seed, c->stream));
+  return VSF_OK;
+}
+
+extern "C" int vsf_debug_tc_trace(vsf_ctx* c, long long* out, int max_ctas, int* n_ctas) {
+  if (!c || !out || !n_ctas || max_ctas < 0) return VSF_ERR_BAD_ARG;
+  if (!c->d_tc_trace) return fail(c, VSF_ERR_STATE, "no timeline recorded (vsf_set_engine flag 16, then a tensor-engine launch)");
+  cudaSetDevice(c->device);
+  const int n = std::min(max_ctas, c->sm_count);
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  VSF_CUDA(c, cudaMemcpy(out, c->d_tc_trace, size_t(n) * kTcTraceSlots * sizeof(long long), cudaMemcpyDeviceToHost));
+  *n_ctas = n;
+  return VSF_OK;
+}
+
+extern "C" int vsf_debug_kernel_trace(vsf_ctx* c, long long* out, int max_records, int* n_records) {
+  if (!c || !out || !n_records || max_records < 0) return VSF_ERR_BAD_ARG;
+  if (!c->d_ktrace) return fail(c, VSF_ERR_STATE, "no kernel timeline recorded (vsf_set_engine flag 32)");
+  cudaSetDevice(c->device);
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int n = int(std::min<long long>(std::min<long long>(max_records, kKtracePoses), c->ktrace_n));
+  VSF_CUDA(c, cudaMemcpy(out, c->d_ktrace, size_t(n) * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+  *n_records = n;
   return VSF_OK;
 }
 

@@ -58,6 +58,7 @@ struct KnnBatch {
   vsf_dmatch* host_matches;
   int* host_counts;
   int host_region_stride;
+  long long* ktrace;   // engine flag 32: [5][2] earliest start / latest end (globaltimer ns) of expand, distance, refine, compaction, refine-after-wait
   KnnProblem p[kMaxProblems];
 };
 
@@ -74,14 +75,43 @@ constexpr int kTcABytes = kTcQ * kTcRowBytes;
 constexpr int kTcBBytes = kTcTileRows * kTcRowBytes;
 constexpr int kTcMaxTrains = 2;      // distinct train frames per batch that can be expanded
 
+// The work of a launch is the flattened list of (256-query block, piece) slots, query block
+// major, where a piece is tiles_per_piece consecutive train tiles and a block has `pieces` of
+// them: T = blocks * pieces slots.  CTA i of the G CTAs of the persistent kernel owns the
+// contiguous range [i*T/G, (i+1)*T/G) ("stream-K"): every SM gets the same number of pieces to
+// within one, whatever the frame sizes are.  A range covers runs of pieces ("segments") of one
+// or more query blocks; a block is covered by the consecutive CTAs owner(first slot) ..
+// owner(last slot), and segment s of a block stores its partial top-2 bucket keys in slot s of
+// the block's rows.  The host picks the granularity from the shape of the launch:
+//   one tile per piece           the general case (frame-to-window matching at C4 size)
+//   G = T, one piece per CTA     small launches that cannot fill the machine with whole blocks
+//   a few long pieces per block  very large launches: the CTAs then walk the train tiles nearly
+//                                in step, which keeps the tiles they fetch hot in L2
 struct TcBatch {
   const uint8_t* t_exp[kMaxProblems];  // expanded train image of every problem
-  int unit_begin[kMaxProblems + 1];    // prefix sum of work units (query blocks x splits)
-  int split;                           // train splits per problem
-  int rows_per_split;                  // multiple of kTcTileRows
-  int total_units;
+  int qb_begin[kMaxProblems + 1];      // prefix sum of 256-query blocks
+  int tiles;                           // train tiles per query block (largest train frame)
+  int pieces;                          // slots per query block
+  int tiles_per_piece;
+  int grid;                            // G: CTAs of knn2_tc_kernel
+  int slots;                           // partial segments stored per query row (max over blocks)
+  long long total;                     // T = qb_begin[num_problems] * pieces
   int flags;                           // bring-up knobs (timing experiments; results invalid): 2 = skip the bucket reduction, 4 = skip the TMEM loads
+  long long* trace;                    // flag 16 (builds with -DVSF_TC_TRACE): per-CTA timeline, kTcTraceSlots values per CTA
 };
+constexpr int kTcTraceSlots = 16;
+
+// CTA that owns slot x = the largest i with floor(i*T/G) <= x
+__host__ __device__ __forceinline__ int tc_owner(long long x, long long T, int G) {
+  const unsigned long long num = (unsigned long long)(x + 1) * (unsigned long long)G - 1ull;
+  if (((num | (unsigned long long)T) >> 32) == 0) return int(unsigned(num) / unsigned(T));   // the usual case: one 32-bit divide
+  return int(num / (unsigned long long)T);
+}
+// number of segments (partial slots in use) of query block gqb
+__host__ __device__ __forceinline__ int tc_block_segments(const TcBatch& tc, int gqb) {
+  const long long s0 = (long long)gqb * tc.pieces;
+  return tc_owner(s0 + tc.pieces - 1, tc.total, tc.grid) - tc_owner(s0, tc.total, tc.grid) + 1;
+}
 
 // ---- PTX helpers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -137,6 +167,18 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void ktrace_start(long long* kt, int k) {
+  if (kt) atomicMin(reinterpret_cast<long long*>(kt + 2 * k), globaltimer_ns());
+}
+__device__ __forceinline__ void ktrace_end(long long* kt, int k) {
+  if (kt) atomicMax(reinterpret_cast<long long*>(kt + 2 * k + 1), globaltimer_ns());
 }
 
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
