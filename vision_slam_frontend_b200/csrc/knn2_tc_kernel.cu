@@ -97,6 +97,13 @@ expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// TcBatch::flags 2 / 4 (skip the bucket reduction / the TMEM loads: timing experiments whose
+// results are invalid) only exist in builds with -DVSF_TC_BRINGUP
+#ifdef VSF_TC_BRINGUP
+constexpr bool kBringup = true;
+#else
+constexpr bool kBringup = false;
+#endif
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcColSplit = 2;                      // epilogue warps per (accumulator half, lane quarter)
 constexpr int kTcEpiCols = kTcTileRows / kTcColSplit;  // columns of a tile one epilogue warp reduces
@@ -435,7 +442,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
           }
         };
         const bool full_tile = row0 + kTcEpiCols <= U.t_end;   // warp-uniform
-        if (tc.flags & 4) {
+        if (kBringup && (tc.flags & 4)) {
           release();
         } else if (I8) {
           // int32 accumulators hold |dot| <= 256: read them as packed int16 pairs
@@ -446,7 +453,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
           tc::tmem_ld_32x32_pack16(taddr + 64u, v[1]);
           tc::tmem_ld_wait();
           release();
-          if (!(tc.flags & 2)) {
+          if (!(kBringup && (tc.flags & 2))) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
               uint32_t* b = &v[(j * RPB) / 32][(j * RPB) % 32];
@@ -477,7 +484,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
             tc::tmem_ld_wait();
             if (l + 1 < kTcEpiCols / 32) tc::tmem_ld_32x32(taddr + uint32_t((l + 1) * 32), v[(l + 1) & 1]);
             else release();
-            if (!(tc.flags & 2)) {
+            if (!(kBringup && (tc.flags & 2))) {
 #pragma unroll
               for (int jj = 0; jj < BPL; ++jj) {
                 const int j = l * BPL + jj;
