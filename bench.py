@@ -55,8 +55,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-lag", type=int, default=3,
-                    help="frames submitted ahead of the one being collected in the pipelined e2e leg (1..3)")
+    ap.add_argument("--e2e-lag", type=int, default=6,
+                    help="frames submitted ahead of the one being collected in the pipelined e2e leg "
+                         "(1 .. VSF_PIPELINE_DEPTH - 1)")
     ap.add_argument("--popc-mode", type=int, default=-1)
     ap.add_argument("--split", type=int, default=0)
     ap.add_argument("--qpt", type=int, default=0)
@@ -285,6 +286,8 @@ def run_b200(a):
     ctx.set_engine(a.engine, 0)
     # host threads for the reference's std::sort (e2e leg): the ranks of one box share its cores
     host_threads = max(2, min(16, (os.cpu_count() or 16) // world))
+    if os.environ.get("VSF_HOST_THREADS"):
+        host_threads = int(os.environ["VSF_HOST_THREADS"])
     ctx.set_host_threads(host_threads)
 
     # ---- device-resident sequence: this rank's pose range, larger than L2 ----------------
@@ -479,7 +482,8 @@ def measure_e2e(a, ctx, seq, n, W, K, WU, world, dist, torch):
     nf = C.c_int(0)
     fid = C.c_uint64(0)
     h2d_b, d2h_b = C.c_size_t(0), C.c_size_t(0)
-    lag = max(1, min(a.e2e_lag, 3))
+    from vision_slam_frontend_b200 import PIPELINE_DEPTH
+    lag = max(1, min(a.e2e_lag, PIPELINE_DEPTH - 1))
     res = {}
 
     def check(rc):

@@ -200,7 +200,7 @@ int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
  * meaning; *frame_id = the id given at submit; sort_mode / best_percent are the
  * ones given at submit).  VSF_ERR_STATE: submit with VSF_PIPELINE_DEPTH frames
  * in flight, or collect with none. */
-#define VSF_PIPELINE_DEPTH 4
+#define VSF_PIPELINE_DEPTH 8
 #define VSF_SUBMIT_PINNED_DESC 1
 int vsf_window_submit(vsf_ctx* ctx, uint64_t frame_id, const uint8_t* desc, int n,
                       size_t stride, double nn_match_ratio, float best_percent,

@@ -202,15 +202,15 @@ def test_window_pipelined_submit_collect(sort_mode, engine, pinned):
     """vsf_window_submit / vsf_window_collect with several frames in flight return, frame by
     frame, what the reference's loop (src/slam_frontend.cc:424-434, :467-470) produces."""
     n, W = 1300, 3
-    frames = [synth.synth_pose(n - 53 * (p % 4), p, 130, 17) for p in range(9)]
+    frames = [synth.synth_pose(n - 53 * (p % 4), p, 130, 17) for p in range(13)]
     frames[5] = frames[5][:0]                       # an empty frame in the middle of the stream
     if pinned:                                      # VSF_SUBMIT_PINNED_DESC: page-locked rows, read in place
         import torch
         keep_alive = [torch.from_numpy(np.ascontiguousarray(D)).pin_memory() for D in frames]
         frames = [t.numpy() for t in keep_alive]
     bp = restate.BEST_PERCENT
-    depth = 4                                       # VSF_PIPELINE_DEPTH
     import vision_slam_frontend_b200 as vsf
+    depth = vsf.PIPELINE_DEPTH                      # VSF_PIPELINE_DEPTH
     with new_ctx(window=W) as ctx:
         ctx.set_engine(engine, 0)
         with pytest.raises(vsf.VsfError) as e:

@@ -9,6 +9,6 @@ multi-GPU runs.  There is no CPU fallback: importing works anywhere, but every
 compute call raises if the CUDA library or a device is missing.
 """
 from .capi import (VsfError, Context, DMATCH_DTYPE, KEYPOINT_DTYPE,  # noqa: F401
-                   FEATURE_MATCH_DTYPE, load_library, library_path)
+                   FEATURE_MATCH_DTYPE, PIPELINE_DEPTH, load_library, library_path)
 
 __version__ = "0.1.0"

@@ -17,6 +17,8 @@ _LIB_PATH = os.environ.get("VSF_LIB_PATH") or os.path.join(_PKG, "libvsf_cuda.so
 _LIB = None
 
 # cv::DMatch / cv::KeyPoint / slam_types::FeatureMatch layouts (include/vsf.h)
+PIPELINE_DEPTH = 8   # VSF_PIPELINE_DEPTH (include/vsf.h): frames vsf_window_submit keeps in flight
+
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"),
                          ("imgIdx", "<i4"), ("distance", "<f4")])
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"),

@@ -54,6 +54,10 @@ struct ProblemSpec {
   int nt;
   const int* nt_dev;
   int region;  // which d_matches region / d_match_count slot receives the survivors
+  // optional: the train frame already expanded to +-1 bytes (tensor engine image) by the caller,
+  // in the operand kind t_exp_int8 says (1 = int8, 0 = e4m3); run_knn then skips its expansion
+  const uint8_t* t_exp = nullptr;
+  int t_exp_int8 = 1;
 };
 
 struct vsf_ctx {
@@ -135,6 +139,7 @@ struct vsf_ctx {
     cudaEvent_t ev_chain = nullptr;     // main stream: the kernels of this frame have finished
     cudaEvent_t done = nullptr;         // download stream: the lists are in host memory
     uint8_t* h_desc = nullptr;          // pinned staging of the submitted frame
+    uint8_t* d_train_exp = nullptr;     // device: the frame expanded to +-1 bytes on the upload stream
     vsf_dmatch* d_matches = nullptr;    // device: [window][rows_pad] ratio survivors of this frame
     vsf_feature_match* d_fm = nullptr;  // device: [window][rows_pad] sorted + cut (sort_mode 0)
     vsf_dmatch* h_matches = nullptr;    // pinned copy of d_matches (sort_mode 1)
@@ -334,16 +339,23 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       ++c->ktrace_n;
     }
     b.ktrace = kt;
-    for (int k = 0; k < n_trains; ++k)
+    const uint8_t* exp_image[kTcMaxTrains];
+    for (int k = 0; k < n_trains; ++k) {
+      if (train_spec[k]->t_exp && train_spec[k]->t_exp_int8 == int8) {
+        exp_image[k] = train_spec[k]->t_exp;   // expanded by the caller (pipelined path: on the upload stream)
+        continue;
+      }
+      exp_image[k] = c->d_train_exp[k];
       VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
                                       c->d_train_exp[k], int8, pdl, c->stream, kt));
+    }
     TcBatch tb;
     std::memset(&tb, 0, sizeof(tb));
     // Work = (256-query block, piece of train tiles) slots, shared out to the CTAs as equal
     // contiguous ranges (see TcBatch).
     int qblocks = 0;
     for (int i = 0; i < b.num_problems; ++i) {
-      tb.t_exp[i] = c->d_train_exp[train_of[i]];
+      tb.t_exp[i] = exp_image[train_of[i]];
       tb.qb_begin[i] = qblocks;
       qblocks += (specs[i].nq + kTcQ - 1) / kTcQ;
     }
@@ -477,6 +489,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
     for (void* p : fh)
       if (p) cudaFreeHost(p);
     if (f.d_matches) cudaFree(f.d_matches);
+    if (f.d_train_exp) cudaFree(f.d_train_exp);
     if (f.d_fm) cudaFree(f.d_fm);
     for (cudaEvent_t e : {f.ev_up, f.ev_chain, f.done})
       if (e) cudaEventDestroy(e);
@@ -1029,6 +1042,8 @@ static int flights_init(vsf_ctx* c) {
     VSF_CUDA(c, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_desc), N * c->row_bytes));
     VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_matches), list_bytes));
+    if (c->words == 8)
+      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_train_exp), size_t(round_up(c->max_features, kTcTileRows)) * kTcRowBytes));
     VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_fm), list_bytes));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_matches), list_bytes));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_fm), list_bytes));
@@ -1096,6 +1111,12 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
     }
     VSF_CUDA(c, cudaMemcpyAsync(c->slot_ptr(S), src, size_t(n) * c->row_bytes, cudaMemcpyHostToDevice, c->up_stream));
   }
+  // the tensor engine's +-1 image of the frame is made here too, right behind the copy, so the
+  // main stream goes from one frame's compaction straight to the next frame's distance kernel
+  const bool pre_expand = n > 0 && nf > 0 && f.d_train_exp && c->engine != 1;
+  const int exp_int8 = c->engine == 3 ? 0 : 1;
+  if (pre_expand)
+    VSF_CUDA(c, launch_expand_train(c->slot_ptr(S), n, nullptr, f.d_train_exp, exp_int8, 0, c->up_stream, nullptr));
   VSF_CUDA(c, cudaEventRecord(f.ev_up, c->up_stream));
   VSF_CUDA(c, cudaStreamWaitEvent(c->stream, f.ev_up, 0));
   // ---- main stream: every resident past frame (query side) against this frame (train side);
@@ -1104,6 +1125,10 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   for (int j = 0; j < nf; ++j) {
     const int s = c->live[j];
     specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, c->slot_ptr(S), n, nullptr, j});
+    if (pre_expand) {
+      specs.back().t_exp = f.d_train_exp;
+      specs.back().t_exp_int8 = exp_int8;
+    }
   }
   c->match_base = f.d_matches;
   c->mir_dm = nullptr;
