@@ -397,12 +397,19 @@ def run_b200(a):
                 "peak_source": "2 x bf16_tflops (burst) of %s: 8-bit operands run the tensor pipe at twice the "
                                "bf16 rate; ops are int8 multiply-accumulates counted as 2 (TOP/s)" % peak_src,
                 "algorithmic_ops_per_launch": ops,
+                "peak_sustained": 2.0 * float(peaks.get("bf16_tflops_sustained", 0.0)) or None,
+                "frac_of_sustained": (ops / main_s / 1e12 / (2.0 * float(peaks["bf16_tflops_sustained"])))
+                                     if peaks.get("bf16_tflops_sustained") else None,
                 "nominal_peak": 4500.0,
                 "frac_of_nominal": ops / main_s / 1e12 / 4500.0,
                 "other_kernels_ms": {"expand_train": float(kt[0]), "refine": float(kt[2]), "compact": float(kt[3])},
                 "note": "512 ops per 256-bit comparison x comparisons per launch / CUDA-event duration of the "
                         "tensor-core kernel; the refine (exact POPC re-scan of <= 32 train rows per query) and "
-                        "the compaction are separate, small kernels listed in other_kernels_ms",
+                        "the compaction are separate, small kernels listed in other_kernels_ms.  frac is against "
+                        "the burst figure (kernel timed alone); the kernel runs back to back for the whole timed "
+                        "region, for which the driver's sustained figure (frac_of_sustained) is the like-for-like "
+                        "denominator: under tensor load the SM clock the kernel itself sees is ~1.72 GHz, not "
+                        "the 1.965 GHz nvidia-smi reports (profiles/r01_tc_timeline_c4.json)",
             }
         else:
             roofline = {

@@ -87,7 +87,9 @@ int vsf_synchronize(vsf_ctx* ctx);
 /* Kernel tuning knobs; (-1, 0, 0, -1) restores the library defaults.
  * popc_mode: 0 = 8 POPC per 256-bit comparison (the naive count the roofline is
  * quoted against), 2 / 3 = carry-save adder trees with 5 / 4 POPC, -1 = default.
- * train_split: number of train-dimension splits per problem, 0 = automatic.
+ * train_split: POPC engine: number of train-dimension splits per problem; tensor
+ * engine: pieces a query block's train tiles are cut into (granularity of the
+ * per-CTA work ranges); 0 = automatic.
  * queries_per_thread: 1, 2 or 4, 0 = automatic.  variant: 0..3 kernel structure
  * (producer warp / unroll, see csrc/knn2_kernel.cu), -1 = default.
  * Every setting produces bit-identical results. */
@@ -100,7 +102,10 @@ int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
  * int8 operands (tcgen05.mma kind::i8 over +-1 expanded descriptor bits,
  * csrc/knn2_tc_kernel.cu), 3 = tensor cores, e4m3 operands (kind::f8f6f4).
  * The tensor-core engines need desc_bytes <= 32.  Every engine produces
- * bit-identical results.  flags: bring-up knobs, pass 0. */
+ * bit-identical results.  flags: pass 0; 16 / 32 record the per-CTA / per-kernel
+ * timelines read by vsf_debug_tc_trace / vsf_debug_kernel_trace (16, and the
+ * timing-only flags 2 / 4, exist only in libraries built with VSF_TC_TRACE /
+ * VSF_TC_BRINGUP, see vision_slam_frontend_b200/build.py). */
 int vsf_set_engine(vsf_ctx* ctx, int engine, int flags);
 /* Engine (1..3) used by the most recent kNN launch of this ctx. */
 int vsf_last_engine(const vsf_ctx* ctx);

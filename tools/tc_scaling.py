@@ -1,6 +1,8 @@
 """Timing probe for the tensor-core engine's main kernel (run under gpurun): per-kernel CUDA-event
 times (vsf_set_profile) of the window launch for a list of (features, window) shapes and
-bring-up flags, to separate the fixed cost of a launch from the per-tile cost.
+bring-up flags (2 = no bucket reduction, 4 = no TMEM loads; they only act in a library built with
+`VSF_TC_BRINGUP=1 python -m vision_slam_frontend_b200.build --force`), to separate the fixed cost
+of a launch from the per-tile cost.
 
     python tools/tc_scaling.py [out.json]
 """
