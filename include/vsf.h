@@ -329,6 +329,13 @@ int vsf_probe_pipe(vsf_ctx* ctx, int kind, int iters, double* ops_per_second);
 
 int vsf_device_sm_count(const vsf_ctx* ctx);
 
+/* Host-side planner of the tensor engine's work partition, no device needed (CPU tests): for a
+ * launch of query_blocks 256-query blocks against train_tiles 256-row tiles on sm_count SMs,
+ * out5 = {pieces per block, tiles per piece, CTAs, partial slots per query row, segments of
+ * block 0}.  rows / partial_cap: the capacity check of the partial-key buffer (uint2 units). */
+int vsf_debug_tc_plan(int query_blocks, int train_tiles, int sm_count, int force_split,
+                      long long rows, long long partial_cap, int* out5);
+
 /* Bring-up aid: per-CTA timeline of the last tensor-engine launch made with engine flag 16
  * (vsf_set_engine(ctx, 2, 16)): 16 values per CTA, layout documented in
  * csrc/knn2_tc_kernel.cu.  Waits for the ctx stream. */

@@ -238,3 +238,26 @@ def test_tc_per_kernel_times(tc_ctx):
     finally:
         tc_ctx.set_profile(False)
     assert len(ms) == 4 and all(v >= 0 for v in ms) and ms[1] > 0
+
+
+def test_tc_window_c5_size_long_pieces(tc_ctx):
+    """BASELINE config 5's frame size (20000 features), 4 past frames: 25 000 tile slots, which
+    puts the work partition in its "few long pieces per block" regime (>= 128 tiles per SM)."""
+    import torch
+    ctx = tc_ctx
+    n, W, stride, seed = 20000, 4, 2000, 31
+    buf = torch.empty((W + 1, n, 32), dtype=torch.uint8, device="cuda")
+    ctx.synth_sequence_device(buf.data_ptr(), n, 0, W + 1, stride, seed)
+    base = buf.data_ptr()
+    # ragged: the train frame has 19 877 rows, the query frames 20 000, 19 999, ...
+    nt = n - 123
+    nq = [n - j for j in range(W)]
+    ctx.window_match_device([base + j * n * 32 for j in range(W)], nq, base + W * n * 32, nt, RATIO)
+    assert ctx.last_engine >= 2
+    got = ctx.fetch_window(W)
+    host = buf.cpu().numpy()
+    total = 0
+    for j in range(W):
+        np.testing.assert_array_equal(got[j], native.get_matches(host[j][:nq[j]], host[W][:nt], RATIO))
+        total += len(got[j])
+    assert total > 10000

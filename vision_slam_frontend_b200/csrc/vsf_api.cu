@@ -3,6 +3,10 @@
 // every entry point reports VSF_ERR_CUDA.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#ifdef __linux__
+#include <sys/prctl.h>
+#endif
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -174,6 +178,7 @@ struct vsf_ctx {
   std::deque<Flight*> disp_q;
   std::deque<SortTask> pool_q;
   bool pool_stop = false;
+  bool dispatch_spin = false;   // dispatcher waits with cudaEventSynchronize (spins on a core) instead of polling
   Flight flights[VSF_PIPELINE_DEPTH];
   cudaStream_t up_stream = nullptr, down_stream = nullptr;   // copy engines of the pipelined path
   cudaEvent_t ev_main = nullptr;
@@ -251,6 +256,50 @@ static int upload_xy(vsf_ctx* c, int which, const vsf_keypoint* kp, int n, float
   for (int i = 0; i < n; ++i) h[i] = make_float2(kp[i].x, kp[i].y);
   VSF_CUDA(c, cudaMemcpyAsync(d_dst, h, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
   return VSF_OK;
+}
+
+// Granularity of the tensor engine's work slots and number of CTAs (see TcBatch): fills
+// pieces / tiles_per_piece / total / grid / slots from tb->tiles and the shape of the launch.
+// Pure host arithmetic (also exported as vsf_debug_tc_plan for the CPU tests).
+static void plan_tc_partition(TcBatch* tbp, int qblocks, int sm, int force_split, size_t rows, size_t partial_cap) {
+  TcBatch& tb = *tbp;
+  const long long tile_slots = (long long)qblocks * tb.tiles;
+  int S = tb.tiles;                  // pieces per block; default: one tile per piece
+  long long G = 0;                   // 0: one CTA per SM (or per slot when there are fewer)
+  if (force_split > 0) {
+    // tuning knob (tests): about force_split pieces per block, one piece per CTA when they fit
+    S = std::min(force_split, tb.tiles);
+    if ((long long)qblocks * S <= sm) G = (long long)qblocks * S;
+  } else if (tile_slots < 4LL * sm && qblocks <= sm) {
+    // small launch: one piece of one block per CTA, as many pieces as fill the machine once
+    S = int(std::max<long long>(1, std::min<long long>(tb.tiles, sm / qblocks)));
+    G = (long long)qblocks * S;
+  } else if (tile_slots > 128LL * sm) {
+    // very large launch: a few long pieces per block; maximise (fill of the last round of
+    // pieces) x (piece length vs ~1.5 tiles of fixed cost per segment)
+    double best = -1.0;
+    for (int cand = 1; cand <= std::min(tb.tiles, 16); ++cand) {
+      const int tpp = (tb.tiles + cand - 1) / cand;
+      const long long P = (long long)qblocks * ((tb.tiles + tpp - 1) / tpp);
+      const long long rounds = (P + sm - 1) / sm;
+      const double eff = double(P) / double(rounds * sm) * double(tpp) / (double(tpp) + 1.5);
+      if (eff > best + 1e-9) { best = eff; S = cand; }
+    }
+  }
+  for (;;) {
+    S = std::max(1, std::min(S, tb.tiles));
+    tb.tiles_per_piece = (tb.tiles + S - 1) / S;
+    tb.pieces = (tb.tiles + tb.tiles_per_piece - 1) / tb.tiles_per_piece;   // drop pieces that would be empty
+    tb.total = (long long)qblocks * tb.pieces;
+    long long g = G > 0 ? std::min<long long>(G, tb.total) : std::min<long long>(sm, tb.total);
+    if (G > 0 && (long long)qblocks * tb.pieces <= sm) g = tb.total;          // one piece per CTA
+    // a block's `pieces` consecutive slots cross at most 1 + ceil((pieces - 1) / shortest range) ranges
+    const long long lmin = tb.total / g;
+    tb.slots = int(std::min<long long>(tb.pieces, 1 + (tb.pieces - 1 + lmin - 1) / lmin));
+    tb.grid = int(g);
+    if (S == 1 || rows * size_t(tb.slots) * 2 <= partial_cap) break;   // x2: column halves of the epilogue
+    S = (S + 1) / 2;                 // coarser pieces, fewer segments per block
+  }
 }
 
 // Build the batch, choose (R, split) and launch kernel 1.
@@ -367,45 +416,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       VSF_CUDA(c, cudaMemsetAsync(c->d_tc_trace, 0, size_t(c->sm_count) * kTcTraceSlots * sizeof(long long), c->stream));
       tb.trace = c->d_tc_trace;
     }
-    // Granularity of the slots and number of CTAs (see TcBatch).
-    const int sm = c->sm_count;
-    const long long tile_slots = (long long)qblocks * tb.tiles;
-    int S = tb.tiles;                  // pieces per block; default: one tile per piece
-    long long G = 0;                   // 0: one CTA per SM (or per slot when there are fewer)
-    if (c->force_split > 0) {
-      // tuning knob (tests): about force_split pieces per block, one piece per CTA when they fit
-      S = std::min(c->force_split, tb.tiles);
-      if ((long long)qblocks * S <= sm) G = (long long)qblocks * S;
-    } else if (tile_slots < 4LL * sm && qblocks <= sm) {
-      // small launch: one piece of one block per CTA, as many pieces as fill the machine once
-      S = int(std::max<long long>(1, std::min<long long>(tb.tiles, sm / qblocks)));
-      G = (long long)qblocks * S;
-    } else if (tile_slots > 128LL * sm) {
-      // very large launch: a few long pieces per block; maximise (fill of the last round of
-      // pieces) x (piece length vs ~1.5 tiles of fixed cost per segment)
-      double best = -1.0;
-      for (int cand = 1; cand <= std::min(tb.tiles, 16); ++cand) {
-        const int tpp = (tb.tiles + cand - 1) / cand;
-        const long long P = (long long)qblocks * ((tb.tiles + tpp - 1) / tpp);
-        const long long rounds = (P + sm - 1) / sm;
-        const double eff = double(P) / double(rounds * sm) * double(tpp) / (double(tpp) + 1.5);
-        if (eff > best + 1e-9) { best = eff; S = cand; }
-      }
-    }
-    for (;;) {
-      S = std::max(1, std::min(S, tb.tiles));
-      tb.tiles_per_piece = (tb.tiles + S - 1) / S;
-      tb.pieces = (tb.tiles + tb.tiles_per_piece - 1) / tb.tiles_per_piece;   // drop pieces that would be empty
-      tb.total = (long long)qblocks * tb.pieces;
-      long long g = G > 0 ? std::min<long long>(G, tb.total) : std::min<long long>(sm, tb.total);
-      if (G > 0 && (long long)qblocks * tb.pieces <= sm) g = tb.total;          // one piece per CTA
-      // a block's `pieces` consecutive slots cross at most 1 + ceil((pieces - 1) / shortest range) ranges
-      const long long lmin = tb.total / g;
-      tb.slots = int(std::min<long long>(tb.pieces, 1 + (tb.pieces - 1 + lmin - 1) / lmin));
-      tb.grid = int(g);
-      if (S == 1 || size_t(row0) * tb.slots * 2 <= c->partial_cap) break;   // x2: column halves of the epilogue
-      S = (S + 1) / 2;                 // coarser pieces, fewer segments per block
-    }
+    plan_tc_partition(&tb, qblocks, c->sm_count, c->force_split, size_t(row0), c->partial_cap);
     b.split = tb.slots;
     VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
     c->pev_valid = c->profile != 0;
@@ -999,6 +1010,9 @@ static void pool_worker(vsf_ctx* c) {
 
 static void pool_dispatcher(vsf_ctx* c) {
   cudaSetDevice(c->device);
+#ifdef __linux__
+  prctl(PR_SET_TIMERSLACK, 1UL, 0UL, 0UL, 0UL);   // this thread's short sleeps should be short
+#endif
   for (;;) {
     vsf_ctx::Flight* f;
     {
@@ -1010,7 +1024,17 @@ static void pool_dispatcher(vsf_ctx* c) {
     }
     // once the event completes the survivors + counts of the frame are in host memory; every
     // past frame's list then becomes one task, longest first (they bound the finish time)
-    const cudaError_t e = cudaEventSynchronize(f->done);
+    // Poll with short sleeps instead of cudaEventSynchronize: that call spins on a core the sort
+    // workers can use (a blocking-sync event frees the core too, but its wake-up latency under
+    // load cost 20 us per frame on a 16-core host); the few tens of microseconds a sleep may
+    // overshoot are hidden by the frames in flight.
+    cudaError_t e;
+    if (c->dispatch_spin) {
+      e = cudaEventSynchronize(f->done);
+    } else {
+      while ((e = cudaEventQuery(f->done)) == cudaErrorNotReady)
+        std::this_thread::sleep_for(std::chrono::microseconds(10));
+    }
     if (e != cudaSuccess) f->cuda_error = int(e);
     const int nf = (e == cudaSuccess) ? f->nf : 0;
     if (nf > 0) {
@@ -1055,8 +1079,13 @@ static int flights_init(vsf_ctx* c) {
   }
   // worker threads for the host-side finish of sort_mode 1: lists of different frames in flight
   // are sorted concurrently, so the host keeps up with the device
-  // (the caller's thread and the dispatcher keep a core each)
-  const int nworkers = std::max(1, c->host_threads - 2);
+  // The dispatcher sleeps between frames; the caller's thread and the CUDA driver's own threads
+  // need about two cores (measured on a 16-core host: 13 or 14 workers 58.4 us/pose, 15 workers
+  // 64.3), which a small share of a many-GPU host cannot spare (4 threads: 3 workers 158 us/pose,
+  // 2 workers 235).
+  int nworkers = c->host_threads >= 8 ? c->host_threads - 2 : std::max(1, c->host_threads - 1);
+  if (const char* e = std::getenv("VSF_SORT_WORKERS")) nworkers = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("VSF_DISPATCH_SPIN")) c->dispatch_spin = std::atoi(e) != 0;
   for (int i = 0; i < nworkers; ++i) c->workers.emplace_back(pool_worker, c);
   c->dispatcher = std::thread(pool_dispatcher, c);
   c->flights_ready = true;
@@ -1451,6 +1480,22 @@ extern "C" int vsf_synth_sequence_device(vsf_ctx* c, void* d_out, int n, int fir
     return fail(c, VSF_ERR_BAD_ARG, "bad synth arguments (generator produces 32-byte rows)");
   cudaSetDevice(c->device);
   VSF_CUDA(c, launch_synth(static_cast<uint32_t*>(d_out), n, first_pose, n_poses, stride, seed, c->stream));
+  return VSF_OK;
+}
+
+extern "C" int vsf_debug_tc_plan(int query_blocks, int train_tiles, int sm_count, int force_split,
+                                 long long rows, long long partial_cap, int* out5) {
+  if (query_blocks < 1 || train_tiles < 1 || sm_count < 1 || force_split < 0 || rows < 0 || partial_cap < 0 || !out5)
+    return VSF_ERR_BAD_ARG;
+  TcBatch tb;
+  std::memset(&tb, 0, sizeof(tb));
+  tb.tiles = train_tiles;
+  plan_tc_partition(&tb, query_blocks, sm_count, force_split, size_t(rows), size_t(partial_cap));
+  out5[0] = tb.pieces;
+  out5[1] = tb.tiles_per_piece;
+  out5[2] = tb.grid;
+  out5[3] = tb.slots;
+  out5[4] = tc_block_segments(tb, 0);   // segments of the first block (host copy of the device formula)
   return VSF_OK;
 }
 
