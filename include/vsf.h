@@ -329,6 +329,11 @@ int vsf_probe_pipe(vsf_ctx* ctx, int kind, int iters, double* ops_per_second);
 
 int vsf_device_sm_count(const vsf_ctx* ctx);
 
+/* Host side of the sort + cut of sort_mode 1, no device needed (CPU tests): keys are
+ * (distance << 22 | position); afterwards keys[0 .. keep) are what std::sort by distance leaves
+ * there (csrc/exact_sort.h). */
+int vsf_debug_sort_prefix(uint32_t* keys, int n, int keep);
+
 /* Host-side planner of the tensor engine's work partition, no device needed (CPU tests): for a
  * launch of query_blocks 256-query blocks against train_tiles 256-row tiles on sm_count SMs,
  * out5 = {pieces per block, tiles per piece, CTAs, partial slots per query row, segments of

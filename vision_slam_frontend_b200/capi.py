@@ -102,6 +102,7 @@ def load_library():
         "vsf_debug_tc_trace": ([vp, vp, i, C.POINTER(i)], i),
         "vsf_debug_kernel_trace": ([vp, vp, i, C.POINTER(i)], i),
         "vsf_debug_tc_plan": ([i, i, i, i, C.c_longlong, C.c_longlong, vp], i),
+        "vsf_debug_sort_prefix": ([vp, i, i], i),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)   # AttributeError if the library lacks a declared symbol
@@ -121,7 +122,7 @@ EXPORTED_SYMBOLS = [
     "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_observe_features",
     "vsf_device_row_bytes", "vsf_window_match_device", "vsf_fetch_window",
     "vsf_synth_sequence_device", "vsf_probe_pipe", "vsf_device_sm_count",
-    "vsf_debug_tc_trace", "vsf_debug_kernel_trace", "vsf_debug_tc_plan",
+    "vsf_debug_tc_trace", "vsf_debug_kernel_trace", "vsf_debug_tc_plan", "vsf_debug_sort_prefix",
 ]
 
 

@@ -17,6 +17,7 @@
 #include <thread>
 #include <vector>
 
+#include "exact_sort.h"
 #include "stereo_args.cuh"
 #include "vsf_device.cuh"
 
@@ -896,15 +897,13 @@ namespace {
 // of moves depends only on the comparison results and the element count, never on the element
 // type, so sorting 4-byte (distance << 22 | position) keys with a distance-only comparator
 // yields exactly the permutation the reference gets on its 16-byte DMatch records, at a
-// fraction of the memory traffic.  Returns the kept count.
-struct ByKeyDistance {
-  bool operator()(uint32_t a, uint32_t b) const { return (a >> kIdxBits) < (b >> kIdxBits); }
-};
+// fraction of the memory traffic.  Only the part of the sort that can reach the first `keep`
+// positions is carried out (exact_sort.h).  Returns the kept count.
 int sort_cut_list(const vsf_dmatch* m, int n, float best_percent, uint32_t* keys, vsf_feature_match* out, int cap) {
   const int keep = int(float(size_t(n)) * best_percent);   // float multiply, truncation (:290)
   if (keep > cap) return -1;
   for (int i = 0; i < n; ++i) keys[i] = (uint32_t(int(m[i].distance)) << kIdxBits) | uint32_t(i);
-  std::sort(keys, keys + n, ByKeyDistance());
+  vsf_exact_sort::sort_prefix<kIdxBits>(keys, n, keep);
   for (int i = 0; i < keep; ++i) {
     const vsf_dmatch& d = m[keys[i] & kIdxMask];
     out[i].feature_idx_initial = uint64_t(d.queryIdx);
@@ -1480,6 +1479,12 @@ extern "C" int vsf_synth_sequence_device(vsf_ctx* c, void* d_out, int n, int fir
     return fail(c, VSF_ERR_BAD_ARG, "bad synth arguments (generator produces 32-byte rows)");
   cudaSetDevice(c->device);
   VSF_CUDA(c, launch_synth(static_cast<uint32_t*>(d_out), n, first_pose, n_poses, stride, seed, c->stream));
+  return VSF_OK;
+}
+
+extern "C" int vsf_debug_sort_prefix(uint32_t* keys, int n, int keep) {
+  if (n < 0 || keep < 0 || keep > n || (n > 0 && !keys)) return VSF_ERR_BAD_ARG;
+  vsf_exact_sort::sort_prefix<kIdxBits>(keys, n, keep);
   return VSF_OK;
 }
 
