@@ -253,6 +253,9 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None   # set when file descriptor 1 has been redirected (multi-rank runs)
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -268,7 +271,15 @@ def run_b200(a):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("VSF_NCCL_DEBUG", "WARN")   # keep stdout = one JSON line
+        # keep stdout = one JSON line: NCCL writes its version banner (and any NCCL_DEBUG output)
+        # to file descriptor 1 from native code, so the descriptor itself is pointed at stderr and
+        # the JSON line goes to a saved copy of the real stdout
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        if "VSF_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["VSF_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, W = a.features, a.window
@@ -460,7 +471,7 @@ def run_b200(a):
             line["nccl_gathered_matches"] = gathered
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT or sys.stdout, flush=True)
     ctx.close()
     if world > 1:
         dist.barrier()
