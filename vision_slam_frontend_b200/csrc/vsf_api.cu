@@ -82,7 +82,9 @@ struct vsf_ctx {
   long long* d_ktrace = nullptr;     // engine flag 32: kernel-level timeline, kKtracePoses records of [5][2]
   long long ktrace_n = 0;
   int last_engine = 0;    // engine the last kNN launch used
-  double tc_auto_min_cmp = 1e7;  // automatic mode: tensor cores from this many comparisons per batch
+  // automatic mode: tensor cores from this many comparisons per batch (measured crossover,
+  // tools/engine_crossover.py: 1e6 POPC 12 us vs 20; 4e6 18 vs 14; 2.5e7 52 vs 24)
+  double tc_auto_min_cmp = 3e6;
   uint8_t* d_train_exp[kTcMaxTrains] = {nullptr, nullptr};  // +-1 expanded train images
 
   int rows_pad = 0;    // max_features rounded up to 128
