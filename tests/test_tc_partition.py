@@ -78,7 +78,9 @@ def test_plan_small_launch_is_one_piece_per_cta():
     pieces, tpp, G, slots = check(8, 8, 148)              # C2 on the tensor engine
     assert G == 8 * pieces and slots == pieces
     pieces, tpp, G, slots = check(20, 20, 148)            # 5000 x 5000, one pair
-    assert (pieces, tpp, G) == (7, 3, 140)
+    assert (pieces, tpp, G) == (5, 4, 100)                # about two thirds of the SMs, not all of them
+    pieces, tpp, G, slots = check(12, 12, 148)            # 3000 x 3000
+    assert (pieces, tpp, G) == (6, 2, 72)
 
 
 def test_plan_very_large_launch_uses_long_pieces():

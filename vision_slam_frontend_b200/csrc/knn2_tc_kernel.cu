@@ -585,16 +585,31 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     // the query block's tile slots were shared out to consecutive CTAs, one partial segment each
     const int nseg = tc_block_segments(tc, tc.qb_begin[blockIdx.y] + q / kTcQ);
     const int np = nseg * kTcColSplit;
-    const uint2* part = reinterpret_cast<const uint2*>(batch.partial) + size_t(P.row0 + q) * (tc.slots * kTcColSplit);
-#pragma unroll 4
-    for (int z = 0; z < np; ++z) {
-      const uint2 p = __ldcg(part + z);
-      const int a1 = int(p.x), a2 = int(p.y);
-      // merge two descending pairs
+    // a segment's two column-half partials are one aligned 16-byte record; four records are
+    // fetched together so that a block cut into many segments costs one L2 round trip per four
+    // segments, not one per partial
+    static_assert(kTcColSplit == 2, "one uint4 = the two column-half partials of a segment");
+    const uint4* part = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(batch.partial) +
+                                                        size_t(P.row0 + q) * (tc.slots * kTcColSplit));
+    auto merge = [&](int a1, int a2) {   // merge two descending pairs
       const int hi = max(b1, a1), lo = min(b1, a1);
       b2 = max(lo, max(b2, a2));
       b1 = hi;
+    };
+    for (int z0 = 0; z0 < nseg; z0 += 4) {
+      uint4 p[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        p[j] = (z0 + j < nseg) ? __ldcg(part + z0 + j)
+                               : make_uint4(uint32_t(kTcKeySentinel), uint32_t(kTcKeySentinel),
+                                            uint32_t(kTcKeySentinel), uint32_t(kTcKeySentinel));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        merge(int(p[j].x), int(p[j].y));
+        merge(int(p[j].z), int(p[j].w));
+      }
     }
+    (void)np;
     key = c ? b2 : b1;
   }
   // first train row of this lane's candidate bucket, -1 = none

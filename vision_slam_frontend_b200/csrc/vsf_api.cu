@@ -274,8 +274,13 @@ static void plan_tc_partition(TcBatch* tbp, int qblocks, int sm, int force_split
     S = std::min(force_split, tb.tiles);
     if ((long long)qblocks * S <= sm) G = (long long)qblocks * S;
   } else if (tile_slots < 4LL * sm && qblocks <= sm) {
-    // small launch: one piece of one block per CTA, as many pieces as fill the machine once
-    S = int(std::max<long long>(1, std::min<long long>(tb.tiles, sm / qblocks)));
+    // small launch: one piece of one block per CTA.  Not as many pieces as there are SMs: these
+    // launches are a few tile times long and bound by the latencies of the four kernels, which
+    // overlap better (programmatic dependent launch) when the distance kernel leaves about a
+    // third of the SMs to its neighbours - measured optimum 64..100 CTAs on 148 SMs for every
+    // shape tried, with a cliff above ~120 (3000 x 3000: 72 CTAs 14.9 us, 144 CTAs 22.3)
+    const long long cap = std::max<long long>(1, (long long)sm * 11 / 16);
+    S = int(std::max<long long>(1, std::min<long long>(tb.tiles, cap / qblocks)));
     G = (long long)qblocks * S;
   } else if (tile_slots > 128LL * sm) {
     // very large launch: a few long pieces per block; maximise (fill of the last round of
