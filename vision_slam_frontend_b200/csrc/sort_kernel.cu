@@ -27,6 +27,7 @@ struct SortArgs {
   int out_stride;
   int* out_counts;
   float best_percent;
+  int bins;   // distances are 0 .. 8 * row_bytes: 257 bins for 32-byte descriptors, 513 for 64-byte ones
 };
 
 __global__ void __launch_bounds__(kSortThreads) sort_cut_kernel(const __grid_constant__ SortArgs a) {
@@ -35,12 +36,15 @@ __global__ void __launch_bounds__(kSortThreads) sort_cut_kernel(const __grid_con
   const int p = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const vsf_dmatch* m = a.matches[p];
+  const int nbins = a.bins;
+  // clearing the histograms overlaps the tail of the compaction kernel (programmatic dependent launch)
+  for (int b = lane; b < nbins; b += 32) s_hist[warp][b] = 0;   // every warp clears its own histogram
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = *a.counts[p];
   // `matches.size() * config_.best_percent_` truncated to int (src/slam_frontend.cc:290)
   const int keep = int(__fmul_rn(float(size_t(n)), a.best_percent));
   vsf_feature_match* out = a.out + size_t(p) * a.out_stride;
-
-  for (int i = tid; i < kSortWarps * kBins; i += kSortThreads) (&s_hist[0][0])[i] = 0;
   __syncthreads();
 
   const int seg = ((n + kSortWarps - 1) / kSortWarps + 31) & ~31;
@@ -51,12 +55,12 @@ __global__ void __launch_bounds__(kSortThreads) sort_cut_kernel(const __grid_con
     const bool ok = i < end;
     const uint32_t d = ok ? uint32_t(int(m[i].distance)) : (0xFFFF0000u + lane);
     const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (ok && (peers & ((1u << lane) - 1u)) == 0) s_hist[warp][min(d, uint32_t(kBins - 1))] += __popc(peers);
+    if (ok && (peers & ((1u << lane) - 1u)) == 0) s_hist[warp][min(d, uint32_t(nbins - 1))] += __popc(peers);
     __syncwarp();
   }
   __syncthreads();
   // per bin: exclusive offsets across warps, bin totals
-  for (int b = tid; b < kBins; b += kSortThreads) {
+  for (int b = tid; b < nbins; b += kSortThreads) {
     uint32_t tot = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
@@ -69,16 +73,16 @@ __global__ void __launch_bounds__(kSortThreads) sort_cut_kernel(const __grid_con
   __syncthreads();
   if (warp == 0) {
     uint32_t run = 0;
-    for (int b0 = 0; b0 < kBins; b0 += 32) {
+    for (int b0 = 0; b0 < nbins; b0 += 32) {
       const int b = b0 + lane;
-      const uint32_t c = (b < kBins) ? s_start[b] : 0u;
+      const uint32_t c = (b < nbins) ? s_start[b] : 0u;
       uint32_t incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
-      if (b < kBins) s_start[b] = run + incl - c;
+      if (b < nbins) s_start[b] = run + incl - c;
       run += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_cut_kernel(const __grid_con
     const bool ok = i < end;
     vsf_dmatch dm = {0, 0, 0, 0.f};
     if (ok) dm = m[i];
-    const uint32_t d = ok ? min(uint32_t(int(dm.distance)), uint32_t(kBins - 1)) : (0xFFFF0000u + lane);
+    const uint32_t d = ok ? min(uint32_t(int(dm.distance)), uint32_t(nbins - 1)) : (0xFFFF0000u + lane);
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     if (ok) {
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_cut_kernel(const __grid_con
 
 cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* counts, int n_problems,
                             float best_percent, vsf_feature_match* out, int out_stride, int* out_counts,
-                            int /*max_matches*/, cudaStream_t stream) {
+                            int bins, cudaStream_t stream) {
   if (n_problems <= 0) return cudaSuccess;
   if (n_problems > kMaxProblems) return cudaErrorInvalidValue;
   SortArgs a;
@@ -121,8 +125,17 @@ cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* 
   a.out_stride = out_stride;
   a.out_counts = out_counts;
   a.best_percent = best_percent;
-  sort_cut_kernel<<<n_problems, kSortThreads, 0, stream>>>(a);
-  return cudaGetLastError();
+  a.bins = bins > 1 && bins <= kBins ? bins : kBins;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_problems);
+  cfg.blockDim = dim3(kSortThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, sort_cut_kernel, a);
 }
 
 }  // namespace vsf

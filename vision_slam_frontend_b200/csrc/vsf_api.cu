@@ -41,7 +41,7 @@ cudaError_t launch_triangulate_matches(const float* P1, const float* P2, const v
                                        float4* X4, cudaStream_t stream);
 cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* counts,
                             int n_problems, float best_percent, vsf_feature_match* out,
-                            int out_stride, int* out_counts, int max_matches, cudaStream_t stream);
+                            int out_stride, int* out_counts, int bins, cudaStream_t stream);
 }  // namespace vsf
 
 
@@ -942,7 +942,7 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
     }
     if (nf > 0) {
       VSF_CUDA(c, launch_sort_cut(mp.data(), cp.data(), nf, best_percent, c->d_fm, c->rows_pad,
-                                  c->d_fm_count, max_matches, c->stream));
+                                  c->d_fm_count, 8 * c->row_bytes + 1, c->stream));
       VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_fm_count, nf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       VSF_CUDA(c, cudaStreamSynchronize(c->stream));
       for (int j = 0; j < nf; ++j)
@@ -1178,7 +1178,7 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
       mp[j] = c->region_ptr(j);
       cp[j] = c->d_match_count + j;
     }
-    const cudaError_t e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, c->max_features, c->stream);
+    const cudaError_t e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, 8 * c->row_bytes + 1, c->stream);
     if (e != cudaSuccess) {
       c->err = std::string("launch_sort_cut: ") + cudaGetErrorString(e);
       rc = VSF_ERR_CUDA;
