@@ -11,7 +11,9 @@ constexpr int kScanChunk = 256;
 
 struct TailSmem {
   uint32_t off[kScanChunk];
-  int flag;
+  int flag;     // this CTA is the last one of its problem
+  int total;    // running survivor count after the chunk being scanned (its own word: warp 0 may
+                // write it while slower warps are still reading `flag`)
 };
 
 // Called by every thread of the CTA (blockDim.x = NTHREADS >= QB, a multiple of 32).
@@ -76,7 +78,7 @@ __device__ __forceinline__ void finalize_and_compact(const KnnBatch& batch, cons
         if (i < cn) sm.off[i] = run + incl - c;
         run += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (lane == 0) sm.flag = int(run);
+      if (lane == 0) sm.total = int(run);
     }
     __syncthreads();
     for (int b = warp; b < cn; b += NWARPS) {
@@ -105,7 +107,7 @@ __device__ __forceinline__ void finalize_and_compact(const KnnBatch& batch, cons
       }
     }
     __syncthreads();
-    base = uint32_t(sm.flag);
+    base = uint32_t(sm.total);
     __syncthreads();
   }
   if (tid == 0) {
