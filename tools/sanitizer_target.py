@@ -29,4 +29,28 @@ with vsf.Context(device=0, max_features=4096, desc_bytes=32, window=3) as ctx:
         ctx.window_submit(100 + p, D, ratio, 0.3, p % 2, False)
     while ctx.window_in_flight():
         ctx.window_collect()
+# the fused ObserveImage path: stereo match + residual filter + compaction, window, triangulation
+P1, P2 = synth.kitti_projections()
+F = synth.kitti_fundamental()
+for eng in (0, 2):
+    with vsf.Context(device=0, max_features=4096, desc_bytes=32, window=3) as ctx:
+        ctx.set_engine(eng, 0)
+        for p, (kl, dl, kr, dr) in enumerate(synth.stereo_sequence(4, 1800 if eng else 500, seed=6)):
+            ctx.observe_features(p, kl, dl, kr, dr, F, P1, P2, ratio)
+# blocking window calls with the device sort and the host sort; 64-byte descriptors (POPC engine)
+with vsf.Context(device=0, max_features=2048, desc_bytes=32, window=3) as ctx:
+    for p in range(5):
+        D = synth.synth_pose(1500 - 31 * p, p, 150, 3)
+        for mode in (0, 1):
+            ctx.window_feature_matches(D, ratio, 0.3, mode)
+        ctx.window_match(D, ratio)
+        ctx.window_commit(p, len(D))
+with vsf.Context(device=0, max_features=1024, desc_bytes=61, window=2) as ctx:
+    Q, T = synth.descriptor_pair(700, 650, width=61, seed=8)
+    idx, dist = ctx.knn2(Q, T)
+    ei, ed = native.knn2_hamming(Q, T)
+    assert (idx == ei).all() and (dist == ed).all()
+x1 = np.random.default_rng(0).random((300, 2), dtype=np.float32) * 300
+with vsf.Context(device=0, max_features=1024, desc_bytes=32, window=2) as ctx:
+    ctx.triangulate(P1, P2, x1, x1 + np.float32([5, 0]))
 print("sanitizer target ok")

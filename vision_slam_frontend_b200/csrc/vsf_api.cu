@@ -656,6 +656,16 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   c->slot_frame.assign(c->ring_slots, 0);
   c->slot_last_chain.assign(c->ring_slots, nullptr);
   reset_ring(c);
+  // result buffers are read back up to a bound in places: start from zeros, not from whatever
+  // the allocator handed out
+  cudaMemset(c->d_knn_out, 0, rows_cap * sizeof(uint4));
+  cudaMemset(c->d_matches, 0, rows_cap * sizeof(vsf_dmatch));
+  cudaMemset(c->d_fm, 0, size_t(window) * N * sizeof(vsf_feature_match));
+  cudaMemset(c->d_X4, 0, N * sizeof(float4));
+  cudaMemset(c->d_resid, 0, N * sizeof(float));
+  cudaMemset(c->d_kept_left, 0, N * sizeof(int));
+  cudaMemset(c->d_kept_right, 0, N * sizeof(int));
+  cudaMemset(c->d_tri_io, 0, N * 8 * sizeof(float));
   if (cudaDeviceSynchronize() != cudaSuccess) {
     vsf_destroy(c);
     return VSF_ERR_CUDA;
@@ -1075,6 +1085,9 @@ static int flights_init(vsf_ctx* c) {
     if (c->words == 8)
       VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_train_exp), size_t(round_up(c->max_features, kTcTileRows)) * kTcRowBytes));
     VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_fm), list_bytes));
+    // lists are downloaded up to their bound, not their (device-side) length: start from zeros
+    VSF_CUDA(c, cudaMemset(f.d_matches, 0, list_bytes));
+    VSF_CUDA(c, cudaMemset(f.d_fm, 0, list_bytes));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_matches), list_bytes));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_fm), list_bytes));
     VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_counts), kMaxProblems * sizeof(int), cudaHostAllocMapped));
