@@ -216,17 +216,91 @@ def test_tc_window_c4_full_size_device_entry_point(tc_ctx):
     assert total > 10000
 
 
-def test_tc_rejects_64_byte_descriptors():
+@pytest.mark.parametrize("width", [61, 64])
+def test_tc_wide_descriptors_against_opencv_golden(width):
+    """64-byte rows (AKAZE's 61 bytes zero-padded, BRISK's 64) on the tensor cores
+    (csrc/knn2_tc64_kernel.cu): the OpenCV golden vectors, bit-exact; the e4m3 engine does not
+    exist for this width."""
     import vision_slam_frontend_b200 as vsf
-    with vsf.Context(device=0, max_features=1024, desc_bytes=64, window=2) as ctx:
+    g = np.load(os.path.join(GOLD, f"knn_planted_{width}.npz"))
+    with vsf.Context(device=0, max_features=4096, desc_bytes=width, window=2) as ctx:
         with pytest.raises(vsf.VsfError):
-            ctx.set_engine(2, 0)
-        Q, T = synth.descriptor_pair(500, 600, width=64, seed=8)
+            ctx.set_engine(3, 0)
+        ctx.set_engine(2, 0)
+        idx, dist = ctx.knn2(g["Q"], g["T"])
+        assert ctx.last_engine == 2
+        np.testing.assert_array_equal(idx, g["idx"])
+        np.testing.assert_array_equal(dist, g["dist"])
+        ctx.set_engine(1, 0)
+        i1, d1 = ctx.knn2(g["Q"], g["T"])
+        np.testing.assert_array_equal(i1, g["idx"])
+        np.testing.assert_array_equal(d1, g["dist"])
+
+
+@pytest.mark.parametrize("width", [61, 64])
+@pytest.mark.parametrize("split", [0, 1, 3, 8])
+def test_tc_wide_descriptors_ragged_sizes(width, split):
+    import vision_slam_frontend_b200 as vsf
+    with vsf.Context(device=0, max_features=5200, desc_bytes=width, window=2) as ctx:
+        ctx.set_engine(2, 0)
+        ctx.set_tuning(-1, split, 0, -1)
+        for (nq, nt, seed) in [(128, 128, 1), (129, 300, 3), (1000, 33, 5), (77, 1, 6), (300, 4097, 8), (2300, 2100, 4),
+                               (5000, 5000, 7)]:
+            Q, T = synth.descriptor_pair(nq, nt, width=width, seed=seed)
+            ei, ed = native.knn2_hamming(Q, T)
+            idx, dist = ctx.knn2(Q, T)
+            assert ctx.last_engine == 2
+            np.testing.assert_array_equal(idx, ei)
+            np.testing.assert_array_equal(dist, ed)
+            np.testing.assert_array_equal(ctx.get_matches(Q, T, RATIO), native.get_matches(Q, T, RATIO))
+        Q, T = synth.tie_pair(900, 1100, width=width)      # adversarial ties: lowest train index twice
         ei, ed = native.knn2_hamming(Q, T)
-        idx, dist = ctx.knn2(Q, T)                 # automatic choice falls back to the POPC kernel
-        assert ctx.last_engine == 1
+        idx, dist = ctx.knn2(Q, T)
         np.testing.assert_array_equal(idx, ei)
         np.testing.assert_array_equal(dist, ed)
+
+
+@pytest.mark.parametrize("sort_mode", [0, 1])
+def test_tc_wide_descriptors_window_and_pipeline(sort_mode):
+    """61-byte frames through the blocking window call and the pipelined frame stream on the
+    tensor cores: lists as the reference's loop produces them (src/slam_frontend.cc:424-434)."""
+    import vision_slam_frontend_b200 as vsf
+    rng = np.random.default_rng(3)
+    n, W, width = 1400, 3, 61
+    base = rng.integers(0, 256, (n + 800, width), dtype=np.uint8)
+    frames = []
+    for p in range(7):
+        D = base[100 * p: 100 * p + n - 37 * (p % 3)].copy()
+        flips = rng.integers(0, 8 * width, (len(D), 6))
+        for j in range(flips.shape[1]):
+            D[np.arange(len(D)), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+        frames.append(D[rng.permutation(len(D))])
+    bp = restate.BEST_PERCENT
+    with vsf.Context(device=0, max_features=2048, desc_bytes=width, window=W) as ctx:
+        ctx.set_engine(2, 0)
+        live, expected = [], []
+        for p, D in enumerate(frames):
+            if ctx.window_in_flight() == vsf.PIPELINE_DEPTH:
+                break
+            ctx.window_submit(p, D, RATIO, float(bp), sort_mode, False)
+            expected.append((p, list(live), D))
+            if len(live) >= W:
+                live.pop(0)
+            live.append((p, D))
+        assert ctx.last_engine == 2
+        while expected:
+            fid, got = ctx.window_collect()
+            efid, elive, D = expected.pop(0)
+            assert fid == efid and len(got) == len(elive)
+            for (pfid, pairs), (pid, past) in zip(got, elive):
+                assert pfid == pid
+                m = native.get_matches(past, D, RATIO)
+                keep = restate.num_good_matches(len(m), bp)
+                order = restate.sort_order_stdsort(m) if sort_mode == 1 else restate.sort_order_stable(m)
+                exp = m[order][:keep]
+                assert len(pairs) == keep and keep > 100
+                np.testing.assert_array_equal(pairs[:, 0], exp["queryIdx"].astype(np.uint64))
+                np.testing.assert_array_equal(pairs[:, 1], exp["trainIdx"].astype(np.uint64))
 
 
 def test_tc_per_kernel_times(tc_ctx):

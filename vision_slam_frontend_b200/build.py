@@ -16,7 +16,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "libvsf_cuda.so")
 FRONTEND_LIB = os.path.join(PKG, "libvsf_frontend.so")
 
-CUDA_SOURCES = ["knn2_kernel.cu", "knn2_tc_kernel.cu", "stereo_kernels.cu", "sort_kernel.cu",
+CUDA_SOURCES = ["knn2_kernel.cu", "knn2_tc_kernel.cu", "knn2_tc64_kernel.cu", "stereo_kernels.cu", "sort_kernel.cu",
                 "aux_kernels.cu", "vsf_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp", "--use_fast_math=false"]

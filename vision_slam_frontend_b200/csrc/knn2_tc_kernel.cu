@@ -777,6 +777,12 @@ cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, 
               : launch_pdl(expand_train_kernel<false>, dim3(blocks), dim3(kExpandThreads), 0, stream, pdl != 0, tp, nt_bound, nt_dev, op, ktrace);
 }
 
+// the ordered compaction alone (shared with the 64-byte engine, knn2_tc64_kernel.cu)
+cudaError_t launch_knn2_compact(const KnnBatch& batch, int max_nq, bool pdl, cudaStream_t stream) {
+  dim3 cgrid((max_nq + kCompactQB - 1) / kCompactQB, batch.num_problems);
+  return launch_pdl(knn2_compact_kernel, cgrid, dim3(kCompactQB), 0, stream, pdl, batch);
+}
+
 // ev (optional, 4 events): recorded before the main kernel, after it, after the refine and
 // after the compaction kernel (per-kernel timing for bench.py's roofline; an event between two
 // kernels removes their programmatic overlap, so it is only used in dedicated timing passes).

@@ -28,6 +28,10 @@ cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, 
                                 int pdl, cudaStream_t stream, long long* ktrace);
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
                            cudaEvent_t* ev, cudaStream_t stream);
+cudaError_t launch_expand_train64(const void* t, int nt_bound, const int* nt_dev, void* out, int pdl,
+                                  cudaStream_t stream);
+cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_nq, int pdl, cudaEvent_t* ev,
+                             cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
                          uint64_t seed, cudaStream_t stream);
 int probe_ops_per_step(int kind);
@@ -369,7 +373,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   int train_of[kMaxProblems];
   int n_trains = 0;
   const ProblemSpec* train_spec[kTcMaxTrains];
-  bool tc_ok = (c->words == 8) && max_nt >= 1;
+  // (64-byte rows: int8 operands only, engine 3 falls back to the POPC kernel)
+  bool tc_ok = (c->words == 8 || (c->words == 16 && c->engine != 3)) && max_nt >= 1;
   if (tc_ok) {
     for (int i = 0; i < b.num_problems && tc_ok; ++i) {
       int k = 0;
@@ -388,6 +393,9 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
 
   if (engine >= 2) {
     const int int8 = engine == 2;
+    const bool wide = c->words == 16;                // 64-byte rows: knn2_tc64_kernel.cu
+    const int unit_q = wide ? 128 : kTcQ;            // queries per work unit
+    const int tile_rows = wide ? 128 : kTcTileRows;  // train rows per tile
     const int pdl = (c->engine_flags & 8) ? 0 : 1;   // flag 8: ordinary launches (A/B timing)
     if (c->profile) VSF_CUDA(c, cudaEventRecord(c->pev[0], c->stream));
     long long* kt = nullptr;
@@ -403,8 +411,12 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
         continue;
       }
       exp_image[k] = c->d_train_exp[k];
-      VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
-                                      c->d_train_exp[k], int8, pdl, c->stream, kt));
+      if (wide)
+        VSF_CUDA(c, launch_expand_train64(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
+                                          c->d_train_exp[k], pdl, c->stream));
+      else
+        VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
+                                        c->d_train_exp[k], int8, pdl, c->stream, kt));
     }
     TcBatch tb;
     std::memset(&tb, 0, sizeof(tb));
@@ -414,19 +426,23 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     for (int i = 0; i < b.num_problems; ++i) {
       tb.t_exp[i] = exp_image[train_of[i]];
       tb.qb_begin[i] = qblocks;
-      qblocks += (specs[i].nq + kTcQ - 1) / kTcQ;
+      qblocks += (specs[i].nq + unit_q - 1) / unit_q;
     }
     tb.qb_begin[b.num_problems] = qblocks;
-    tb.tiles = (max_nt + kTcTileRows - 1) / kTcTileRows;
+    tb.tiles = (max_nt + tile_rows - 1) / tile_rows;
     tb.flags = c->engine_flags;
     if (c->engine_flags & 16) {   // per-CTA timeline for tools/tc_timeline.py
       if (!c->d_tc_trace) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_tc_trace), size_t(c->sm_count) * kTcTraceSlots * sizeof(long long)));
       VSF_CUDA(c, cudaMemsetAsync(c->d_tc_trace, 0, size_t(c->sm_count) * kTcTraceSlots * sizeof(long long), c->stream));
       tb.trace = c->d_tc_trace;
     }
-    plan_tc_partition(&tb, qblocks, c->sm_count, c->force_split, size_t(row0), c->partial_cap);
+    // (64-byte rows store 4 partial key pairs per query and segment, 32-byte rows 2)
+    plan_tc_partition(&tb, qblocks, c->sm_count, c->force_split, size_t(row0) * (wide ? 2 : 1), c->partial_cap);
     b.split = tb.slots;
-    VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
+    if (wide)
+      VSF_CUDA(c, launch_knn2_tc64(b, tb, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
+    else
+      VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
     c->pev_valid = c->profile != 0;
     return VSF_OK;
   }
@@ -614,9 +630,8 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC(c, c->d_sink, 64);
   VSF_ALLOC(c, c->d_fm, size_t(window) * N * sizeof(vsf_feature_match));
   VSF_ALLOC(c, c->d_fm_count, kMaxProblems * sizeof(int));
-  if (c->words == 8)
-    for (int k = 0; k < kTcMaxTrains; ++k)
-      VSF_ALLOC(c, c->d_train_exp[k], size_t(round_up(max_features, kTcTileRows)) * kTcRowBytes);
+  for (int k = 0; k < kTcMaxTrains; ++k)   // +-1 images: one byte per descriptor bit
+    VSF_ALLOC(c, c->d_train_exp[k], size_t(round_up(max_features, kTcTileRows)) * size_t(c->row_bytes) * 8);
   {
     const float init[2] = {10000.0f, 10000.0f};  // stereo_ambig_constraint (src/slam_frontend.cc:353)
     cudaMemcpy(c->d_thresh, init, sizeof(init), cudaMemcpyHostToDevice);
@@ -650,7 +665,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC_HOST(c, c->h_fm, size_t(window) * N * sizeof(vsf_feature_match));
   if (const char* e = std::getenv("VSF_ENGINE")) {   // test / bench override of the automatic choice
     const int v = std::atoi(e);
-    if (v >= 0 && v <= 3 && (v < 2 || c->words == 8)) c->engine = v;
+    if (v >= 0 && v <= 3 && (v < 3 || c->words == 8)) c->engine = v;
   }
   c->slot_count.assign(c->ring_slots, 0);
   c->slot_frame.assign(c->ring_slots, 0);
@@ -713,7 +728,7 @@ extern "C" int vsf_set_tuning(vsf_ctx* c, int popc_mode, int train_split, int qu
 extern "C" int vsf_set_engine(vsf_ctx* c, int engine, int flags) {
   if (!c) return VSF_ERR_BAD_ARG;
   if (engine < 0 || engine > 3) return fail(c, VSF_ERR_BAD_ARG, "engine must be 0 (auto), 1 (POPC), 2 (tensor int8) or 3 (tensor e4m3)");
-  if (engine >= 2 && c->words != 8) return fail(c, VSF_ERR_BAD_ARG, "the tensor-core engine needs descriptors of at most 32 bytes");
+  if (engine == 3 && c->words != 8) return fail(c, VSF_ERR_BAD_ARG, "the e4m3 tensor-core engine needs descriptors of at most 32 bytes (64-byte rows: engine 2)");
   c->engine = engine;
   c->engine_flags = flags;
   if (flags & 32) {
@@ -1082,8 +1097,7 @@ static int flights_init(vsf_ctx* c) {
     VSF_CUDA(c, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_desc), N * c->row_bytes));
     VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_matches), list_bytes));
-    if (c->words == 8)
-      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_train_exp), size_t(round_up(c->max_features, kTcTileRows)) * kTcRowBytes));
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_train_exp), size_t(round_up(c->max_features, kTcTileRows)) * size_t(c->row_bytes) * 8));
     VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_fm), list_bytes));
     // lists are downloaded up to their bound, not their (device-side) length: start from zeros
     VSF_CUDA(c, cudaMemset(f.d_matches, 0, list_bytes));
@@ -1161,10 +1175,14 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   }
   // the tensor engine's +-1 image of the frame is made here too, right behind the copy, so the
   // main stream goes from one frame's compaction straight to the next frame's distance kernel
-  const bool pre_expand = n > 0 && nf > 0 && f.d_train_exp && c->engine != 1;
+  const bool pre_expand = n > 0 && nf > 0 && f.d_train_exp && c->engine != 1 && !(c->words == 16 && c->engine == 3);
   const int exp_int8 = c->engine == 3 ? 0 : 1;
-  if (pre_expand)
-    VSF_CUDA(c, launch_expand_train(c->slot_ptr(S), n, nullptr, f.d_train_exp, exp_int8, 0, c->up_stream, nullptr));
+  if (pre_expand) {
+    if (c->words == 16)
+      VSF_CUDA(c, launch_expand_train64(c->slot_ptr(S), n, nullptr, f.d_train_exp, 0, c->up_stream));
+    else
+      VSF_CUDA(c, launch_expand_train(c->slot_ptr(S), n, nullptr, f.d_train_exp, exp_int8, 0, c->up_stream, nullptr));
+  }
   VSF_CUDA(c, cudaEventRecord(f.ev_up, c->up_stream));
   VSF_CUDA(c, cudaStreamWaitEvent(c->stream, f.ev_up, 0));
   // ---- main stream: every resident past frame (query side) against this frame (train side);
