@@ -101,8 +101,9 @@ int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
  * otherwise), 1 = POPC pipe (XOR + POPC, csrc/knn2_kernel.cu), 2 = tensor cores,
  * int8 operands (tcgen05.mma kind::i8 over +-1 expanded descriptor bits,
  * csrc/knn2_tc_kernel.cu), 3 = tensor cores, e4m3 operands (kind::f8f6f4).
- * The tensor-core engines need desc_bytes <= 32.  Every engine produces
- * bit-identical results.  flags: pass 0; 16 / 32 record the per-CTA / per-kernel
+ * Engine 2 exists for every descriptor width (csrc/knn2_tc64_kernel.cu for 33..64
+ * bytes), engine 3 for desc_bytes <= 32 only.  Every engine produces bit-identical
+ * results.  flags: pass 0; 16 / 32 record the per-CTA / per-kernel
  * timelines read by vsf_debug_tc_trace / vsf_debug_kernel_trace (16, and the
  * timing-only flags 2 / 4, exist only in libraries built with VSF_TC_TRACE /
  * VSF_TC_BRINGUP, see vision_slam_frontend_b200/build.py). */

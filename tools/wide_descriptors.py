@@ -63,6 +63,13 @@ def main():
             torch.cuda.synchronize()
             times[name] = e0.elapsed_time(e1) / (4 * poses)
         ms = times["tensor"]
+        ctx.set_profile(True)                      # per-kernel event times of the tensor sequence
+        kt = np.zeros(4)
+        for t in range(poses):
+            step(t)
+            kt += np.array(ctx.last_kernel_times())
+        ctx.set_profile(False)
+        kt /= poses
         got = ctx.fetch_window(W)
         # parity of the last pose's newest pair against the oracle, and the CPU time of that pair
         host = seq[poses - 1 + W - 1: poses + W].cpu().numpy()[:, :, :width].copy()
@@ -78,7 +85,8 @@ def main():
             cpu_s = time.perf_counter() - t0
         rec = dict(features=n, window=W, descriptor_bytes=width, engine=ctx.last_engine, us_per_pose=ms * 1e3,
                    gpu_cmp_per_s=W * n * n / (ms * 1e-3), popc_us_per_pose=times["popc"] * 1e3,
-                   popc_cmp_per_s=W * n * n / (times["popc"] * 1e-3), survivors_newest_pair=int(len(exp)), bit_exact_vs_oracle=same,
+                   popc_cmp_per_s=W * n * n / (times["popc"] * 1e-3),
+                   tensor_kernel_us=dict(expand=kt[0] * 1e3, distance=kt[1] * 1e3, refine=kt[2] * 1e3, compact=kt[3] * 1e3), survivors_newest_pair=int(len(exp)), bit_exact_vs_oracle=same,
                    cpu_pair_s=cpu_s, cpu_cmp_per_s=(n * n / cpu_s) if cpu_s else None, cpu_threads=os.cpu_count())
         out.append(rec)
         print(json.dumps(rec), flush=True)
