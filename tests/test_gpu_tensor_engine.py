@@ -335,3 +335,29 @@ def test_tc_window_c5_size_long_pieces(tc_ctx):
         np.testing.assert_array_equal(got[j], native.get_matches(host[j][:nq[j]], host[W][:nt], RATIO))
         total += len(got[j])
     assert total > 10000
+
+
+def test_tc_wide_descriptors_observe_features_sequence():
+    """The fused ObserveImage path on 61-byte descriptors with the tensor-core engine: device-side
+    row counts (compacted frames), two train frames in one batch, stereo filter, triangulation."""
+    import vision_slam_frontend_b200 as vsf
+    P1, P2 = synth.kitti_projections()
+    F = synth.kitti_fundamental()
+    W = 3
+    frames = synth.stereo_sequence(5, 2000, seed=9, width=61)
+    fo = restate.FrontendOracle(P1, P2, F, frame_life=W, order="stable")
+    with vsf.Context(device=0, max_features=4096, desc_bytes=61, window=W) as ctx:
+        ctx.set_engine(2, 0)
+        for p, (kl, dl, kr, dr) in enumerate(frames):
+            past = list(fo.frame_list)
+            r = fo.observe_features(kl, dl, kr, dr)
+            got = ctx.observe_features(p, kl, dl, kr, dr, F, P1, P2, RATIO)
+            assert ctx.last_engine == 2
+            sm = r.stereo_matches
+            np.testing.assert_array_equal(got["kept_left"], sm["queryIdx"][r.stereo_keep])
+            np.testing.assert_array_equal(got["kept_right"], sm["trainIdx"][r.stereo_keep])
+            for (fid, m), pf in zip(got["window"], past):
+                assert fid == pf.frame_ID
+                np.testing.assert_array_equal(m, native.get_matches(pf.descriptors, r.left.descriptors, RATIO))
+            tm = native.get_matches(r.right.descriptors, r.left.descriptors, RATIO)
+            np.testing.assert_array_equal(got["tri_matches"], tm)
