@@ -361,3 +361,32 @@ def test_tc_wide_descriptors_observe_features_sequence():
                 np.testing.assert_array_equal(m, native.get_matches(pf.descriptors, r.left.descriptors, RATIO))
             tm = native.get_matches(r.right.descriptors, r.left.descriptors, RATIO)
             np.testing.assert_array_equal(got["tri_matches"], tm)
+
+
+@pytest.mark.parametrize("width", [32, 61, 64])
+def test_tc_random_shapes_against_popc_engine(width):
+    """Random (queries, train rows) shapes, forced onto the tensor cores with random piece counts:
+    indices, distances and ratio survivors equal to the POPC engine's (which the other tests pin
+    to the oracle and to OpenCV)."""
+    import vision_slam_frontend_b200 as vsf
+    rng = np.random.default_rng(100 + width)
+    with vsf.Context(device=0, max_features=3000, desc_bytes=width, window=2) as ctx:
+        for it in range(24):
+            nq = int(rng.integers(1, 3000))
+            nt = int(rng.integers(1, 3000)) if it % 5 else int(rng.integers(1, 40))
+            Q, T = synth.descriptor_pair(nq, nt, width=width, seed=int(rng.integers(1 << 30)))
+            if it % 3 == 0:                       # duplicate rows: ties between distant train rows
+                T[rng.integers(0, nt, nt // 2 + 1)] = T[rng.integers(0, nt, nt // 2 + 1)]
+            ctx.set_engine(1, 0)
+            ctx.set_tuning()
+            ri, rd = ctx.knn2(Q, T)
+            rm = ctx.get_matches(Q, T, RATIO)
+            ctx.set_engine(2, 0)
+            ctx.set_tuning(-1, int(rng.choice([0, 0, 1, 2, 3, 6, 11])), 0, -1)
+            gi, gd = ctx.knn2(Q, T)
+            gm = ctx.get_matches(Q, T, RATIO)
+            assert ctx.last_engine == 2
+            np.testing.assert_array_equal(gi, ri, err_msg=f"nq={nq} nt={nt}")
+            np.testing.assert_array_equal(gd, rd, err_msg=f"nq={nq} nt={nt}")
+            np.testing.assert_array_equal(gm, rm)
+        ctx.set_tuning()
