@@ -263,6 +263,12 @@ int vsf_get_stereo_threshold(vsf_ctx* ctx, float* value);
 int vsf_triangulate(vsf_ctx* ctx, const float* P1, const float* P2,
                     const float* x1, const float* x2, int n, float* X4);
 
+/* N1: cv::undistortPoints(pts, K, dist, R = {}, P = K) as Frontend::UndistortFeaturePoints
+ * calls it (src/slam_frontend.cc:323-351).  K: 3x3 row-major, dist: k1 k2 p1 p2 k3,
+ * xy / out: n interleaved (x, y) pairs.  Five fixed-point iterations in fp64, float output
+ * (matches OpenCV to float rounding). */
+int vsf_undistort_points(vsf_ctx* ctx, const float* K, const float* dist, const float* xy, int n, float* out);
+
 /* ----------------- whole matching path of Frontend::ObserveImage, fused */
 
 typedef struct vsf_observe_out {

@@ -397,3 +397,24 @@ def test_probe_pipe_reports_plausible_rates(vsf_ctx):
     popc = vsf_ctx.probe_pipe(0, 2048)
     lop3 = vsf_ctx.probe_pipe(1, 2048)
     assert 1e11 < popc < 1e14 and 1e11 < lop3 < 1e14
+
+
+def test_undistort_points_device_matches_opencv_golden(vsf_ctx):
+    """N1: cv::undistortPoints(pts, K, dist, R = {}, P = K) (src/slam_frontend.cc:323-351) on the
+    device: the OpenCV golden vector and the oracle restatement.  Floating point: fp64 internals,
+    float output; tolerance 1e-4 relative (north_star), measured at float rounding."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "undistort_pointgrey.npz"))
+    got = vsf_ctx.undistort_points(g["K"], g["dist"], g["px"])
+    exp = np.asarray(g["out"], np.float32).reshape(-1, 2)
+    rel = np.abs(got - exp).max() / np.abs(exp).max()
+    assert rel < 1e-4, rel
+    np.testing.assert_allclose(got, restate.undistort_points(g["px"], g["K"], g["dist"]), rtol=0, atol=2e-3)
+    # a wider field of points, strong distortion, empty input
+    rng = np.random.default_rng(2)
+    px = (rng.random((5000, 2)) * np.float32([1280, 1024])).astype(np.float32)
+    K = np.float32([[700, 0, 640], [0, 705, 512], [0, 0, 1]])
+    dist = np.float32([-0.31, 0.12, 1e-3, -2e-3, -0.02])
+    got = vsf_ctx.undistort_points(K, dist, px)
+    exp = restate.undistort_points(px, K, dist)
+    assert np.abs(got - exp).max() / np.abs(exp).max() < 1e-4
+    assert vsf_ctx.undistort_points(K, dist, np.zeros((0, 2), np.float32)).shape == (0, 2)

@@ -91,6 +91,7 @@ def load_library():
         "vsf_set_stereo_threshold": ([vp, f], i),
         "vsf_get_stereo_threshold": ([vp, C.POINTER(f)], i),
         "vsf_triangulate": ([vp, vp, vp, vp, vp, i, vp], i),
+        "vsf_undistort_points": ([vp, vp, vp, vp, i, vp], i),
         "vsf_observe_features": ([vp, u64, vp, vp, i, sz, vp, vp, i, sz, vp, vp, vp, d,
                                   C.POINTER(_ObserveOut)], i),
         "vsf_device_row_bytes": ([vp], i),
@@ -119,7 +120,7 @@ EXPORTED_SYMBOLS = [
     "vsf_window_commit", "vsf_window_clear", "vsf_window_size", "vsf_window_match",
     "vsf_window_feature_matches", "vsf_window_submit", "vsf_window_collect",
     "vsf_window_in_flight", "vsf_set_host_threads", "vsf_window_last_transfer", "vsf_stereo_filter", "vsf_set_stereo_threshold",
-    "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_observe_features",
+    "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_undistort_points", "vsf_observe_features",
     "vsf_device_row_bytes", "vsf_window_match_device", "vsf_fetch_window",
     "vsf_synth_sequence_device", "vsf_probe_pipe", "vsf_device_sm_count",
     "vsf_debug_tc_trace", "vsf_debug_kernel_trace", "vsf_debug_tc_plan", "vsf_debug_sort_prefix",
@@ -347,6 +348,16 @@ class Context:
         self._check(self._L.vsf_triangulate(self._h, _ptr(P1), _ptr(P2), _ptr(x1), _ptr(x2), n,
                                             _ptr(X4)))
         return X4
+
+    def undistort_points(self, K, dist, xy) -> np.ndarray:
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        d = np.zeros(5, np.float32)
+        dd = np.asarray(dist, np.float32).ravel()
+        d[:min(5, len(dd))] = dd[:5]
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.zeros_like(xy)
+        self._check(self._L.vsf_undistort_points(self._h, _ptr(K), _ptr(d), _ptr(xy), len(xy), _ptr(out)))
+        return out
 
     # -- fused ObserveImage matching path ------------------------------------------------
     def observe_features(self, frame_id: int, kp_left, desc_left, kp_right, desc_right, F,

@@ -127,4 +127,49 @@ cudaError_t launch_probe(int kind, uint32_t* sink, int iters, int blocks, int th
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// N1: cv::undistortPoints as Frontend::UndistortFeaturePoints calls it (src/slam_frontend.cc:323-351:
+// R empty, P = K_left): normalise with K, five fixed-point iterations of the radial / tangential
+// model in double (OpenCV's default criteria), re-project with K, store float.  One thread per
+// point; O(n) and trivially parallel, here so that the pixels of a node's features can stay on
+// the device.
+struct UndistortArgs {
+  double fx, fy, cx, cy, k1, k2, p1, p2, k3;
+};
+
+__global__ void undistort_points_kernel(const float2* __restrict__ in, int n, const UndistortArgs a,
+                                        float2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 p = in[i];
+  const double x0 = (double(p.x) - a.cx) / a.fx, y0 = (double(p.y) - a.cy) / a.fy;
+  double x = x0, y = y0;
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    const double r2 = x * x + y * y;
+    const double icdist = 1.0 / (1.0 + ((a.k3 * r2 + a.k2) * r2 + a.k1) * r2);
+    if (icdist < 0) {      // OpenCV restores the starting point for this iteration
+      x = x0;
+      y = y0;
+      continue;
+    }
+    const double dx = 2 * a.p1 * x * y + a.p2 * (r2 + 2 * x * x);
+    const double dy = a.p1 * (r2 + 2 * y * y) + 2 * a.p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  out[i] = make_float2(float(x * a.fx + a.cx), float(y * a.fy + a.cy));
+}
+
+cudaError_t launch_undistort_points(const float2* in, int n, const float* K9, const float* dist5, float2* out,
+                                    cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  UndistortArgs a;
+  a.fx = double(K9[0]); a.fy = double(K9[4]); a.cx = double(K9[2]); a.cy = double(K9[5]);
+  a.k1 = double(dist5[0]); a.k2 = double(dist5[1]); a.p1 = double(dist5[2]); a.p2 = double(dist5[3]);
+  a.k3 = double(dist5[4]);
+  undistort_points_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, n, a, out);
+  return cudaGetLastError();
+}
+
 }  // namespace vsf

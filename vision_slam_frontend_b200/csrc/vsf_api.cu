@@ -43,6 +43,8 @@ cudaError_t launch_triangulate_matches(const float* P1, const float* P2, const v
                                        const int* n_matches, int max_matches,
                                        const float2* xy_left_c, const float2* xy_right_c,
                                        float4* X4, cudaStream_t stream);
+cudaError_t launch_undistort_points(const float2* in, int n, const float* K9, const float* dist5, float2* out,
+                                    cudaStream_t stream);
 cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* counts,
                             int n_problems, float best_percent, vsf_feature_match* out,
                             int out_stride, int* out_counts, int bins, cudaStream_t stream);
@@ -1419,6 +1421,24 @@ extern "C" int vsf_triangulate(vsf_ctx* c, const float* P1, const float* P2, con
 }
 
 // ------------------------------------------------------------------- fused ObserveImage path
+
+extern "C" int vsf_undistort_points(vsf_ctx* c, const float* K, const float* dist, const float* xy, int n, float* out) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (n < 0 || !K || !dist || (n > 0 && (!xy || !out))) return fail(c, VSF_ERR_BAD_ARG, "bad undistort arguments");
+  if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more points than max_features");
+  if (n == 0) return VSF_OK;
+  cudaSetDevice(c->device);
+  std::memcpy(c->h_tri_io, xy, size_t(n) * 2 * sizeof(float));
+  VSF_CUDA(c, cudaMemcpyAsync(c->d_tri_io, c->h_tri_io, size_t(n) * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  float* d_out = c->d_tri_io + size_t(c->rows_pad) * 4;
+  VSF_CUDA(c, launch_undistort_points(reinterpret_cast<const float2*>(c->d_tri_io), n, K, dist,
+                                      reinterpret_cast<float2*>(d_out), c->stream));
+  float* h_out = c->h_tri_io + size_t(c->rows_pad) * 4;
+  VSF_CUDA(c, cudaMemcpyAsync(h_out, d_out, size_t(n) * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::memcpy(out, h_out, size_t(n) * 2 * sizeof(float));
+  return VSF_OK;
+}
 
 extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_keypoint* kpl, const uint8_t* dl,
                                     int nl, size_t sl, const vsf_keypoint* kpr, const uint8_t* dr, int nr,
