@@ -53,4 +53,13 @@ with vsf.Context(device=0, max_features=1024, desc_bytes=61, window=2) as ctx:
 x1 = np.random.default_rng(0).random((300, 2), dtype=np.float32) * 300
 with vsf.Context(device=0, max_features=1024, desc_bytes=32, window=2) as ctx:
     ctx.triangulate(P1, P2, x1, x1 + np.float32([5, 0]))
+    ctx.undistort_points(np.float32([[700, 0, 640], [0, 705, 512], [0, 0, 1]]), np.float32([-0.3, 0.1, 1e-3, -2e-3, 0]), x1)
+# 61-byte descriptors on the tensor cores (knn2_tc64_kernel.cu)
+with vsf.Context(device=0, max_features=2600, desc_bytes=61, window=2) as ctx:
+    ctx.set_engine(2, 0)
+    for (nq, nt, seed) in [(2300, 2100, 2), (129, 300, 3), (1000, 33, 4)]:
+        Q, T = synth.descriptor_pair(nq, nt, width=61, seed=seed)
+        idx, dist = ctx.knn2(Q, T)
+        ei, ed = native.knn2_hamming(Q, T)
+        assert (idx == ei).all() and (dist == ed).all()
 print("sanitizer target ok")
