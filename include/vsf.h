@@ -208,6 +208,9 @@ int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
  * in flight, or collect with none. */
 #define VSF_PIPELINE_DEPTH 8
 #define VSF_SUBMIT_PINNED_DESC 1
+/* together with VSF_SUBMIT_PINNED_DESC for descriptors narrower than the device row (61 -> 64):
+ * the rows are already padded to vsf_device_row_bytes(ctx) with zero bytes */
+#define VSF_SUBMIT_PADDED_ROWS 2
 int vsf_window_submit(vsf_ctx* ctx, uint64_t frame_id, const uint8_t* desc, int n,
                       size_t stride, double nn_match_ratio, float best_percent,
                       int sort_mode, int flags);
@@ -253,6 +256,23 @@ int vsf_stereo_filter(vsf_ctx* ctx,
 int vsf_set_stereo_threshold(vsf_ctx* ctx, float value);
 int vsf_get_stereo_threshold(vsf_ctx* ctx, float* value);
 
+/* Behaviour switches of the stereo stage (both default to 0).
+ * VSF_OPT_RESIDUAL_ORDER: float32 summation order of the two 3-term dot products inside
+ *   `(left_ph.transpose() * F * right_ph).norm()` (src/slam_frontend.cc:380-381).  The order is
+ *   Eigen's, and Eigen is not vendored by the reference: 0 = left to right, (c0 + c1) + c2
+ *   (Eigen 3.2's unrolled coefficient products), 1 = c0 + (c1 + c2) (Eigen 3.3's
+ *   redux_novec_unroller, which halves the range).  The two differ by at most one ulp of the
+ *   residual, i.e. only for pairs sitting exactly on the threshold.
+ * VSF_OPT_HOLD_THRESHOLD_ON_EMPTY: 0 = the reference's arithmetic, a frame without stereo
+ *   matches sets the threshold to 0/0 + 2 = NaN and every later frame loses all its pairs
+ *   (src/slam_frontend.cc:392-394); 1 = such a frame leaves the threshold unchanged. */
+enum {
+  VSF_OPT_RESIDUAL_ORDER = 1,
+  VSF_OPT_HOLD_THRESHOLD_ON_EMPTY = 2
+};
+int vsf_set_option(vsf_ctx* ctx, int option, int value);
+int vsf_get_option(const vsf_ctx* ctx, int option, int* value);
+
 /* ------------------------------------------- a6: cv::triangulatePoints */
 
 /* Replaces cv::triangulatePoints(P1, P2, pts1, pts2, out)
@@ -286,7 +306,11 @@ typedef struct vsf_observe_out {
   int n_tri;
   vsf_dmatch* tri_matches;     /* [cap] */
   float* tri_X4;               /* [cap][4] homogeneous points, match order */
-  int cap;                     /* capacity of the per-frame arrays */
+  int cap;                     /* capacity of the per-frame arrays: must be >= n_left AND >= the
+                                * row count of every frame resident in the window (a window list
+                                * has one entry per row of the PAST frame at most); the ctx's
+                                * max_features always suffices.  VSF_ERR_CAPACITY otherwise, with
+                                * the ctx state (window, stereo threshold) left as before the call. */
 } vsf_observe_out;
 
 /* Replaces everything Frontend::ObserveImage does between ExtractFeatures and
@@ -320,11 +344,37 @@ int vsf_window_match_device(vsf_ctx* ctx, const void* const* d_queries,
 int vsf_fetch_window(vsf_ctx* ctx, int n_frames, int* counts, vsf_dmatch* out,
                      int cap_per_frame);
 
+/* The same for a run of `count` consecutive poses of a device-resident sequence buffer that
+ * holds n_poses frames of n rows each (rows vsf_device_row_bytes(ctx) wide, back to back): for
+ * k in [0, count) the current frame is c = (first + k) mod (n_poses - window) + window and the
+ * query frames are c - window .. c - 1 (the bag loop of src/slam_frontend_main.cc:236-328 with
+ * src/slam_frontend.cc:424-434 inside, device-resident).  Asynchronous; the results of the last
+ * pose stay in the ctx's device buffers (vsf_fetch_window). */
+int vsf_window_match_block_device(vsf_ctx* ctx, const void* d_seq, int n, int n_poses,
+                                  long long first, int count, double nn_match_ratio);
+
+/* Host-buffer counterpart: streams `count` frames of a PAGE-LOCKED host buffer (n_poses frames
+ * of n rows, device row width, back to back; frame k of the run = frame (first + k) mod n_poses
+ * of the buffer, frame id first + k) through vsf_window_submit / vsf_window_collect with `lag`
+ * frames submitted ahead of the one being collected (1 .. VSF_PIPELINE_DEPTH - 1), i.e. the
+ * loop a C++ caller writes around the two calls.  The FeatureMatch lists of frame k are written
+ * to out + (k mod ring) * window * cap_per_frame (list j at + j * cap_per_frame) and their
+ * lengths to counts + (k mod ring) * window, so a ring of >= 1 frames of output is enough when
+ * the caller only wants the lists to have reached host memory.  The window must hold the frames
+ * the caller wants frame `first` matched against (vsf_window_push).  Returns after every frame
+ * has been collected; *h2d_bytes / *d2h_bytes (optional) accumulate vsf_window_last_transfer. */
+int vsf_window_run_sequence(vsf_ctx* ctx, const uint8_t* h_seq, int n, int n_poses,
+                            long long first, int count, double nn_match_ratio,
+                            float best_percent, int sort_mode, int lag,
+                            vsf_feature_match* out, int* counts, int ring, int cap_per_frame,
+                            size_t* h2d_bytes, size_t* d2h_bytes);
+
 /* Synthetic sequence generator (bench / test frame source; counter-based so
  * any pose range can be produced on any rank): pose p observes landmarks
  * [stride*p, stride*p + n) in a per-pose affine permutation, every bit flipped
  * with probability 1/32.  Writes n rows per pose for poses
- * [first_pose, first_pose + n_poses) at d_out. */
+ * [first_pose, first_pose + n_poses) at d_out, vsf_device_row_bytes(ctx) bytes per row (bytes
+ * at and beyond the ctx's desc_bytes are zero). */
 int vsf_synth_sequence_device(vsf_ctx* ctx, void* d_out, int n, int first_pose,
                               int n_poses, int stride, uint64_t seed);
 

@@ -234,32 +234,42 @@ def get_feature_matches(past: Frame, curr: Frame,
 # a5: Frontend::RemoveAmbigStereo  (src/slam_frontend.cc:353-398)
 # ---------------------------------------------------------------------------
 
-def epipolar_residual(xl: np.ndarray, xr: np.ndarray, F: np.ndarray) -> np.ndarray:
+def epipolar_residual(xl: np.ndarray, xr: np.ndarray, F: np.ndarray, order: int = 0) -> np.ndarray:
     """`(left_ph.transpose() * config_.fundamental * right_ph).norm()` (:380-381)
-    in float32, evaluated the way Eigen's fixed-size coefficient products do
-    it: v = l^T F accumulated left to right, c = v . r left to right, no FMA
-    contraction, then norm of the 1x1 result = sqrt(c*c)."""
+    in float32 without FMA contraction: v = l^T F (three 3-term dot products),
+    c = v . r (one more), then the norm of the 1x1 result = sqrt(c*c).
+
+    The summation order inside a 3-term dot product is Eigen's, and Eigen is
+    not vendored by the reference (nor installed here), so it cannot be pinned:
+      order 0: (c0 + c1) + c2  - Eigen 3.2's unrolled coefficient product
+               (product_coeff_impl<DefaultTraversal, 2>: res(0..1) + c2);
+      order 1: c0 + (c1 + c2)  - Eigen 3.3's `.sum()` via redux_novec_unroller,
+               which splits a range of 3 into 1 + 2.
+    The two differ by at most one ulp of c; the device implements both
+    (VSF_OPT_RESIDUAL_ORDER) and is bit-identical to this function for each."""
     f = np.asarray(F, dtype=np.float32).reshape(3, 3)
     xl = np.asarray(xl, dtype=np.float32).reshape(-1, 2)
     xr = np.asarray(xr, dtype=np.float32).reshape(-1, 2)
     one = np.float32(1.0)
     l = [xl[:, 0], xl[:, 1], np.full(len(xl), one, np.float32)]
     r = [xr[:, 0], xr[:, 1], np.full(len(xr), one, np.float32)]
-    v = []
-    for j in range(3):
-        acc = l[0] * f[0, j]
-        acc = acc + l[1] * f[1, j]
-        acc = acc + l[2] * f[2, j]
-        v.append(acc.astype(np.float32))
-    c = v[0] * r[0]
-    c = c + v[1] * r[1]
-    c = c + v[2] * r[2]
+
+    def dot3(a0, a1, a2):
+        if order == 0:
+            return ((a0 + a1).astype(np.float32) + a2).astype(np.float32)
+        return (a0 + (a1 + a2).astype(np.float32)).astype(np.float32)
+
     with np.errstate(over="ignore", invalid="ignore"):
+        v = [dot3((l[0] * f[0, j]).astype(np.float32), (l[1] * f[1, j]).astype(np.float32),
+                  (l[2] * f[2, j]).astype(np.float32)) for j in range(3)]
+        c = dot3((v[0] * r[0]).astype(np.float32), (v[1] * r[1]).astype(np.float32),
+                 (v[2] * r[2]).astype(np.float32))
         return np.sqrt((c * c).astype(np.float32)).astype(np.float32)
 
 
 def remove_ambig_stereo(left: Frame, right: Frame, stereo_matches: np.ndarray,
-                        F: np.ndarray, thresh: np.float32):
+                        F: np.ndarray, thresh: np.float32, residual_order: int = 0,
+                        hold_on_empty: bool = False):
     """Returns (left', right', new_thresh, residuals, keep_mask).
 
     Survivors keep match order (ascending left index); both frames are rebuilt
@@ -270,13 +280,15 @@ def remove_ambig_stereo(left: Frame, right: Frame, stereo_matches: np.ndarray,
     qi, ti = stereo_matches["queryIdx"], stereo_matches["trainIdx"]
     xl = np.stack([left.keypoints["x"][qi], left.keypoints["y"][qi]], 1)
     xr = np.stack([right.keypoints["x"][ti], right.keypoints["y"][ti]], 1)
-    c = epipolar_residual(xl, xr, F)
+    c = epipolar_residual(xl, xr, F, residual_order)
     avg = np.float32(0.0)
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         for v in c:                                   # :382 sequential float sum
             avg = np.float32(avg + v)
         keep = c <= np.float32(thresh)                # :383 (false for NaN)
         new_thresh = np.float32(np.float32(avg / np.float32(len(c))) + STEREO_PADDING)
+    if hold_on_empty and len(c) == 0:                 # opt-in deviation (VSF_OPT_HOLD_THRESHOLD_ON_EMPTY)
+        new_thresh = np.float32(thresh)
     L = Frame(left.keypoints[qi[keep]], left.descriptors[qi[keep]], left.frame_ID)
     R = Frame(right.keypoints[ti[keep]], right.descriptors[ti[keep]], right.frame_ID)
     return L, R, new_thresh, c, keep
@@ -416,7 +428,9 @@ class FrontendOracle:
     def __init__(self, P_left, P_right, fundamental,
                  nn_match_ratio: float = NN_MATCH_RATIO,
                  best_percent=BEST_PERCENT, frame_life: int = FRAME_LIFE,
-                 order: str = "stdsort"):
+                 order: str = "stdsort", residual_order: int = 0, hold_on_empty: bool = False):
+        self.residual_order = int(residual_order)
+        self.hold_on_empty = bool(hold_on_empty)
         self.P_left = np.asarray(P_left, np.float32).reshape(3, 4)
         self.P_right = np.asarray(P_right, np.float32).reshape(3, 4)
         self.F = np.asarray(fundamental, np.float32).reshape(3, 3)
@@ -435,7 +449,8 @@ class FrontendOracle:
         stereo = get_matches(curr.descriptors, right.descriptors,
                              self.nn_match_ratio)                        # :414-416
         curr, right, new_t, resid, keep = remove_ambig_stereo(
-            curr, right, stereo, self.F, self.stereo_ambig_constraint)   # :417
+            curr, right, stereo, self.F, self.stereo_ambig_constraint,
+            self.residual_order, self.hold_on_empty)                     # :417
         self.stereo_ambig_constraint = new_t
         factors = []
         for past in self.frame_list:                                     # :424-434

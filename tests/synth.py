@@ -139,10 +139,13 @@ def mix64(x):
         return x ^ (x >> np.uint64(31))
 
 
-def synth_pose(n: int, pose: int, stride: int, seed: int) -> np.ndarray:
-    """Descriptors (n, 32) uint8 of one pose of the synthetic sequence; identical,
-    bit for bit, to vsf_synth_sequence_device."""
+def synth_pose(n: int, pose: int, stride: int, seed: int, width: int = 32) -> np.ndarray:
+    """Descriptors (n, width) uint8 of one pose of the synthetic sequence; identical, bit for
+    bit, to vsf_synth_sequence_device on a context of that descriptor width (32-byte device
+    rows for width <= 32, 64-byte rows above; bytes beyond `width` are zero on the device and
+    not returned here)."""
     import math
+    words = 8 if width <= 32 else 16
     seed = np.uint64(seed)
     with np.errstate(over="ignore"):
         hp = int(mix64(seed ^ (np.uint64(0xA5A5A5A5) + np.uint64(pose) * np.uint64(0x100000001B3))))
@@ -153,14 +156,14 @@ def synth_pose(n: int, pose: int, stride: int, seed: int) -> np.ndarray:
         i = np.arange(n, dtype=np.uint64)
         perm = (np.uint64(a) * i + np.uint64(b)) % np.uint64(n)
         L = np.uint64(stride) * np.uint64(pose) + perm
-        w = np.arange(8, dtype=np.uint64)
-        code = (mix64(seed ^ (L[:, None] * np.uint64(8) + w[None, :])) & np.uint64(0xFFFFFFFF))
-        c = (np.uint64(pose) * np.uint64(n) + i)[:, None] * np.uint64(8) + w[None, :]
+        w = np.arange(words, dtype=np.uint64)
+        code = (mix64(seed ^ (L[:, None] * np.uint64(words) + w[None, :])) & np.uint64(0xFFFFFFFF))
+        c = (np.uint64(pose) * np.uint64(n) + i)[:, None] * np.uint64(words) + w[None, :]
         ns = ~seed
         r0 = mix64(ns ^ (c * np.uint64(3)))
         r1 = mix64(ns ^ (c * np.uint64(3) + np.uint64(1)))
         r2 = mix64(ns ^ (c * np.uint64(3) + np.uint64(2)))
         lo = np.uint64(0xFFFFFFFF)
         flip = (r0 & lo) & (r0 >> np.uint64(32)) & (r1 & lo) & (r1 >> np.uint64(32)) & (r2 & lo)
-        words = (code ^ flip).astype(np.uint32)
-    return words.view(np.uint8).reshape(n, 32)
+        out = (code ^ flip).astype(np.uint32)
+    return np.ascontiguousarray(out.view(np.uint8).reshape(n, 4 * words)[:, :width])

@@ -1,0 +1,341 @@
+"""Parity cases added in round 2: the shapes and switches the first round left unchecked.
+
+* a5 residual: both float32 summation orders Eigen may use, each bit-identical to the oracle;
+* the adaptive threshold through a frame without stereo matches (reference NaN / opt-in hold);
+* vsf_observe_features when frame sizes shrink between poses (capacity contract);
+* C5's real shape: 20000 features against a 32-frame window, every list checked;
+* the C++ Frontend mirror at 61-byte (AKAZE, the reference default) descriptors;
+* a sequence sharded into pose ranges with a (window + 1)-frame halo reproduces the unsharded
+  output bit for bit (two contexts: on two GPUs when the box has them, else on one).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import native, restate
+
+pytestmark = pytest.mark.gpu
+
+RATIO = restate.NN_MATCH_RATIO
+BP = restate.BEST_PERCENT
+
+
+def new_ctx(**kw):
+    import vision_slam_frontend_b200 as vsf
+    args = dict(device=0, max_features=4096, desc_bytes=32, window=10)
+    args.update(kw)
+    return vsf.Context(**args)
+
+
+# ------------------------------------------------------------------ a5: residual order switch
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_stereo_residual_order_switch(order):
+    from vision_slam_frontend_b200 import capi
+    F = synth.kitti_fundamental()
+    frames = synth.stereo_sequence(3, 2000, seed=11)
+    thresh = restate.STEREO_AMBIG_INIT
+    differs = 0
+    with new_ctx() as ctx:
+        ctx.set_option(capi.OPT_RESIDUAL_ORDER, order)
+        assert ctx.get_option(capi.OPT_RESIDUAL_ORDER) == order
+        for kl, dl, kr, dr in frames:
+            got = ctx.stereo_filter(kl, dl, kr, dr, F, RATIO)
+            sm = native.get_matches(dl, dr, RATIO)
+            L, R, thresh_next, c, keep = restate.remove_ambig_stereo(
+                restate.Frame(kl, dl, 0), restate.Frame(kr, dr, 0), sm, F, thresh, residual_order=order)
+            np.testing.assert_array_equal(got["residuals"].view(np.uint32), c.view(np.uint32))
+            np.testing.assert_array_equal(got["kept_left"], sm["queryIdx"][keep])
+            np.testing.assert_array_equal(got["kept_right"], sm["trainIdx"][keep])
+            assert ctx.get_stereo_threshold().view(np.uint32) == np.float32(thresh_next).view(np.uint32)
+            # what is actually known about the other order: at most one ulp of the accumulated
+            # sum away (relative to the residual that can be more after cancellation), and it
+            # only matters for a pair sitting exactly on the threshold
+            qi, ti = sm["queryIdx"], sm["trainIdx"]
+            xl = np.stack([kl["x"][qi], kl["y"][qi]], 1)
+            xr = np.stack([kr["x"][ti], kr["y"][ti]], 1)
+            other = restate.epipolar_residual(xl, xr, F, 1 - order)
+            differs += int((other.view(np.uint32) != c.view(np.uint32)).sum())
+            scale = np.abs(xl).max() * np.abs(F).max() * np.abs(xr).max() * 4
+            assert np.abs(other.astype(np.float64) - c.astype(np.float64)).max() <= 4 * np.spacing(np.float32(scale))
+            thresh = thresh_next
+    assert differs > 0, "the two orders never differed on this data: the switch is not exercised"
+
+
+@pytest.mark.parametrize("hold", [0, 1])
+def test_threshold_through_an_empty_frame(hold):
+    """Reference arithmetic (src/slam_frontend.cc:392-394): 0 matches -> 0/0 + 2 = NaN, and every
+    later frame loses all its stereo pairs.  VSF_OPT_HOLD_THRESHOLD_ON_EMPTY = 1 keeps the old
+    threshold instead (opt-in deviation)."""
+    from vision_slam_frontend_b200 import capi
+    F = synth.kitti_fundamental()
+    P1, P2 = synth.kitti_projections()
+    frames = synth.stereo_sequence(3, 800, seed=13)
+    rng = np.random.default_rng(0)
+    kl = synth.make_keypoints(rng.uniform(0, 300, (60, 2)))
+    empty = (kl, rng.integers(0, 256, (60, 32), dtype=np.uint8), kl, rng.integers(0, 256, (60, 32), dtype=np.uint8))
+    seq = [frames[0], empty, frames[1], frames[2]]
+    fo = restate.FrontendOracle(P1, P2, F, frame_life=3, order="stable", hold_on_empty=bool(hold))
+    with new_ctx(window=3) as ctx:
+        ctx.set_option(capi.OPT_HOLD_THRESHOLD_ON_EMPTY, hold)
+        for p, (a, b, c, d) in enumerate(seq):
+            r = fo.observe_features(a, b, c, d)
+            got = ctx.observe_features(p, a, b, c, d, F, P1, P2, RATIO)
+            np.testing.assert_array_equal(got["kept_left"], r.stereo_matches["queryIdx"][r.stereo_keep])
+            assert got["stereo_threshold_next"].view(np.uint32) == \
+                np.float32(fo.stereo_ambig_constraint).view(np.uint32)
+            if p == 1:
+                assert np.isnan(got["stereo_threshold_next"]) == (hold == 0)
+            if p == 2:     # the frame filtered with that threshold: emptied, or untouched
+                assert (len(got["kept_left"]) > 300) if hold else (len(got["kept_left"]) == 0)
+        # mean + 2 depends only on the previous frame's raw matches, so the NaN lasts one frame
+        assert len(got["kept_left"]) > 300
+
+
+# ------------------------------------------------- capacity contract of vsf_observe_features
+
+def _observe_raw(ctx, frame_id, kl, dl, kr, dr, F, P1, P2, cap):
+    """vsf_observe_features with a caller-chosen capacity (the Python wrapper always passes
+    max_features)."""
+    from vision_slam_frontend_b200 import capi
+    kl = np.ascontiguousarray(kl, capi.KEYPOINT_DTYPE)
+    kr = np.ascontiguousarray(kr, capi.KEYPOINT_DTYPE)
+    W = ctx.window
+    kept_l, kept_r = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    fids, wc = np.zeros(W, np.uint64), np.zeros(W, np.int32)
+    guard = 64
+    wm = np.zeros(W * cap + guard, capi.DMATCH_DTYPE)
+    wm["queryIdx"][W * cap:] = -777                     # canary behind the caller's buffer
+    tm = np.zeros(cap, capi.DMATCH_DTYPE)
+    X4 = np.zeros((cap, 4), np.float32)
+    o = capi._ObserveOut(kept_l.ctypes.data, kept_r.ctypes.data, 0, 0.0, 0, fids.ctypes.data, wc.ctypes.data,
+                         wm.ctypes.data, 0, tm.ctypes.data, X4.ctypes.data, cap)
+    Ff = np.ascontiguousarray(F, np.float32).reshape(9)
+    P1f = np.ascontiguousarray(P1, np.float32).reshape(12)
+    P2f = np.ascontiguousarray(P2, np.float32).reshape(12)
+    rc = ctx._L.vsf_observe_features(ctx._h, frame_id, kl.ctypes.data, dl.ctypes.data, len(kl), dl.strides[0],
+                                     kr.ctypes.data, dr.ctypes.data, len(kr), dr.strides[0], Ff.ctypes.data,
+                                     P1f.ctypes.data, P2f.ctypes.data, float(RATIO), C.byref(o))
+    assert (wm["queryIdx"][W * cap:] == -777).all(), "wrote behind the caller's window_matches buffer"
+    lists = [wm[j * cap: j * cap + wc[j]].copy() for j in range(o.n_frames)] if rc == 0 else None
+    return rc, lists, kept_l[:o.n_kept].copy()
+
+
+def test_observe_features_when_frames_shrink():
+    """A past frame with ~1700 kept rows followed by a 300-feature frame: the window list of that
+    pair can hold more entries than the current frame has features.  A capacity of n_left is
+    refused (VSF_ERR_CAPACITY, state untouched); with enough room the lists are the oracle's."""
+    P1, P2 = synth.kitti_projections()
+    F = synth.kitti_fundamental()
+    big = synth.stereo_sequence(2, 2000, seed=31)
+    # the small frame re-observes 300 of the second big frame's landmarks (same descriptors, few flips)
+    rng = np.random.default_rng(5)
+    kl2, dl2, kr2, dr2 = big[1]
+    rows = rng.permutation(len(kl2))[:300]
+    small = (kl2[rows], synth.flip_bits(dl2[rows], 4, rng), kr2[rows], synth.flip_bits(dr2[rows], 4, rng))
+    fo = restate.FrontendOracle(P1, P2, F, frame_life=3, order="stable")
+    with new_ctx(window=3) as ctx:
+        for p in range(2):
+            fo.observe_features(*big[p])
+            rc, _, _ = _observe_raw(ctx, p, *big[p], F, P1, P2, cap=2000)
+            assert rc == 0
+        thr_before = ctx.get_stereo_threshold()
+        rc, _, _ = _observe_raw(ctx, 2, *small, F, P1, P2, cap=300)
+        assert rc == 2                                   # VSF_ERR_CAPACITY
+        assert ctx.window_size() == 2                    # nothing was committed ...
+        assert ctx.get_stereo_threshold().view(np.uint32) == thr_before.view(np.uint32)   # ... or advanced
+        past = list(fo.frame_list)
+        r = fo.observe_features(*small)
+        rc, lists, kept = _observe_raw(ctx, 2, *small, F, P1, P2, cap=2000)
+        assert rc == 0 and ctx.window_size() == 3
+        np.testing.assert_array_equal(kept, r.stereo_matches["queryIdx"][r.stereo_keep])
+        for m, pf in zip(lists, past):
+            np.testing.assert_array_equal(m, native.get_matches(pf.descriptors, r.left.descriptors, RATIO))
+        assert ctx.get_stereo_threshold().view(np.uint32) == np.float32(fo.stereo_ambig_constraint).view(np.uint32)
+
+
+def test_descriptor_width_is_checked():
+    with new_ctx(desc_bytes=61) as ctx:
+        Q, T = synth.descriptor_pair(100, 100, width=64, seed=1)
+        with pytest.raises(ValueError):
+            ctx.knn2(Q, T)
+
+
+# ----------------------------------------------------------------- C5 at its real shape
+
+def test_window_c5_real_shape():
+    """BASELINE config 5's per-pose shape: 20000 features against a 32-frame window, 33 problems
+    in one launch sequence (kMaxProblems = 40), through the blocking host call with the
+    reference's sort order; every one of the 32 lists is compared with the oracle."""
+    n, W = 20000, 32
+    stride = n // W
+    frames = [synth.synth_pose(n, p, stride, 23) for p in range(W + 2)]
+    with new_ctx(max_features=n, window=W) as ctx:
+        for p in range(W):
+            ctx.window_push(p, frames[p])
+        got = ctx.window_feature_matches(frames[W], RATIO, float(BP), sort_mode=1)
+        assert ctx.last_engine == 2
+        assert len(got) == W
+        total = 0
+        for j, (fid, pairs) in enumerate(got):
+            assert fid == j
+            m = native.get_matches(frames[j], frames[W], RATIO)
+            keep = restate.num_good_matches(len(m), BP)
+            exp = m[restate.sort_order_stdsort(m)][:keep]
+            assert len(pairs) == keep
+            np.testing.assert_array_equal(pairs[:, 0], exp["queryIdx"].astype(np.uint64))
+            np.testing.assert_array_equal(pairs[:, 1], exp["trainIdx"].astype(np.uint64))
+            total += keep
+        assert total > 30000
+        # eviction at W = 32 (src/slam_frontend.cc:467-470), then the query-ordered lists of the
+        # next pose for the oldest and the newest resident frame
+        ctx.window_commit(W, n)
+        assert ctx.window_size() == W
+        got = ctx.window_match(frames[W + 1], RATIO)
+        assert [fid for fid, _ in got] == list(range(1, W + 1))
+        for j in (0, W - 1):
+            np.testing.assert_array_equal(got[j][1], native.get_matches(frames[j + 1], frames[W + 1], RATIO))
+
+
+# ------------------------------------------- the C++ Frontend at the reference's default width
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_frontend_sequence_61_byte_descriptors(exact):
+    from vision_slam_frontend_b200.frontend import Frontend
+    P1, P2 = synth.kitti_projections()
+    F = synth.kitti_fundamental()
+    W = 3
+    frames = synth.stereo_sequence(5, 1500, seed=41, width=61)
+    fo = restate.FrontendOracle(P1, P2, F, frame_life=W, order="stdsort" if exact else "stable")
+    with Frontend(max_features=2048, desc_bytes=61, frame_life=W, P_left=P1, P_right=P2, fundamental=F,
+                  exact_std_sort=exact) as fe:
+        for p, (kl, dl, kr, dr) in enumerate(frames):
+            fe.observe_odometry([0.5 * (p + 1), 0, 0], [1, 0, 0, 0], 10.0 + p)
+            assert fe.observe_features(kl, dl, kr, dr, 10.0 + p)
+            fo.observe_features(kl, dl, kr, dr)
+            assert fe.stereo_threshold.view(np.uint32) == np.float32(fo.stereo_ambig_constraint).view(np.uint32)
+        got, exp = fe.vision_factors(), fo.vision_factors
+        assert len(got) == len(exp)
+        for (a, b, pairs), e in zip(got, exp):
+            assert (a, b) == (e.pose_idx_initial, e.pose_idx_current)
+            np.testing.assert_array_equal(pairs, e.feature_matches)
+        assert sum(len(p) for _, _, p in got) > 1000
+        with pytest.raises(ValueError):
+            fe.observe_features(frames[0][0], frames[0][1][:, :32], frames[0][2], frames[0][3][:, :32])
+
+
+# ----------------------------------------------------- sharded == unsharded (halo + threshold)
+
+def _run_poses(ctx, frames, first, last, F, P1, P2, keep_from):
+    """observe_features over poses [first, last); returns {pose: result} for poses >= keep_from."""
+    out = {}
+    for p in range(first, last):
+        got = ctx.observe_features(p, *frames[p], F, P1, P2, RATIO)
+        if p >= keep_from:
+            out[p] = got
+    return out
+
+
+def test_sharded_sequence_equals_unsharded():
+    """contiguous pose ranges per rank, a read-only halo and no data-path
+    collective.  The halo is window + 1 poses: `window` poses whose compacted left frames are
+    the resident window of the shard's first pose (src/slam_frontend.cc:424-434), and one pose
+    before them whose only purpose is its `mean + 2` threshold (:392-394) - the threshold a
+    frame is filtered with depends on nothing but the raw matches of the frame before it."""
+    import torch
+    from vision_slam_frontend_b200 import sharding
+    P1, P2 = synth.kitti_projections()
+    F = synth.kitti_fundamental()
+    W, n_poses, n = 4, 40, 900
+    frames = synth.stereo_sequence(n_poses, n, seed=51, overlap=0.85)
+    with new_ctx(window=W, max_features=1024) as ctx:
+        whole = _run_poses(ctx, frames, 0, n_poses, F, P1, P2, 0)
+    world = 2
+    ndev = torch.cuda.device_count()
+    merged = {}
+    for rank in range(world):
+        first, last = sharding.pose_range(rank, world, n_poses)
+        h0 = sharding.observe_halo_start(first, W)
+        with new_ctx(window=W, max_features=1024, device=rank % ndev) as ctx:
+            merged.update(_run_poses(ctx, frames, h0, last, F, P1, P2, first))
+    assert sorted(merged) == list(range(n_poses))
+    n_lists = 0
+    for p in range(n_poses):
+        a, b = whole[p], merged[p]
+        np.testing.assert_array_equal(a["kept_left"], b["kept_left"])
+        np.testing.assert_array_equal(a["kept_right"], b["kept_right"])
+        assert a["stereo_threshold_next"].view(np.uint32) == b["stereo_threshold_next"].view(np.uint32)
+        assert [f for f, _ in a["window"]] == [f for f, _ in b["window"]]
+        for (_, ma), (_, mb) in zip(a["window"], b["window"]):
+            np.testing.assert_array_equal(ma, mb)
+            n_lists += 1
+        np.testing.assert_array_equal(a["tri_matches"], b["tri_matches"])
+        np.testing.assert_array_equal(a["tri_X4"].view(np.uint32), b["tri_X4"].view(np.uint32))
+    assert n_lists == sum(min(p, W) for p in range(n_poses))
+
+
+# ----------------------------------------- block entry points used by bench.py (frame streams)
+
+@pytest.mark.parametrize("width", [61, 64])
+def test_synth_sequence_device_wide_rows_match_numpy_twin(width):
+    import torch
+    n, poses, stride, seed = 555, 4, 50, 99
+    with new_ctx(desc_bytes=width, max_features=1024) as ctx:
+        assert ctx.row_bytes == 64
+        buf = torch.empty((poses, n, 64), dtype=torch.uint8, device="cuda")
+        ctx.synth_sequence_device(buf.data_ptr(), n, 3, poses, stride, seed)
+        ctx.synchronize()
+        host = buf.cpu().numpy()
+    for k in range(poses):
+        np.testing.assert_array_equal(host[k][:, :width], synth.synth_pose(n, 3 + k, stride, seed, width))
+        assert (host[k][:, width:] == 0).all()
+
+
+@pytest.mark.parametrize("width", [32, 61])
+def test_window_match_block_device(width):
+    import torch
+    n, W, poses, stride, seed = 1400, 4, 12, 140, 77
+    with new_ctx(desc_bytes=width, max_features=2048, window=W) as ctx:
+        rb = ctx.row_bytes
+        buf = torch.empty((poses, n, rb), dtype=torch.uint8, device="cuda")
+        ctx.synth_sequence_device(buf.data_ptr(), n, 0, poses, stride, seed)
+        # 11 launches: current frames 4..11 then (wrap) 4, 5, 6
+        ctx.window_match_block_device(buf.data_ptr(), n, poses, 0, 11, RATIO)
+        got = ctx.fetch_window(W)
+    cur = (10 % (poses - W)) + W
+    for j in range(W):
+        exp = native.get_matches(synth.synth_pose(n, cur - W + j, stride, seed, width),
+                                 synth.synth_pose(n, cur, stride, seed, width), RATIO)
+        np.testing.assert_array_equal(got[j], exp)
+    assert sum(len(m) for m in got) > 1000
+
+
+@pytest.mark.parametrize("sort_mode", [0, 1])
+def test_window_run_sequence_equals_per_frame_calls(sort_mode):
+    import torch
+    from vision_slam_frontend_b200 import capi
+    n, W, n_pool, count = 1100, 3, 9, 14
+    pool = torch.from_numpy(np.stack([synth.synth_pose(n, p, 110, 3) for p in range(n_pool)])).pin_memory()
+    hp = pool.numpy()
+    with new_ctx(max_features=2048, window=W) as ctx:
+        for p in range(W):
+            ctx.window_push(1000 + p, hp[p])
+        out = np.zeros((count, W, n), capi.FEATURE_MATCH_DTYPE)
+        counts = np.zeros((count, W), np.int32)
+        h2d, d2h = ctx.window_run_sequence(hp, W, count, RATIO, float(BP), sort_mode, 5, out, counts)
+        assert h2d == count * n * 32 and d2h > 0 and ctx.window_in_flight() == 0
+    live = [hp[p] for p in range(W)]
+    for k in range(count):
+        D = hp[(W + k) % n_pool]
+        for j, past in enumerate(live):
+            m = native.get_matches(past, D, RATIO)
+            keep = restate.num_good_matches(len(m), BP)
+            order = restate.sort_order_stdsort(m) if sort_mode == 1 else restate.sort_order_stable(m)
+            exp = m[order][:keep]
+            assert counts[k, j] == keep
+            np.testing.assert_array_equal(out[k, j, :keep]["feature_idx_initial"], exp["queryIdx"].astype(np.uint64))
+            np.testing.assert_array_equal(out[k, j, :keep]["feature_idx_current"], exp["trainIdx"].astype(np.uint64))
+        live.pop(0)
+        live.append(D)

@@ -17,6 +17,8 @@ _LIB_PATH = os.environ.get("VSF_LIB_PATH") or os.path.join(_PKG, "libvsf_cuda.so
 _LIB = None
 
 # cv::DMatch / cv::KeyPoint / slam_types::FeatureMatch layouts (include/vsf.h)
+OPT_RESIDUAL_ORDER = 1            # VSF_OPT_RESIDUAL_ORDER
+OPT_HOLD_THRESHOLD_ON_EMPTY = 2   # VSF_OPT_HOLD_THRESHOLD_ON_EMPTY
 PIPELINE_DEPTH = 8   # VSF_PIPELINE_DEPTH (include/vsf.h): frames vsf_window_submit keeps in flight
 
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"),
@@ -90,6 +92,8 @@ def load_library():
                                C.POINTER(i), vp, vp, C.POINTER(i)], i),
         "vsf_set_stereo_threshold": ([vp, f], i),
         "vsf_get_stereo_threshold": ([vp, C.POINTER(f)], i),
+        "vsf_set_option": ([vp, i, i], i),
+        "vsf_get_option": ([vp, i, C.POINTER(i)], i),
         "vsf_triangulate": ([vp, vp, vp, vp, vp, i, vp], i),
         "vsf_undistort_points": ([vp, vp, vp, vp, i, vp], i),
         "vsf_observe_features": ([vp, u64, vp, vp, i, sz, vp, vp, i, sz, vp, vp, vp, d,
@@ -97,6 +101,9 @@ def load_library():
         "vsf_device_row_bytes": ([vp], i),
         "vsf_window_match_device": ([vp, vp, vp, i, vp, i, d], i),
         "vsf_fetch_window": ([vp, i, vp, vp, i], i),
+        "vsf_window_match_block_device": ([vp, vp, i, i, C.c_longlong, i, d], i),
+        "vsf_window_run_sequence": ([vp, vp, i, i, C.c_longlong, i, d, f, i, i, vp, vp, i, i,
+                                     C.POINTER(sz), C.POINTER(sz)], i),
         "vsf_synth_sequence_device": ([vp, vp, i, i, i, i, u64], i),
         "vsf_probe_pipe": ([vp, i, i, C.POINTER(d)], i),
         "vsf_device_sm_count": ([vp], i),
@@ -120,17 +127,21 @@ EXPORTED_SYMBOLS = [
     "vsf_window_commit", "vsf_window_clear", "vsf_window_size", "vsf_window_match",
     "vsf_window_feature_matches", "vsf_window_submit", "vsf_window_collect",
     "vsf_window_in_flight", "vsf_set_host_threads", "vsf_window_last_transfer", "vsf_stereo_filter", "vsf_set_stereo_threshold",
-    "vsf_get_stereo_threshold", "vsf_triangulate", "vsf_undistort_points", "vsf_observe_features",
+    "vsf_get_stereo_threshold", "vsf_set_option", "vsf_get_option", "vsf_triangulate", "vsf_undistort_points", "vsf_observe_features",
     "vsf_device_row_bytes", "vsf_window_match_device", "vsf_fetch_window",
+    "vsf_window_match_block_device", "vsf_window_run_sequence",
     "vsf_synth_sequence_device", "vsf_probe_pipe", "vsf_device_sm_count",
     "vsf_debug_tc_trace", "vsf_debug_kernel_trace", "vsf_debug_tc_plan", "vsf_debug_sort_prefix",
 ]
 
 
-def _u8rows(a: np.ndarray) -> np.ndarray:
+def _u8rows(a: np.ndarray, width: Optional[int] = None) -> np.ndarray:
     a = np.asarray(a)
     if a.dtype != np.uint8 or a.ndim != 2:
         raise ValueError("descriptors must be a 2-D uint8 array")
+    if width is not None and a.shape[1] != width:
+        raise ValueError("descriptor rows are %d bytes wide, the context was created for %d"
+                         % (a.shape[1], width))
     if a.strides[1] != 1:
         a = np.ascontiguousarray(a)
     return a
@@ -209,7 +220,7 @@ class Context:
 
     # -- a1 / a2 -------------------------------------------------------------------
     def knn2(self, Q: np.ndarray, T: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        Q, T = _u8rows(Q), _u8rows(T)
+        Q, T = _u8rows(Q, self.desc_bytes), _u8rows(T, self.desc_bytes)
         idx = np.full((len(Q), 2), -1, np.int32)
         dist = np.full((len(Q), 2), -1, np.int32)
         self._check(self._L.vsf_knn2(self._h, _ptr(Q), len(Q), Q.strides[0], _ptr(T), len(T),
@@ -217,7 +228,7 @@ class Context:
         return idx, dist
 
     def get_matches(self, Q: np.ndarray, T: np.ndarray, ratio: float) -> np.ndarray:
-        Q, T = _u8rows(Q), _u8rows(T)
+        Q, T = _u8rows(Q, self.desc_bytes), _u8rows(T, self.desc_bytes)
         out = np.zeros(max(len(Q), 1), DMATCH_DTYPE)
         n = C.c_int(0)
         self._check(self._L.vsf_get_matches(self._h, _ptr(Q), len(Q), Q.strides[0], _ptr(T),
@@ -227,7 +238,7 @@ class Context:
 
     # -- a4 ---------------------------------------------------------------------------
     def window_push(self, frame_id: int, D: np.ndarray):
-        D = _u8rows(D)
+        D = _u8rows(D, self.desc_bytes)
         self._check(self._L.vsf_window_push(self._h, frame_id, _ptr(D), len(D), D.strides[0]))
 
     def window_commit(self, frame_id: int, n: int):
@@ -241,7 +252,7 @@ class Context:
 
     def window_match(self, D: np.ndarray, ratio: float):
         """-> list of (frame_id, DMATCH array) per resident past frame, oldest first."""
-        D = _u8rows(D)
+        D = _u8rows(D, self.desc_bytes)
         cap = self.max_features
         fids = np.zeros(self.window, np.uint64)
         counts = np.zeros(self.window, np.int32)
@@ -254,7 +265,7 @@ class Context:
     def window_feature_matches(self, D: np.ndarray, ratio: float, best_percent: float,
                                sort_mode: int = 1):
         """-> list of (frame_id, (m,2) uint64 [initial, current]) per past frame."""
-        D = _u8rows(D)
+        D = _u8rows(D, self.desc_bytes)
         cap = self.max_features
         fids = np.zeros(self.window, np.uint64)
         counts = np.zeros(self.window, np.int32)
@@ -275,7 +286,7 @@ class Context:
                       sort_mode: int = 1, pinned: bool = False):
         """pinned=True: D is page-locked, row-contiguous at the device row width and stays
         untouched until the frame is collected (VSF_SUBMIT_PINNED_DESC)."""
-        D = _u8rows(D)
+        D = _u8rows(D, self.desc_bytes)
         self._check(self._L.vsf_window_submit(self._h, frame_id, _ptr(D), len(D), D.strides[0],
                                               float(ratio), float(best_percent), sort_mode,
                                               1 if pinned else 0))
@@ -314,7 +325,7 @@ class Context:
     def stereo_filter(self, kp_left, desc_left, kp_right, desc_right, F, ratio: float):
         kl = np.ascontiguousarray(kp_left, KEYPOINT_DTYPE)
         kr = np.ascontiguousarray(kp_right, KEYPOINT_DTYPE)
-        dl, dr = _u8rows(desc_left), _u8rows(desc_right)
+        dl, dr = _u8rows(desc_left, self.desc_bytes), _u8rows(desc_right, self.desc_bytes)
         F = np.ascontiguousarray(F, np.float32).reshape(9)
         cap = max(len(kl), 1)
         kept_l = np.zeros(cap, np.int32)
@@ -331,6 +342,14 @@ class Context:
 
     def set_stereo_threshold(self, v: float):
         self._check(self._L.vsf_set_stereo_threshold(self._h, float(v)))
+
+    def set_option(self, option: int, value: int):
+        self._check(self._L.vsf_set_option(self._h, option, value))
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int(0)
+        self._check(self._L.vsf_get_option(self._h, option, C.byref(v)))
+        return v.value
 
     def get_stereo_threshold(self) -> np.float32:
         v = C.c_float(0)
@@ -364,11 +383,11 @@ class Context:
                          P_left, P_right, ratio: float) -> dict:
         kl = np.ascontiguousarray(kp_left, KEYPOINT_DTYPE)
         kr = np.ascontiguousarray(kp_right, KEYPOINT_DTYPE)
-        dl, dr = _u8rows(desc_left), _u8rows(desc_right)
+        dl, dr = _u8rows(desc_left, self.desc_bytes), _u8rows(desc_right, self.desc_bytes)
         F = np.ascontiguousarray(F, np.float32).reshape(9)
         P1 = np.ascontiguousarray(P_left, np.float32).reshape(12)
         P2 = np.ascontiguousarray(P_right, np.float32).reshape(12)
-        cap = max(len(kl), 1)
+        cap = self.max_features          # covers this frame and every resident past frame
         W = self.window
         kept_l, kept_r = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
         fids, wc = np.zeros(W, np.uint64), np.zeros(W, np.int32)
@@ -394,6 +413,24 @@ class Context:
         nn = (C.c_int * max(n, 1))(*[int(v) for v in nq])
         self._check(self._L.vsf_window_match_device(self._h, qp, nn, n, C.c_void_p(int(d_train)),
                                                     int(nt), float(ratio)))
+
+    def window_match_block_device(self, d_seq: int, n: int, n_poses: int, first: int, count: int,
+                                  ratio: float):
+        self._check(self._L.vsf_window_match_block_device(self._h, C.c_void_p(int(d_seq)), n, n_poses,
+                                                          first, count, float(ratio)))
+
+    def window_run_sequence(self, h_seq: np.ndarray, first: int, count: int, ratio: float,
+                            best_percent: float, sort_mode: int, lag: int, out: np.ndarray,
+                            counts: np.ndarray):
+        """h_seq: page-locked (n_poses, n, row_bytes) uint8; out: (ring, window, cap) FEATURE_MATCH;
+        counts: (ring, window) int32.  -> (h2d_bytes, d2h_bytes) of the run."""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        n_poses, n = h_seq.shape[0], h_seq.shape[1]
+        self._check(self._L.vsf_window_run_sequence(
+            self._h, h_seq.ctypes.data, n, n_poses, first, count, float(ratio), float(best_percent),
+            sort_mode, lag, out.ctypes.data, counts.ctypes.data, out.shape[0], out.shape[2],
+            C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def fetch_window(self, n_frames: int, with_matches: bool = True):
         counts = np.zeros(max(n_frames, 1), np.int32)

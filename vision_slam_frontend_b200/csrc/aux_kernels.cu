@@ -1,6 +1,7 @@
 // Synthetic sequence generator (bench / test frame source) and the integer-pipe
 // probe that gives the roofline its measured denominator.
 #include "vsf_device.cuh"
+#include "stereo_args.cuh"
 
 namespace vsf {
 
@@ -24,16 +25,17 @@ __host__ __device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) {
 
 // Pose p observes landmarks [stride*p, stride*p + n); feature i of pose p is
 // landmark stride*p + (a_p*i + b_p) mod n (affine permutation, a_p coprime to n).
-// Landmark L has the 256-bit code word w = low32(mix64(seed ^ (L*8 + w))).  Every
-// bit is flipped with probability 1/32 (AND of five uniform words).
-// One thread per (pose, feature, word).  Rows are 8 words (32 bytes).
+// Landmark L has the code word w = low32(mix64(seed ^ (L*words + w))), words = 8 (256-bit rows)
+// or 16 (64-byte rows; bytes at and beyond desc_bytes are zero, the device layout of 61-byte
+// AKAZE rows).  Every bit is flipped with probability 1/32 (AND of five uniform words).
+// One thread per (pose, feature, word).
 __global__ void synth_sequence_kernel(uint32_t* out, int n, int first_pose, int n_poses,
-                                      int stride, uint64_t seed) {
+                                      int stride, uint64_t seed, int words, int desc_bytes) {
   const size_t gid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = size_t(n_poses) * n * 8;
+  const size_t total = size_t(n_poses) * n * words;
   if (gid >= total) return;
-  const int w = int(gid & 7);
-  const size_t fi = gid >> 3;
+  const int w = int(gid % unsigned(words));
+  const size_t fi = gid / unsigned(words);
   const int i = int(fi % n);
   const int p = first_pose + int(fi / n);
   const uint64_t hp = mix64(seed ^ (0xA5A5A5A5ull + uint64_t(p) * 0x100000001B3ull));
@@ -42,24 +44,26 @@ __global__ void synth_sequence_kernel(uint32_t* out, int n, int first_pose, int 
   const uint32_t b = uint32_t((hp >> 32) % uint32_t(n));
   const uint64_t perm = (uint64_t(a) * uint64_t(i) + b) % uint64_t(n);
   const uint64_t L = uint64_t(stride) * uint64_t(p) + perm;
-  const uint32_t code = uint32_t(mix64(seed ^ (L * 8 + w)));
-  const uint64_t c = (uint64_t(p) * uint64_t(n) + uint64_t(i)) * 8 + w;
+  const uint32_t code = uint32_t(mix64(seed ^ (L * uint64_t(words) + w)));
+  const uint64_t c = (uint64_t(p) * uint64_t(n) + uint64_t(i)) * uint64_t(words) + w;
   const uint64_t r0 = mix64(~seed ^ (c * 3 + 0));
   const uint64_t r1 = mix64(~seed ^ (c * 3 + 1));
   const uint64_t r2 = mix64(~seed ^ (c * 3 + 2));
   const uint32_t flip = uint32_t(r0) & uint32_t(r0 >> 32) & uint32_t(r1) & uint32_t(r1 >> 32) &
                         uint32_t(r2);
-  out[gid] = code ^ flip;
+  const int valid = desc_bytes - 4 * w;            // bytes of this word inside the descriptor
+  const uint32_t mask = valid >= 4 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (8 * valid)) - 1u));
+  out[gid] = (code ^ flip) & mask;
 }
 
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
-                         uint64_t seed, cudaStream_t stream) {
-  const size_t total = size_t(n_poses) * n * 8;
+                         uint64_t seed, int words, int desc_bytes, cudaStream_t stream) {
+  const size_t total = size_t(n_poses) * n * words;
   if (total == 0) return cudaSuccess;
   const int threads = 256;
   const size_t blocks = (total + threads - 1) / threads;
   synth_sequence_kernel<<<unsigned(blocks), threads, 0, stream>>>(out, n, first_pose, n_poses,
-                                                                   stride, seed);
+                                                                   stride, seed, words, desc_bytes);
   return cudaGetLastError();
 }
 
@@ -128,47 +132,20 @@ cudaError_t launch_probe(int kind, uint32_t* sink, int iters, int blocks, int th
 }
 
 // ---------------------------------------------------------------------------------------------
-// N1: cv::undistortPoints as Frontend::UndistortFeaturePoints calls it (src/slam_frontend.cc:323-351:
-// R empty, P = K_left): normalise with K, five fixed-point iterations of the radial / tangential
-// model in double (OpenCV's default criteria), re-project with K, store float.  One thread per
-// point; O(n) and trivially parallel, here so that the pixels of a node's features can stay on
-// the device.
-struct UndistortArgs {
-  double fx, fy, cx, cy, k1, k2, p1, p2, k3;
-};
-
+// N1: cv::undistortPoints (stereo_args.cuh: undistort_one).  One thread per point; O(n) and
+// trivially parallel, here so that the pixels of a node's features can stay on the device (the
+// fused frame path applies the same function inside its triangulation launch).
 __global__ void undistort_points_kernel(const float2* __restrict__ in, int n, const UndistortArgs a,
                                         float2* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float2 p = in[i];
-  const double x0 = (double(p.x) - a.cx) / a.fx, y0 = (double(p.y) - a.cy) / a.fy;
-  double x = x0, y = y0;
-#pragma unroll 1
-  for (int it = 0; it < 5; ++it) {
-    const double r2 = x * x + y * y;
-    const double icdist = 1.0 / (1.0 + ((a.k3 * r2 + a.k2) * r2 + a.k1) * r2);
-    if (icdist < 0) {      // OpenCV restores the starting point for this iteration
-      x = x0;
-      y = y0;
-      continue;
-    }
-    const double dx = 2 * a.p1 * x * y + a.p2 * (r2 + 2 * x * x);
-    const double dy = a.p1 * (r2 + 2 * y * y) + 2 * a.p2 * x * y;
-    x = (x0 - dx) * icdist;
-    y = (y0 - dy) * icdist;
-  }
-  out[i] = make_float2(float(x * a.fx + a.cx), float(y * a.fy + a.cy));
+  out[i] = undistort_one(in[i], a);
 }
 
 cudaError_t launch_undistort_points(const float2* in, int n, const float* K9, const float* dist5, float2* out,
                                     cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  UndistortArgs a;
-  a.fx = double(K9[0]); a.fy = double(K9[4]); a.cx = double(K9[2]); a.cy = double(K9[5]);
-  a.k1 = double(dist5[0]); a.k2 = double(dist5[1]); a.p1 = double(dist5[2]); a.p2 = double(dist5[3]);
-  a.k3 = double(dist5[4]);
-  undistort_points_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, n, a, out);
+  undistort_points_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, n, make_undistort_args(K9, dist5), out);
   return cudaGetLastError();
 }
 

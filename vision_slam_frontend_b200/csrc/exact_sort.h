@@ -12,10 +12,23 @@
 // The first `keep` elements are then identical, ties included, to those of a full std::sort, at
 // about half the work for best_percent = 0.3 (tests/test_exact_sort.py checks it against the
 // real std::sort of oracle/stdsort_oracle.cc; measured 201 -> 97 us for 4500 matches).
+//
+// "Identical to the reference" therefore means: identical to std::sort of the libstdc++ this
+// library is BUILT with (GCC 13 in this image; the introsort of bits/stl_algo.h has had the same
+// pivot rule, threshold 16 and depth limit 2*lg(n) since GCC 4.x, so any libstdc++ a ROS-era
+// reference build used sorts the same way, but that is libstdc++'s promise, not the standard's).
+// The functions called below are libstdc++ internals; the guard keeps other standard libraries
+// (and libstdc++ releases that predate __ops::__iter_comp_iter, GCC < 5) on plain std::sort.
 #pragma once
 
 #include <algorithm>
 #include <cstdint>
+
+#if defined(__GLIBCXX__) && defined(_GLIBCXX_RELEASE) && _GLIBCXX_RELEASE >= 7
+#define VSF_EXACT_SORT_LIBSTDCXX 1
+#elif defined(__GLIBCXX__) && __GLIBCXX__ >= 20150422
+#define VSF_EXACT_SORT_LIBSTDCXX 1
+#endif
 
 namespace vsf_exact_sort {
 
@@ -25,7 +38,7 @@ struct KeyLess {
   bool operator()(uint32_t a, uint32_t b) const { return (a >> SHIFT) < (b >> SHIFT); }
 };
 
-#if defined(__GLIBCXX__)
+#ifdef VSF_EXACT_SORT_LIBSTDCXX
 // std::__introsort_loop, except that a right-hand part which starts at or beyond keep_end is
 // not descended into.  *sorted_end = start of the leftmost such part.
 template <typename Comp>
@@ -50,7 +63,7 @@ inline void introsort_prefix_loop(uint32_t* first, uint32_t* last, long depth_li
 template <int SHIFT>
 inline void sort_prefix(uint32_t* keys, long n, long keep) {
   if (n <= 0 || keep <= 0) return;
-#if defined(__GLIBCXX__)
+#ifdef VSF_EXACT_SORT_LIBSTDCXX
   auto comp = __gnu_cxx::__ops::__iter_comp_iter(KeyLess<SHIFT>());
   uint32_t* sorted_end = keys + n;
   introsort_prefix_loop(keys, keys + n, std::__lg(n) * 2, keys + std::min(keep, n), &sorted_end, comp);

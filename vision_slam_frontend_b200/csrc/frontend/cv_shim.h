@@ -53,7 +53,13 @@ struct DMatch {
 };
 static_assert(sizeof(DMatch) == 16, "cv::DMatch layout");
 
-enum { CV_8U = 0, CV_32F = 5 };
+}  // namespace cv
+// type codes are preprocessor macros in OpenCV (interface.h), not members of namespace cv
+#ifndef CV_8U
+#define CV_8U 0
+#define CV_32F 5
+#endif
+namespace cv {
 enum NormTypes { NORM_L2 = 4, NORM_HAMMING = 6 };
 
 // Row-major byte matrix with shared ownership — the subset of cv::Mat the path uses
@@ -64,7 +70,7 @@ class Mat {
   size_t step = 0;
   uint8_t* data = nullptr;
   Mat() {}
-  Mat(int r, int c, int /*type*/ = CV_8U) { create(r, c); }
+  Mat(int r, int c, int /*type*/) { create(r, c); }   // like cv::Mat: the type is not optional
   Mat(int r, int c, int /*type*/, void* external, size_t step_ = 0)
       : rows(r), cols(c), step(step_ ? step_ : size_t(c)), data(static_cast<uint8_t*>(external)) {}
   void create(int r, int c) {

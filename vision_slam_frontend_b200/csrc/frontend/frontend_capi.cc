@@ -74,8 +74,8 @@ int vsff_observe_features(void* p, const vsf_keypoint* kl, const uint8_t* dl, in
     std::vector<cv::KeyPoint> lk(nl), rk(nr);
     if (nl) std::memcpy(static_cast<void*>(lk.data()), kl, size_t(nl) * sizeof(vsf_keypoint));
     if (nr) std::memcpy(static_cast<void*>(rk.data()), kr, size_t(nr) * sizeof(vsf_keypoint));
-    cv::Mat ld(nl, desc_bytes, cv::CV_8U, const_cast<uint8_t*>(dl));
-    cv::Mat rd(nr, desc_bytes, cv::CV_8U, const_cast<uint8_t*>(dr));
+    cv::Mat ld(nl, desc_bytes, CV_8U, const_cast<uint8_t*>(dl));
+    cv::Mat rd(nr, desc_bytes, CV_8U, const_cast<uint8_t*>(dr));
     return h->fe->ObserveFeatures(lk, ld, rk, rd, time) ? 1 : 0;
   } catch (const std::exception& e) {
     h->err = e.what();
@@ -87,8 +87,8 @@ int vsff_get_matches(void* p, const uint8_t* q, int nq, const uint8_t* t, int nt
                      vsf_dmatch* out, int cap) {
   Handle* h = static_cast<Handle*>(p);
   try {
-    slam::Frame fq(std::vector<cv::KeyPoint>(nq), cv::Mat(nq, desc_bytes, cv::CV_8U, const_cast<uint8_t*>(q)), 0);
-    slam::Frame ft(std::vector<cv::KeyPoint>(nt), cv::Mat(nt, desc_bytes, cv::CV_8U, const_cast<uint8_t*>(t)), 1);
+    slam::Frame fq(std::vector<cv::KeyPoint>(nq), cv::Mat(nq, desc_bytes, CV_8U, const_cast<uint8_t*>(q)), 0);
+    slam::Frame ft(std::vector<cv::KeyPoint>(nt), cv::Mat(nt, desc_bytes, CV_8U, const_cast<uint8_t*>(t)), 1);
     std::vector<cv::DMatch> m = h->fe->GetMatches(fq, ft, ratio);
     if (int(m.size()) > cap) return -2;
     if (!m.empty()) std::memcpy(out, m.data(), m.size() * sizeof(vsf_dmatch));

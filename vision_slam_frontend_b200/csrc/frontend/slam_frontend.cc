@@ -197,8 +197,15 @@ Frame::Frame(const std::vector<cv::KeyPoint>& keypoints, const cv::Mat& descript
 
 // ---------------------------------------------------------------------------------- Frontend
 
+// Both constructors start the odometry members from zero / identity explicitly (the reference
+// leaves them indeterminate, src/slam_frontend.cc:188-190; with the real Eigen types a default
+// constructed Vector3f / Quaternionf holds garbage).
 Frontend::Frontend(const std::string& config_path)
-    : odom_initialized_(false), odom_timestamp_(0), ctx_(nullptr), curr_frame_ID_(0) {
+    : odom_initialized_(false),
+      init_odom_translation_(0.f, 0.f, 0.f), init_odom_rotation_(1.f, 0.f, 0.f, 0.f),
+      prev_odom_translation_(0.f, 0.f, 0.f), prev_odom_rotation_(1.f, 0.f, 0.f, 0.f),
+      odom_translation_(0.f, 0.f, 0.f), odom_rotation_(1.f, 0.f, 0.f, 0.f),
+      odom_timestamp_(0), ctx_(nullptr), curr_frame_ID_(0) {
   // The reference ignores its argument (src/slam_frontend.cc:188-190); a non-empty
   // path is honoured here through FrontendConfig::Load.
   if (!config_path.empty()) config_.Load(config_path);
@@ -207,7 +214,11 @@ Frontend::Frontend(const std::string& config_path)
 }
 
 Frontend::Frontend(const FrontendConfig& config)
-    : odom_initialized_(false), odom_timestamp_(0), config_(config), ctx_(nullptr), curr_frame_ID_(0) {
+    : odom_initialized_(false),
+      init_odom_translation_(0.f, 0.f, 0.f), init_odom_rotation_(1.f, 0.f, 0.f, 0.f),
+      prev_odom_translation_(0.f, 0.f, 0.f), prev_odom_rotation_(1.f, 0.f, 0.f, 0.f),
+      odom_translation_(0.f, 0.f, 0.f), odom_rotation_(1.f, 0.f, 0.f, 0.f),
+      odom_timestamp_(0), config_(config), ctx_(nullptr), curr_frame_ID_(0) {
   Check(vsf_create(config_.cuda_device, config_.max_features, config_.descriptor_bytes,
                    int(config_.frame_life_), &ctx_), "vsf_create");
 }
@@ -242,8 +253,8 @@ void Frontend::ObserveOdometry(const Eigen::Vector3f& translation, const Eigen::
     init_odom_rotation_ = rotation;
     init_odom_translation_ = translation;
     // (the reference copies the still-uninitialised odom_* members here; the first
-    // OdomCheck therefore compares against indeterminate values.  Zero / identity
-    // initial values are used instead.)
+    // OdomCheck therefore compares against indeterminate values.  The constructors
+    // initialise them to zero / identity, so that is what is copied.)
     prev_odom_rotation_ = odom_rotation_;
     prev_odom_translation_ = odom_translation_;
     odom_initialized_ = true;
@@ -263,6 +274,9 @@ std::vector<cv::DMatch> Frontend::GetMatches(const Frame& frame_query, const Fra
                                              double nn_match_ratio) {
   // src/slam_frontend.cc:521-538: knnMatch(k=2) + ratio test, on the device
   const int nq = frame_query.descriptors_.rows, nt = frame_train.descriptors_.rows;
+  if ((nq > 0 && frame_query.descriptors_.cols != config_.descriptor_bytes) ||
+      (nt > 0 && frame_train.descriptors_.cols != config_.descriptor_bytes))
+    throw std::runtime_error("Frontend::GetMatches: descriptor width differs from FrontendConfig::descriptor_bytes");
   std::vector<vsf_dmatch> out(size_t(std::max(nq, 1)));
   int n = 0;
   Check(vsf_get_matches(ctx_, frame_query.descriptors_.data, nq, frame_query.descriptors_.step,
@@ -368,9 +382,18 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
   const int nl = int(left_keypoints.size()), nr = int(right_keypoints.size());
   if (left_descriptors.rows != nl || right_descriptors.rows != nr)
     throw std::runtime_error("Frontend::ObserveFeatures: keypoint / descriptor row mismatch");
+  if ((nl > 0 && left_descriptors.cols != config_.descriptor_bytes) ||
+      (nr > 0 && right_descriptors.cols != config_.descriptor_bytes))
+    throw std::runtime_error("Frontend::ObserveFeatures: descriptor width differs from FrontendConfig::descriptor_bytes");
+  // host-side consistency checks come BEFORE the device call, which commits the frame
+  if (vsf_window_size(ctx_) != int(frame_list_.size()))
+    throw std::runtime_error("Frontend::ObserveFeatures: device window out of sync with frame_list_");
   static_assert(sizeof(cv::KeyPoint) == sizeof(vsf_keypoint), "KeyPoint layout");
   const int W = int(config_.frame_life_);
-  const int cap = std::max(nl, 1);
+  // a window list has one entry per row of the PAST frame at most: size for the largest
+  // resident frame as well as for this one
+  int cap = std::max(nl, 1);
+  for (const Frame& f : frame_list_) cap = std::max(cap, int(f.keypoints_.size()));
   kept_left_.resize(cap);
   kept_right_.resize(cap);
   frame_ids_.resize(W);
@@ -400,9 +423,9 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
 
   // Host copies of the compacted frames (src/slam_frontend.cc:386-389, :396-397).
   const int M = out.n_kept;
-  const int wbytes = left_descriptors.cols;
+  const int wbytes = config_.descriptor_bytes;
   std::vector<cv::KeyPoint> lk(M), rk(M);
-  cv::Mat ld(M, wbytes), rd(M, wbytes);
+  cv::Mat ld(M, wbytes, CV_8U), rd(M, wbytes, CV_8U);
   for (int i = 0; i < M; ++i) {
     lk[i] = left_keypoints[kept_left_[i]];
     rk[i] = right_keypoints[kept_right_[i]];

@@ -33,6 +33,7 @@
 //   knn2_tc_refine_kernel exact top-2 inside the candidate buckets, ratio test.
 //   knn2_compact_kernel   ratio survivors in ascending queryIdx order.
 // launch_knn2_tc chains the four on one stream with programmatic dependent launch.
+#include <atomic>
 #include <utility>
 
 #include "knn2_tail.cuh"
@@ -758,15 +759,18 @@ cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, 
     // ... and the same shared-memory carve-out as that kernel (the largest one): a kernel that
     // prefers another L1 / shared split cannot share an SM with it, the SM is reconfigured only
     // once it has drained
-    static int carveout_set_for = -1;
+    // (function attributes are per device; one bit per device ordinal, set once, safe when
+    // several contexts on several devices launch concurrently)
+    static std::atomic<unsigned long long> carveout_done{0ull};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (carveout_set_for != dev) {
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(carveout_done.load(std::memory_order_acquire) & bit)) {
       cudaError_t e = cudaFuncSetAttribute(expand_train_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(expand_train_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) return e;
-      carveout_set_for = dev;
+      carveout_done.fetch_or(bit, std::memory_order_release);
     }
   }
   const int threads = rows_pad * 4;

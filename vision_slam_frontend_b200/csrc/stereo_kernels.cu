@@ -8,87 +8,132 @@
 #include "vsf_device.cuh"
 #include "stereo_args.cuh"
 
+#include <algorithm>
+#include <cstring>
+
 namespace vsf {
 
 constexpr int kStereoThreads = 256;
 
-// `(left_ph^T * F * right_ph).norm()` (src/slam_frontend.cc:380-381) in float32, in
-// the order Eigen's fixed-size products evaluate it; the *_rn intrinsics forbid
-// FMA contraction so the result is bit-identical to the oracle's float32
-// restatement (oracle/restate.py: epipolar_residual).
-__device__ __forceinline__ float epipolar_residual(float2 l, float2 r, const float* F) {
+// `(left_ph^T * F * right_ph).norm()` (src/slam_frontend.cc:380-381) in float32; the *_rn
+// intrinsics forbid FMA contraction so the result is bit-identical to the oracle's float32
+// restatement (oracle/restate.py: epipolar_residual).  Both products are 3-term dot products
+// whose summation order is Eigen's, and Eigen is not part of the reference checkout:
+// tree = false: (c0 + c1) + c2, Eigen 3.2's unrolled coefficient product;
+// tree = true:  c0 + (c1 + c2), Eigen 3.3's redux_novec_unroller (splits the range in halves).
+__device__ __forceinline__ float dot3_ordered(float a0, float a1, float a2, bool tree) {
+  return tree ? __fadd_rn(a0, __fadd_rn(a1, a2)) : __fadd_rn(__fadd_rn(a0, a1), a2);
+}
+
+__device__ __forceinline__ float epipolar_residual(float2 l, float2 r, const float* F, bool tree) {
   float v[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    float acc = __fmul_rn(l.x, F[j]);
-    acc = __fadd_rn(acc, __fmul_rn(l.y, F[3 + j]));
-    acc = __fadd_rn(acc, __fmul_rn(1.0f, F[6 + j]));
-    v[j] = acc;
-  }
-  float c = __fmul_rn(v[0], r.x);
-  c = __fadd_rn(c, __fmul_rn(v[1], r.y));
-  c = __fadd_rn(c, __fmul_rn(v[2], 1.0f));
+  for (int j = 0; j < 3; ++j)
+    v[j] = dot3_ordered(__fmul_rn(l.x, F[j]), __fmul_rn(l.y, F[3 + j]), __fmul_rn(1.0f, F[6 + j]), tree);
+  const float c = dot3_ordered(__fmul_rn(v[0], r.x), __fmul_rn(v[1], r.y), __fmul_rn(v[2], 1.0f), tree);
   return __fsqrt_rn(__fmul_rn(c, c));
 }
 
+// One CTA per 256-match chunk: residuals + survivors of the chunk.  The last CTA to finish (a
+// self-resetting ticket) turns the per-chunk counts into exclusive offsets and the total M, so
+// the compaction kernel starts from finished offsets.
 __global__ void __launch_bounds__(kStereoThreads)
 stereo_residual_kernel(const __grid_constant__ StereoArgs a) {
+  __shared__ unsigned s_last;
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = *a.n_matches;
   const int m = blockIdx.x * kStereoThreads + threadIdx.x;
   bool keep = false;
   if (m < n) {
     const vsf_dmatch dm = a.matches[m];
-    const float c = epipolar_residual(a.xy_left[dm.queryIdx], a.xy_right[dm.trainIdx], a.F);
+    const float c = epipolar_residual(a.xy_left[dm.queryIdx], a.xy_right[dm.trainIdx], a.F, a.residual_order != 0);
     a.resid[m] = c;
     keep = (c <= *a.thresh_cur);   // false for NaN, as in the reference
   }
   const int cnt = __syncthreads_count(keep);
-  if (threadIdx.x == 0) a.chunk_keep[blockIdx.x] = unsigned(cnt);
+  if (threadIdx.x == 0) {
+    a.chunk_keep[blockIdx.x] = unsigned(cnt);
+    __threadfence();
+    const unsigned t = atomicAdd(a.ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 32) {   // exclusive scan of the chunk counts by one warp
+    const int lane = threadIdx.x;
+    unsigned run = 0;
+    for (int c0 = 0; c0 < int(gridDim.x); c0 += 32) {
+      const int c = c0 + lane;
+      const unsigned v = (c < int(gridDim.x)) ? __ldcg(a.chunk_keep + c) : 0u;
+      unsigned incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (c < int(gridDim.x)) a.chunk_off[c] = run + incl - v;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      *a.n_kept = int(run);
+      *a.ticket = 0u;
+    }
+  }
 }
 
-// grid = chunks + 1.  CTAs [0, chunks) compact their 256-match chunk (the offset
-// is the sum of the earlier chunks' survivor counts) and gather keypoint pixels
-// and descriptor rows of both frames; the extra CTA accumulates the residual mean
-// sequentially in float32 in match order — the order the reference adds them in
-// (src/slam_frontend.cc:382) — so the next threshold is bit-identical.
-__global__ void __launch_bounds__(kStereoThreads)
-stereo_compact_kernel(const __grid_constant__ StereoArgs a) {
-  __shared__ unsigned s_warp[kStereoThreads / 32];
-  __shared__ unsigned s_base;
+// Mean of the residuals, accumulated sequentially in float32 in match order - the order the
+// reference adds them in (src/slam_frontend.cc:382) - so the next threshold is bit-identical.
+// The whole CTA stages the residuals through shared memory (coalesced loads); one thread then
+// walks them: the dependent FADD chain (4 cycles per add) is all that is left.
+constexpr int kThreshStage = 4096;
+__device__ void stereo_threshold_cta(const StereoArgs& a, float* s_buf) {
   const int n = *a.n_matches;
-  const int chunks = gridDim.x - 1;
-  const int tid = threadIdx.x;
-
-  if (int(blockIdx.x) == chunks) {
-    if (tid == 0) {
-      float avg = 0.0f;
-      int m = 0;
-      for (; m + 4 <= n; m += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(a.resid + m);
+  float avg = 0.0f;
+  for (int base = 0; base < n; base += kThreshStage) {
+    const int len = min(kThreshStage, n - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) s_buf[i] = a.resid[base + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int i = 0;
+      for (; i + 4 <= len; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(s_buf + i);
         avg = __fadd_rn(avg, v.x);
         avg = __fadd_rn(avg, v.y);
         avg = __fadd_rn(avg, v.z);
         avg = __fadd_rn(avg, v.w);
       }
-      for (; m < n; ++m) avg = __fadd_rn(avg, a.resid[m]);
-      // avg_constraint / stereo_matches.size() + padding (src/slam_frontend.cc:392-394);
-      // 0/0 = NaN when there were no matches, like the reference.
-      *a.thresh_next = __fadd_rn(__fdiv_rn(avg, float(n)), 2.0f);
-      unsigned total = 0;
-      for (int c = 0; c < chunks; ++c) total += a.chunk_keep[c];
-      *a.n_kept = int(total);
+      for (; i < len; ++i) avg = __fadd_rn(avg, s_buf[i]);
     }
-    return;
   }
+  if (threadIdx.x == 0) {
+    // avg_constraint / stereo_matches.size() + padding (src/slam_frontend.cc:392-394);
+    // 0/0 = NaN when there were no matches, like the reference - unless the caller asked to
+    // keep the threshold through empty frames (VSF_OPT_HOLD_THRESHOLD_ON_EMPTY)
+    float next = __fadd_rn(__fdiv_rn(avg, float(n)), 2.0f);
+    if (n == 0 && a.hold_on_empty) next = *a.thresh_cur;
+    *a.thresh_next = next;
+  }
+}
 
-  // offset of this chunk
-  if (tid < 32) {
-    unsigned s = 0;
-    for (int c = tid; c < int(blockIdx.x); c += 32) s += a.chunk_keep[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (tid == 0) s_base = s;
-  }
+__global__ void __launch_bounds__(kStereoThreads) stereo_threshold_kernel(const __grid_constant__ StereoArgs a) {
+  __shared__ __align__(16) float s_buf[kThreshStage];
+  pdl_wait();
+  pdl_launch_dependents();
+  stereo_threshold_cta(a, s_buf);
+}
+
+// One CTA per 256-match chunk: compacts the chunk behind the survivors of the earlier chunks
+// and gathers keypoint pixels and descriptor rows of both frames.
+__global__ void __launch_bounds__(kStereoThreads)
+stereo_compact_kernel(const __grid_constant__ StereoArgs a) {
+  __shared__ unsigned s_warp[kStereoThreads / 32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int n = *a.n_matches;
+  const int tid = threadIdx.x;
   const int m = blockIdx.x * kStereoThreads + tid;
   bool keep = false;
   vsf_dmatch dm = {0, 0, 0, 0.f};
@@ -100,7 +145,7 @@ stereo_compact_kernel(const __grid_constant__ StereoArgs a) {
   const int lane = tid & 31, warp = tid >> 5;
   if (lane == 0) s_warp[warp] = __popc(bal);
   __syncthreads();
-  unsigned off = s_base;
+  unsigned off = a.chunk_off[blockIdx.x];
   for (int w = 0; w < warp; ++w) off += s_warp[w];
   if (keep) {
     const unsigned dst = off + __popc(bal & ((1u << lane) - 1u));
@@ -120,12 +165,29 @@ stereo_compact_kernel(const __grid_constant__ StereoArgs a) {
   }
 }
 
-cudaError_t launch_stereo_filter(const StereoArgs& a, int max_matches, cudaStream_t stream) {
+template <typename K>
+static cudaError_t launch_stereo_pdl(K kernel, int blocks, cudaStream_t stream, const StereoArgs& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(kStereoThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+// with_threshold = false: the caller runs the threshold sum elsewhere (the fused frame path puts
+// it into an extra CTA of the triangulation kernel, where nothing waits for it)
+cudaError_t launch_stereo_filter(const StereoArgs& a, int max_matches, bool with_threshold, cudaStream_t stream) {
   const int chunks = (max_matches + kStereoThreads - 1) / kStereoThreads;
   if (chunks <= 0) return cudaSuccess;
-  stereo_residual_kernel<<<chunks, kStereoThreads, 0, stream>>>(a);
-  stereo_compact_kernel<<<chunks + 1, kStereoThreads, 0, stream>>>(a);
-  return cudaGetLastError();
+  cudaError_t e = launch_stereo_pdl(stereo_residual_kernel, chunks, stream, a);
+  if (e == cudaSuccess) e = launch_stereo_pdl(stereo_compact_kernel, chunks, stream, a);
+  if (e == cudaSuccess && with_threshold) e = launch_stereo_pdl(stereo_threshold_kernel, 1, stream, a);
+  return e;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -221,12 +283,24 @@ __global__ void triangulate_pairs_kernel(const __grid_constant__ Proj pj, const 
 
 // R'->L' matches (query = compacted right frame, train = compacted left frame):
 // left_pt = left.keypoints_[trainIdx].pt, right_pt = right.keypoints_[queryIdx].pt
-// (src/slam_frontend.cc:137-139).  Output in match order, one float4 per match.
-__global__ void triangulate_matches_kernel(const __grid_constant__ Proj pj,
-                                           const vsf_dmatch* matches, const int* n_matches,
-                                           const float2* xy_left_c, const float2* xy_right_c,
-                                           float4* X4) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// (src/slam_frontend.cc:137-139).  Output in match order, one float4 per match.  One warp per
+// CTA: a point is a long dependent FP64 chain in one thread, so the launch is spread over as
+// many SMs as there are warps.  The last CTA (when ex.do_threshold) is the stereo stage's
+// sequential threshold sum; thread i also undistorts compacted left keypoint i (ex.do_undistort).
+constexpr int kTriThreads = 32;
+__global__ void __launch_bounds__(kTriThreads)
+triangulate_matches_kernel(const __grid_constant__ Proj pj, const vsf_dmatch* matches, const int* n_matches,
+                           const float2* xy_left_c, const float2* xy_right_c, float4* X4,
+                           const __grid_constant__ TriExtras ex) {
+  __shared__ __align__(16) float s_buf[kThreshStage];
+  pdl_wait();
+  pdl_launch_dependents();
+  if (ex.do_threshold && blockIdx.x == gridDim.x - 1) {
+    stereo_threshold_cta(ex.stereo, s_buf);
+    return;
+  }
+  const int i = blockIdx.x * kTriThreads + threadIdx.x;
+  if (ex.do_undistort && i < *ex.n_kept) ex.xy_undist[i] = undistort_one(xy_left_c[i], ex.und);
   if (i >= *n_matches) return;
   const vsf_dmatch dm = matches[i];
   X4[i] = triangulate_one(pj, xy_left_c[dm.trainIdx], xy_right_c[dm.queryIdx]);
@@ -247,16 +321,27 @@ cudaError_t launch_triangulate_pairs(const float* P1, const float* P2, const flo
 cudaError_t launch_triangulate_matches(const float* P1, const float* P2, const vsf_dmatch* matches,
                                        const int* n_matches, int max_matches,
                                        const float2* xy_left_c, const float2* xy_right_c,
-                                       float4* X4, cudaStream_t stream) {
-  if (max_matches <= 0) return cudaSuccess;
+                                       float4* X4, const TriExtras* extras, cudaStream_t stream) {
+  TriExtras ex;
+  std::memset(&ex, 0, sizeof(ex));
+  if (extras) ex = *extras;
+  int blocks = (std::max(max_matches, 0) + kTriThreads - 1) / kTriThreads + (ex.do_threshold ? 1 : 0);
+  if (blocks <= 0) return cudaSuccess;
   Proj pj;
   for (int i = 0; i < 12; ++i) {
     pj.P1[i] = P1[i];
     pj.P2[i] = P2[i];
   }
-  triangulate_matches_kernel<<<(max_matches + 127) / 128, 128, 0, stream>>>(
-      pj, matches, n_matches, xy_left_c, xy_right_c, X4);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(kTriThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, triangulate_matches_kernel, pj, matches, n_matches, xy_left_c, xy_right_c, X4, ex);
 }
 
 }  // namespace vsf

@@ -33,7 +33,7 @@ cudaError_t launch_expand_train64(const void* t, int nt_bound, const int* nt_dev
 cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_nq, int pdl, cudaEvent_t* ev,
                              cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
-                         uint64_t seed, cudaStream_t stream);
+                         uint64_t seed, int words, int desc_bytes, cudaStream_t stream);
 int probe_ops_per_step(int kind);
 cudaError_t launch_probe(int kind, uint32_t* sink, int iters, int blocks, int threads,
                          cudaStream_t stream);
@@ -42,7 +42,7 @@ cudaError_t launch_triangulate_pairs(const float* P1, const float* P2, const flo
 cudaError_t launch_triangulate_matches(const float* P1, const float* P2, const vsf_dmatch* matches,
                                        const int* n_matches, int max_matches,
                                        const float2* xy_left_c, const float2* xy_right_c,
-                                       float4* X4, cudaStream_t stream);
+                                       float4* X4, const TriExtras* extras, cudaStream_t stream);
 cudaError_t launch_undistort_points(const float2* in, int n, const float* K9, const float* dist5, float2* out,
                                     cudaStream_t stream);
 cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* counts,
@@ -106,7 +106,8 @@ struct vsf_ctx {
   vsf_dmatch* d_matches = nullptr;
   int* d_match_count = nullptr;
   float* d_resid = nullptr;
-  unsigned* d_chunk_keep = nullptr;
+  unsigned *d_chunk_keep = nullptr, *d_chunk_off = nullptr, *d_ticket = nullptr;
+  int opt_residual_order = 0, opt_hold_on_empty = 0;   // vsf_set_option
   int *d_kept_left = nullptr, *d_kept_right = nullptr, *d_n_kept = nullptr;
   float* d_thresh = nullptr;  // [2], ping-pong
   int thresh_cur = 0;
@@ -509,7 +510,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
   void* dev[] = {c->d_ring, c->d_raw_left, c->d_raw_right, c->d_right_c, c->d_xy_left, c->d_xy_right,
                  c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
-                 c->d_chunk_keep, c->d_kept_left, c->d_kept_right, c->d_n_kept, c->d_thresh, c->d_X4,
+                 c->d_chunk_keep, c->d_chunk_off, c->d_ticket, c->d_kept_left, c->d_kept_right, c->d_n_kept, c->d_thresh, c->d_X4,
                  c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1], c->d_tc_trace,
                  c->d_ktrace};
   for (void* p : dev)
@@ -623,6 +624,9 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   cudaMemset(c->d_match_count, 0, kMaxProblems * sizeof(int));
   VSF_ALLOC(c, c->d_resid, N * sizeof(float));
   VSF_ALLOC(c, c->d_chunk_keep, (N / 256 + 2) * sizeof(unsigned));
+  VSF_ALLOC(c, c->d_chunk_off, (N / 256 + 2) * sizeof(unsigned));
+  VSF_ALLOC(c, c->d_ticket, sizeof(unsigned));
+  cudaMemset(c->d_ticket, 0, sizeof(unsigned));
   VSF_ALLOC(c, c->d_kept_left, N * sizeof(int));
   VSF_ALLOC(c, c->d_kept_right, N * sizeof(int));
   VSF_ALLOC(c, c->d_n_kept, sizeof(int));
@@ -1162,7 +1166,8 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   if (c->slot_last_chain[S]) VSF_CUDA(c, cudaStreamWaitEvent(c->up_stream, c->slot_last_chain[S], 0));
   if (n > 0) {
     const uint8_t* src = f.h_desc;
-    if ((flags & VSF_SUBMIT_PINNED_DESC) && stride == size_t(c->row_bytes) && c->desc_bytes == c->row_bytes) {
+    if ((flags & VSF_SUBMIT_PINNED_DESC) && stride == size_t(c->row_bytes) &&
+        (c->desc_bytes == c->row_bytes || (flags & VSF_SUBMIT_PADDED_ROWS))) {
       src = desc;   // page-locked and already in the device layout: no staging copy
     } else if (stride == size_t(c->row_bytes) && c->desc_bytes == c->row_bytes) {
       std::memcpy(f.h_desc, desc, size_t(n) * c->row_bytes);
@@ -1313,6 +1318,10 @@ static void fill_stereo_args(vsf_ctx* c, StereoArgs& a, const float* F) {
   a.thresh_next = c->d_thresh + (c->thresh_cur ^ 1);
   a.resid = c->d_resid;
   a.chunk_keep = c->d_chunk_keep;
+  a.chunk_off = c->d_chunk_off;
+  a.ticket = c->d_ticket;
+  a.residual_order = c->opt_residual_order;
+  a.hold_on_empty = c->opt_hold_on_empty;
   a.kept_left = c->d_kept_left;
   a.kept_right = c->d_kept_right;
   a.n_kept = c->d_n_kept;
@@ -1326,9 +1335,12 @@ static void fill_stereo_args(vsf_ctx* c, StereoArgs& a, const float* F) {
 }
 
 // upload both frames, L->R kNN + ratio, epipolar filter + compaction (all async)
+// The ctx's threshold ping-pong (thresh_cur) is NOT advanced here: the caller flips it once
+// every stage of its call has been launched successfully, so a failed call leaves the adaptive
+// threshold as it was.  with_threshold = false: the caller places the threshold sum itself.
 static int stereo_stage(vsf_ctx* c, const vsf_keypoint* kpl, const uint8_t* dl, int nl, size_t sl,
                         const vsf_keypoint* kpr, const uint8_t* dr, int nr, size_t sr, const float* F,
-                        double ratio) {
+                        double ratio, bool with_threshold, StereoArgs* args_out = nullptr) {
   if (nl < 0 || nr < 0 || (nl > 0 && (!kpl || !dl)) || (nr > 0 && (!kpr || !dr)) || !F)
     return fail(c, VSF_ERR_BAD_ARG, "bad stereo arguments");
   if ((nl > 0 && sl < size_t(c->desc_bytes)) || (nr > 0 && sr < size_t(c->desc_bytes)))
@@ -1345,8 +1357,8 @@ static int stereo_stage(vsf_ctx* c, const vsf_keypoint* kpl, const uint8_t* dl, 
   if ((rc = run_knn(c, specs, ratio))) return rc;
   StereoArgs a;
   fill_stereo_args(c, a, F);
-  VSF_CUDA(c, launch_stereo_filter(a, std::max(nl, 1), c->stream));
-  c->thresh_cur ^= 1;
+  VSF_CUDA(c, launch_stereo_filter(a, std::max(nl, 1), with_threshold, c->stream));
+  if (args_out) *args_out = a;
   return VSF_OK;
 }
 
@@ -1356,8 +1368,9 @@ extern "C" int vsf_stereo_filter(vsf_ctx* c, const vsf_keypoint* kpl, const uint
                                  vsf_dmatch* stereo_matches, float* residuals, int* n_stereo) {
   if (!c) return VSF_ERR_BAD_ARG;
   if (!n_kept) return fail(c, VSF_ERR_BAD_ARG, "n_kept is required");
-  int rc = stereo_stage(c, kpl, dl, nl, sl, kpr, dr, nr, sr, F, ratio);
+  int rc = stereo_stage(c, kpl, dl, nl, sl, kpr, dr, nr, sr, F, ratio, true);
   if (rc) return rc;
+  c->thresh_cur ^= 1;
   const int region = c->window + 1;
   VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_match_count + region, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1388,6 +1401,25 @@ extern "C" int vsf_set_stereo_threshold(vsf_ctx* c, float value) {
   VSF_CUDA(c, cudaMemcpyAsync(c->d_thresh + c->thresh_cur, c->h_scalar, sizeof(float), cudaMemcpyHostToDevice, c->stream));
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   return VSF_OK;
+}
+
+extern "C" int vsf_set_option(vsf_ctx* c, int option, int value) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (value != 0 && value != 1) return fail(c, VSF_ERR_BAD_ARG, "option value must be 0 or 1");
+  switch (option) {
+    case VSF_OPT_RESIDUAL_ORDER: c->opt_residual_order = value; return VSF_OK;
+    case VSF_OPT_HOLD_THRESHOLD_ON_EMPTY: c->opt_hold_on_empty = value; return VSF_OK;
+    default: return fail(c, VSF_ERR_BAD_ARG, "unknown option");
+  }
+}
+
+extern "C" int vsf_get_option(const vsf_ctx* c, int option, int* value) {
+  if (!c || !value) return VSF_ERR_BAD_ARG;
+  switch (option) {
+    case VSF_OPT_RESIDUAL_ORDER: *value = c->opt_residual_order; return VSF_OK;
+    case VSF_OPT_HOLD_THRESHOLD_ON_EMPTY: *value = c->opt_hold_on_empty; return VSF_OK;
+    default: return VSF_ERR_BAD_ARG;
+  }
 }
 
 extern "C" int vsf_get_stereo_threshold(vsf_ctx* c, float* value) {
@@ -1447,9 +1479,16 @@ extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_key
   if (!c) return VSF_ERR_BAD_ARG;
   if (!out || !P_left || !P_right) return fail(c, VSF_ERR_BAD_ARG, "null argument");
   const int nf = int(c->live.size());
-  if (out->cap < nl) return fail(c, VSF_ERR_CAPACITY, "vsf_observe_out.cap must be >= n_left");
+  // a window list holds at most one entry per row of the PAST frame, the stereo / triangulation
+  // lists at most one per row of this frame: refuse before anything is launched, so that a
+  // failed call leaves the window and the adaptive threshold untouched
+  int need = nl;
+  for (int s : c->live) need = std::max(need, c->slot_count[s]);
+  if (out->cap < need)
+    return fail(c, VSF_ERR_CAPACITY, "vsf_observe_out.cap must be >= n_left and >= the row count of every resident frame");
   // a5: stereo L->R + filter; the compacted left frame lands in the ring's staging slot
-  int rc = stereo_stage(c, kpl, dl, nl, sl, kpr, dr, nr, sr, F, ratio);
+  StereoArgs sa;
+  int rc = stereo_stage(c, kpl, dl, nl, sl, kpr, dr, nr, sr, F, ratio, false, &sa);
   if (rc) return rc;
   // a4 + a6 matching in one launch: every resident past frame vs the compacted left
   // frame, and compacted right (query) vs compacted left (train)
@@ -1461,13 +1500,19 @@ extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_key
   const int tri_region = c->window;
   specs.push_back(ProblemSpec{c->d_right_c, nl, c->d_n_kept, cur, nl, c->d_n_kept, tri_region});
   if ((rc = run_knn(c, specs, ratio, true))) return rc;
+  // triangulation; its extra CTA carries the stereo stage's sequential threshold sum, which
+  // nothing on this frame's critical path waits for
+  TriExtras ex;
+  std::memset(&ex, 0, sizeof(ex));
+  ex.do_threshold = 1;
+  ex.stereo = sa;
   VSF_CUDA(c, launch_triangulate_matches(P_left, P_right, c->region_ptr(tri_region),
                                          c->d_match_count + tri_region, nl, c->d_xy_left_c,
-                                         c->d_xy_right_c, c->d_X4, c->stream));
+                                         c->d_xy_right_c, c->d_X4, &ex, c->stream));
   // match lists and their counts arrive in mapped host memory with the kernels; the rest is
   // sized by two scalars, so: scalars, sync, exactly-sized copies, sync
   VSF_CUDA(c, cudaMemcpyAsync(c->h_counts + kMaxProblems, c->d_n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VSF_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_thresh + c->thresh_cur, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_thresh + (c->thresh_cur ^ 1), sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int k = 0; k <= c->window; ++k) c->h_counts[k] = c->h_region_counts[k];
   const int M = c->h_counts[kMaxProblems];
@@ -1495,6 +1540,8 @@ extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_key
   if (n_tri > 0 && out->tri_matches)
     std::memcpy(out->tri_matches, c->h_matches + size_t(tri_region) * c->rows_pad, size_t(n_tri) * sizeof(vsf_dmatch));
   if (n_tri > 0 && out->tri_X4) std::memcpy(out->tri_X4, c->h_X4, size_t(n_tri) * sizeof(float4));
+  // every stage succeeded: advance the adaptive threshold and the window together
+  c->thresh_cur ^= 1;
   commit_staging(c, frame_id, M);
   return VSF_OK;
 }
@@ -1512,6 +1559,64 @@ extern "C" int vsf_window_match_device(vsf_ctx* c, const void* const* d_queries,
     specs.push_back(ProblemSpec{d_queries[j], nq[j], nullptr, d_train, nt, nullptr, j});
   c->last_n_frames = n_frames;
   return run_knn(c, specs, ratio);
+}
+
+extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int n, int n_poses, long long first,
+                                             int count, double ratio) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  const int W = c->window;
+  if (!d_seq || n < 0 || n > c->max_features || n_poses <= W || first < 0 || count < 0)
+    return fail(c, VSF_ERR_BAD_ARG, "bad device sequence arguments");
+  cudaSetDevice(c->device);
+  const size_t fb = size_t(n) * c->row_bytes;
+  const uint8_t* base = static_cast<const uint8_t*>(d_seq);
+  std::vector<ProblemSpec> specs(W);
+  for (int k = 0; k < count; ++k) {
+    const long long cur = (first + k) % (n_poses - W) + W;
+    for (int j = 0; j < W; ++j)
+      specs[j] = ProblemSpec{base + size_t(cur - W + j) * fb, n, nullptr, base + size_t(cur) * fb, n, nullptr, j};
+    const int rc = run_knn(c, specs, ratio);
+    if (rc) return rc;
+  }
+  c->last_n_frames = W;
+  return VSF_OK;
+}
+
+extern "C" int vsf_window_run_sequence(vsf_ctx* c, const uint8_t* h_seq, int n, int n_poses, long long first,
+                                       int count, double ratio, float best_percent, int sort_mode, int lag,
+                                       vsf_feature_match* out, int* counts, int ring, int cap_per_frame,
+                                       size_t* h2d_bytes, size_t* d2h_bytes) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!h_seq || n < 0 || n_poses < 1 || first < 0 || count < 0 || !out || !counts || ring < 1 || cap_per_frame < 0 ||
+      lag < 1 || lag > VSF_PIPELINE_DEPTH - 1)
+    return fail(c, VSF_ERR_BAD_ARG, "bad host sequence arguments");
+  const int W = c->window;
+  const size_t fb = size_t(n) * c->row_bytes;
+  const int flags = VSF_SUBMIT_PINNED_DESC | VSF_SUBMIT_PADDED_ROWS;   // the buffer is in the device layout
+  uint64_t fid = 0, fids[kMaxProblems];
+  int nf = 0;
+  long long collected = 0;
+  auto collect_one = [&]() -> int {
+    const size_t slot = size_t(collected % ring);
+    const int rc = vsf_window_collect(c, &fid, fids, counts + slot * W, out + slot * W * size_t(cap_per_frame),
+                                      cap_per_frame, &nf);
+    if (rc) return rc;
+    ++collected;
+    if (h2d_bytes) *h2d_bytes += c->last_h2d;
+    if (d2h_bytes) *d2h_bytes += c->last_d2h;
+    return VSF_OK;
+  };
+  for (int k = 0; k < count; ++k) {
+    const uint8_t* D = h_seq + size_t((first + k) % n_poses) * fb;
+    int rc = vsf_window_submit(c, uint64_t(first + k), D, n, size_t(c->row_bytes), ratio, best_percent, sort_mode, flags);
+    if (rc) return rc;
+    if (c->flight_count > lag && (rc = collect_one())) return rc;
+  }
+  while (c->flight_count > 0) {
+    const int rc = collect_one();
+    if (rc) return rc;
+  }
+  return VSF_OK;
 }
 
 extern "C" int vsf_fetch_window(vsf_ctx* c, int n_frames, int* counts, vsf_dmatch* out, int cap_per_frame) {
@@ -1533,10 +1638,11 @@ extern "C" int vsf_fetch_window(vsf_ctx* c, int n_frames, int* counts, vsf_dmatc
 extern "C" int vsf_synth_sequence_device(vsf_ctx* c, void* d_out, int n, int first_pose, int n_poses, int stride,
                                          uint64_t seed) {
   if (!c) return VSF_ERR_BAD_ARG;
-  if (!d_out || n < 1 || n_poses < 0 || first_pose < 0 || stride < 0 || c->row_bytes != 32)
-    return fail(c, VSF_ERR_BAD_ARG, "bad synth arguments (generator produces 32-byte rows)");
+  if (!d_out || n < 1 || n_poses < 0 || first_pose < 0 || stride < 0)
+    return fail(c, VSF_ERR_BAD_ARG, "bad synth arguments");
   cudaSetDevice(c->device);
-  VSF_CUDA(c, launch_synth(static_cast<uint32_t*>(d_out), n, first_pose, n_poses, stride, seed, c->stream));
+  VSF_CUDA(c, launch_synth(static_cast<uint32_t*>(d_out), n, first_pose, n_poses, stride, seed, c->words,
+                           c->desc_bytes, c->stream));
   return VSF_OK;
 }
 

@@ -92,6 +92,13 @@ class Frontend:
     def __exit__(self, *exc):
         self.close()
 
+    def _desc(self, a) -> np.ndarray:
+        """Descriptor matrix as the C++ side reads it: 2-D uint8, exactly desc_bytes wide."""
+        a = np.ascontiguousarray(a, np.uint8)
+        if a.ndim != 2 or a.shape[1] != self.desc_bytes:
+            raise ValueError("descriptors must be (n, %d) uint8, got %r" % (self.desc_bytes, a.shape))
+        return a
+
     def observe_odometry(self, translation, rotation_wxyz, timestamp: float):
         t = np.ascontiguousarray(translation, np.float32)
         q = np.ascontiguousarray(rotation_wxyz, np.float32)
@@ -100,8 +107,10 @@ class Frontend:
     def observe_features(self, kp_left, desc_left, kp_right, desc_right, time: float = 0.0) -> bool:
         kl = np.ascontiguousarray(kp_left, KEYPOINT_DTYPE)
         kr = np.ascontiguousarray(kp_right, KEYPOINT_DTYPE)
-        dl = np.ascontiguousarray(desc_left, np.uint8)
-        dr = np.ascontiguousarray(desc_right, np.uint8)
+        dl = self._desc(desc_left)
+        dr = self._desc(desc_right)
+        if len(dl) != len(kl) or len(dr) != len(kr):
+            raise ValueError("keypoint / descriptor row mismatch")
         rc = self._L.vsff_observe_features(self._h, kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data,
                                            dr.ctypes.data, len(kr), self.desc_bytes, float(time))
         if rc < 0:
@@ -109,8 +118,7 @@ class Frontend:
         return bool(rc)
 
     def get_matches(self, Q, T, ratio: float) -> np.ndarray:
-        Q = np.ascontiguousarray(Q, np.uint8)
-        T = np.ascontiguousarray(T, np.uint8)
+        Q, T = self._desc(Q), self._desc(T)
         out = np.zeros(max(len(Q), 1), DMATCH_DTYPE)
         n = self._L.vsff_get_matches(self._h, Q.ctypes.data, len(Q), T.ctypes.data, len(T), self.desc_bytes,
                                      float(ratio), out.ctypes.data, len(out))

@@ -33,6 +33,17 @@ def halo_range(first: int, window: int) -> Tuple[int, int]:
     return max(0, first - window), first
 
 
+def observe_halo_start(first: int, window: int) -> int:
+    """First pose a rank must run through the full ObserveImage path (stereo stage included)
+    before its own range starts at `first`: the `window` poses whose compacted left frames are
+    resident when pose `first` is matched (src/slam_frontend.cc:424-434), plus ONE pose before
+    them that only supplies the adaptive stereo threshold - `stereo_ambig_constraint` after a
+    frame is the mean residual of that frame's raw matches + 2 (:392-394) and does not depend
+    on the threshold the frame itself was filtered with, so one extra pose re-creates the
+    1-float halo without any communication."""
+    return max(0, first - window - 1)
+
+
 def pack_records(lists: Sequence[np.ndarray], pose_initial: Sequence[int] = None,
                  pose_current: Sequence[int] = None) -> np.ndarray:
     """DMATCH arrays (one per frame pair) -> (n, 6) int32 records."""
