@@ -382,13 +382,27 @@ def run_b200(a):
     if not a.no_e2e:
         e2e = measure_e2e(a, ctx, seq, n, W, K, WU, B, world, dist, torch, host_threads)
 
-    # ---- gather the last step's match lists over NCCL (outside the timed region) ------------
+    # ---- gather one pose's match lists from every rank (outside the timed region): libvsf_nccl's
+    # vsf_gather_matches, two ncclAllGathers straight from the device regions on the ctx stream
     gathered = None
     if world > 1:
+        from vision_slam_frontend_b200 import nccl
+        comm = nccl.Comm.from_torch_distributed(local)
         ctx.window_match_block_device(base, n, n_poses, 0, 1, RATIO)
-        last = ctx.fetch_window(W)
-        gathered = sharding.gather_match_lists(last, device=torch.device("cuda", local))
-        gathered = sum(len(m) for r in gathered for m in r)
+        S = nccl.match_list_stride(ctx)
+        d_counts = torch.zeros((world, W), dtype=torch.int32, device="cuda")
+        d_lists = torch.zeros((world, W, S, 16), dtype=torch.uint8, device="cuda")
+        comm.gather_matches(ctx, W, d_counts.data_ptr(), d_lists.data_ptr())     # warm-up (NCCL channel setup)
+        ctx.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        comm.gather_matches(ctx, W, d_counts.data_ptr(), d_lists.data_ptr())
+        g1.record(stream)
+        ctx.synchronize()
+        gathered = {"matches": int(d_counts.sum().item()), "ranks": world, "ms": g0.elapsed_time(g1),
+                    "bytes_per_rank": W * S * 16 + 4 * W,
+                    "api": "vsf_gather_matches (libvsf_nccl.so): ncclAllGather of counts + list regions, device to device"}
+        comm.close()
 
     if rank == 0:
         # integer-pipe denominators, measured here
@@ -503,7 +517,7 @@ def run_b200(a):
         if e2e:
             line["e2e"] = e2e
         if gathered is not None:
-            line["nccl_gathered_matches"] = gathered
+            line["nccl_gather"] = gathered
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
         if world == 1 and not a.no_extra:

@@ -311,6 +311,9 @@ typedef struct vsf_observe_out {
                                 * has one entry per row of the PAST frame at most); the ctx's
                                 * max_features always suffices.  VSF_ERR_CAPACITY otherwise, with
                                 * the ctx state (window, stereo threshold) left as before the call. */
+  /* N1 (src/slam_frontend.cc:323-351), filled by vsf_observe_collect when the frame was submitted
+   * with K_left / dist_left: the undistorted pixel of compacted left keypoint i */
+  float* xy_undist;            /* [cap][2], optional */
 } vsf_observe_out;
 
 /* Replaces everything Frontend::ObserveImage does between ExtractFeatures and
@@ -328,6 +331,35 @@ int vsf_observe_features(vsf_ctx* ctx, uint64_t frame_id,
                          const float* fundamental, const float* P_left,
                          const float* P_right, double nn_match_ratio,
                          vsf_observe_out* out);
+
+/* Pipelined form of vsf_observe_features for a frame stream.  Everything a frame needs from its
+ * predecessors lives on the device (the compacted left frames in the window ring with their row
+ * counts, the adaptive stereo threshold), so vsf_observe_submit enqueues a whole frame - one
+ * upload of both images' descriptors and pixels, stereo kNN + filter + compaction, window kNN,
+ * R'->L' kNN, triangulation (+ the undistorted pixels of the kept left keypoints when K_left and
+ * dist_left are given, N1) - and returns WITHOUT waiting; the kernels store their results
+ * straight into page-locked host memory.  Up to VSF_OBSERVE_DEPTH frames may be in flight;
+ * vsf_observe_collect waits for the OLDEST one and fills `out` exactly as vsf_observe_features
+ * would have (out->cap as documented above; a collect that fails with VSF_ERR_CAPACITY has
+ * consumed the frame, which stays in the window).  vsf_observe_features itself is submit +
+ * collect. */
+typedef struct vsf_observe_params {
+  const float* fundamental;  /* 9, row-major, x_left^T F x_right */
+  const float* P_left;       /* 12 */
+  const float* P_right;      /* 12 */
+  const float* K_left;       /* 9, optional (with dist_left): undistort the kept left pixels */
+  const float* dist_left;    /* 5: k1 k2 p1 p2 k3 */
+  double nn_match_ratio;
+} vsf_observe_params;
+#define VSF_OBSERVE_DEPTH 4
+int vsf_observe_submit(vsf_ctx* ctx, uint64_t frame_id,
+                       const vsf_keypoint* kp_left, const uint8_t* desc_left,
+                       int n_left, size_t stride_left,
+                       const vsf_keypoint* kp_right, const uint8_t* desc_right,
+                       int n_right, size_t stride_right,
+                       const vsf_observe_params* params);
+int vsf_observe_collect(vsf_ctx* ctx, uint64_t* frame_id, vsf_observe_out* out);
+int vsf_observe_in_flight(const vsf_ctx* ctx);
 
 /* ------------------------ device-resident entry points (no host copies) */
 
@@ -368,6 +400,16 @@ int vsf_window_run_sequence(vsf_ctx* ctx, const uint8_t* h_seq, int n, int n_pos
                             float best_percent, int sort_mode, int lag,
                             vsf_feature_match* out, int* counts, int ring, int cap_per_frame,
                             size_t* h2d_bytes, size_t* d2h_bytes);
+
+/* Where the compaction kernels leave the match lists of the most recent window launch: region j
+ * (past frame j, oldest first) = *d_lists + j * *stride records, its length at (*d_counts)[j];
+ * *regions = number of regions.  Device pointers, valid for the life of the ctx; contents are
+ * ordered on the ctx's stream (vsf_stream).  For consumers that keep the lists on the device
+ * (libvsf_nccl's vsf_gather_matches). */
+int vsf_device_match_lists(vsf_ctx* ctx, const vsf_dmatch** d_lists, const int** d_counts,
+                           int* stride, int* regions);
+/* The CUDA stream (cudaStream_t as void*) the ctx currently launches on. */
+void* vsf_stream(vsf_ctx* ctx);
 
 /* Synthetic sequence generator (bench / test frame source; counter-based so
  * any pose range can be produced on any rank): pose p observes landmarks

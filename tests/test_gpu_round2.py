@@ -346,3 +346,170 @@ def test_window_run_sequence_equals_per_frame_calls(sort_mode):
             np.testing.assert_array_equal(out[k, j, :keep]["feature_idx_current"], exp["trainIdx"].astype(np.uint64))
         live.pop(0)
         live.append(D)
+
+
+# ------------------------------------------- the whole frame, pipelined (vsf_observe_submit / collect)
+
+@pytest.mark.parametrize("depth", [1, 4])
+def test_observe_submit_collect_against_frontend_oracle(depth):
+    """Up to VSF_OBSERVE_DEPTH whole frames in flight: everything a frame needs from its
+    predecessors (compacted frames, their row counts, the adaptive threshold) stays on the
+    device.  Every collected frame equals the oracle's, N1 included."""
+    P1, P2 = synth.kitti_projections()
+    F = synth.kitti_fundamental()
+    K = synth.KITTI_K.astype(np.float32)
+    dist = np.array([-0.153137, 0.075666, -0.000227, -0.000320, 0.01], np.float32)
+    W = 3
+    frames = synth.stereo_sequence(9, 1800, seed=61)
+    frames[4] = tuple(a[:700] for a in frames[4])          # a smaller frame in the middle of the stream
+    fo = restate.FrontendOracle(P1, P2, F, frame_life=W, order="stable")
+    expected = []
+    with new_ctx(window=W, max_features=2048) as ctx:
+        def check_one():
+            got = ctx.observe_collect()
+            p, past, r, thr = expected.pop(0)
+            assert got["frame_id"] == p
+            sm = r.stereo_matches
+            np.testing.assert_array_equal(got["kept_left"], sm["queryIdx"][r.stereo_keep])
+            np.testing.assert_array_equal(got["kept_right"], sm["trainIdx"][r.stereo_keep])
+            assert same_f32(got["stereo_threshold_next"], thr)
+            assert [fid for fid, _ in got["window"]] == [f.frame_ID for f in past]
+            for (fid, m), pf in zip(got["window"], past):
+                np.testing.assert_array_equal(m, native.get_matches(pf.descriptors, r.left.descriptors, RATIO))
+            tm = native.get_matches(r.right.descriptors, r.left.descriptors, RATIO)
+            np.testing.assert_array_equal(got["tri_matches"], tm)
+            order = restate.sort_order_stable(tm)
+            pts = restate.dehomogenize(got["tri_X4"].T)[order]
+            rel = np.abs(pts - r.points).max(1) / np.abs(r.points).max(1)
+            assert rel.max() < 1e-4, rel.max()
+            np.testing.assert_allclose(got["xy_undist"], restate.undistort_points(r.features_pixel, K, dist), atol=2e-3)
+
+        for p, (kl, dl, kr, dr) in enumerate(frames):
+            past = list(fo.frame_list)
+            r = fo.observe_features(kl, dl, kr, dr)
+            expected.append((p, past, r, fo.stereo_ambig_constraint))
+            ctx.observe_submit(p, kl, dl, kr, dr, F, P1, P2, K, dist, RATIO)
+            assert ctx.observe_in_flight() == len(expected)
+            while ctx.observe_in_flight() >= depth:
+                check_one()
+        while expected:
+            check_one()
+        assert ctx.window_size() == W
+        assert same_f32(ctx.get_stereo_threshold(), fo.stereo_ambig_constraint)
+
+
+@pytest.mark.parametrize("width", [32, 61])
+def test_frontend_pipelined_equals_blocking(width):
+    """Frontend::SubmitFeatures / CollectFeatures with several frames pending produce the same
+    SLAMProblem bytes as ObserveFeatures frame by frame."""
+    from vision_slam_frontend_b200.frontend import Frontend, synthetic_rig, synth_frame
+    rig = synthetic_rig()
+    n, W, poses = 1200, 3, 9
+    seq = [synth_frame(n, width, 7, p) for p in range(poses)]
+
+    def run(pipelined):
+        with Frontend(max_features=n, desc_bytes=width, frame_life=W, P_left=rig["P_left"], P_right=rig["P_right"],
+                      fundamental=rig["fundamental"], K_left=rig["K_left"], dist_left=rig["dist_left"]) as fe:
+            for p, (kl, dl, kr, dr, t, q, ts) in enumerate(seq):
+                fe.observe_odometry(t, q, ts)
+                if pipelined:
+                    assert fe.submit_features(kl, dl, kr, dr, ts)
+                    while fe.in_flight >= 3:
+                        assert fe.collect_features()
+                else:
+                    assert fe.observe_features(kl, dl, kr, dr, ts)
+            while fe.collect_features():
+                pass
+            assert fe.num_poses == poses
+            return fe.serialize_problem()
+
+    a, b = run(False), run(True)
+    assert len(a) > 100000 and a == b
+
+
+def test_synthetic_sequence_against_frontend_oracle():
+    """The C++ chain synthetic source -> Frontend (pipelined) -> SLAMProblem message against the
+    FrontendOracle fed with the same frames: every vision factor and node."""
+    from vision_slam_frontend_b200.frontend import (parse_slam_problem, run_synthetic_sequence, synth_frame,
+                                                    synthetic_rig)
+    rig = synthetic_rig()
+    n, W, poses, width, seed = 1500, 4, 9, 61, 5
+    msg = parse_slam_problem(run_synthetic_sequence(n, width, W, poses, world=1, in_flight=3, seed=seed))
+    fo = restate.FrontendOracle(rig["P_left"], rig["P_right"], rig["fundamental"], frame_life=W, order="stdsort")
+    results = []
+    for p in range(poses):
+        kl, dl, kr, dr, t, q, ts = synth_frame(n, width, seed, p)
+        results.append((fo.observe_features(kl, dl, kr, dr), t, ts))
+    assert len(msg["vision_factors"]) == len(fo.vision_factors) == sum(min(p, W) for p in range(poses))
+    for (a, b, pairs), e in zip(msg["vision_factors"], fo.vision_factors):
+        assert (a, b) == (e.pose_idx_initial, e.pose_idx_current)
+        np.testing.assert_array_equal(pairs, e.feature_matches)
+    assert sum(len(p) for _, _, p in msg["vision_factors"]) > 1000
+    assert len(msg["nodes"]) == poses and len(msg["odometry_factors"]) == poses - 1
+    for p, (r, t, ts) in enumerate(results):
+        node = msg["nodes"][p]
+        assert node["id"] == p and node["timestamp"] == ts and len(node["features"]) == len(r.features_pixel)
+        pix = np.array([f[1][:2] for f in node["features"]], np.float32)
+        np.testing.assert_allclose(pix, restate.undistort_points(r.features_pixel, rig["K_left"], rig["dist_left"]),
+                                   atol=2e-3)
+        p3 = np.array([f[2] for f in node["features"]], np.float32)
+        np.testing.assert_array_equal(np.isnan(p3), np.isnan(r.features_point3d))
+        ok = ~np.isnan(p3).any(1)
+        rel = np.abs(p3[ok] - r.features_point3d[ok]).max(1) / np.abs(r.features_point3d[ok]).max(1)
+        assert rel.max() < 1e-4
+
+
+@pytest.mark.parametrize("width", [32, 61])
+def test_synthetic_sequence_sharded_bytes_equal_unsharded(width):
+    """SURVEY 8(e) at the level the reference writes its output (src/slam_frontend_main.cc:369-374):
+    the SLAMProblem message of a sequence run as 2 and 3 pose-range shards (each with its
+    (window + 1)-frame halo, pipelined) is byte-identical to the unsharded one."""
+    from vision_slam_frontend_b200.frontend import run_synthetic_sequence
+    n, W, poses = 1000, 3, 23
+    whole = run_synthetic_sequence(n, width, W, poses, world=1, in_flight=1)
+    assert len(whole) > 300000
+    for world, depth in ((2, 3), (3, 4)):
+        assert run_synthetic_sequence(n, width, W, poses, world=world, in_flight=depth) == whole
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_sequence_driver_two_ranks_over_nccl(tmp_path):
+    """vsf_sequence_driver as 2 processes on 2 GPUs: pieces gathered to rank 0 with
+    vsf_nccl_gather_bytes; the file equals the one a single process writes."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "vision_slam_frontend_b200", "vsf_sequence_driver")
+    common = ["--poses", "30", "--features", "1200", "--window", "4", "--desc-bytes", "61"]
+    one = str(tmp_path / "one.bin")
+    subprocess.run([exe, *common, "--world", "1", "--rank", "0", "--device", "0", "--out", one], check=True, timeout=300)
+    two = str(tmp_path / "two.bin")
+    rdv = str(tmp_path / "nccl_id")
+    procs = [subprocess.Popen([exe, *common, "--world", "2", "--rank", str(r), "--device", str(r), "--out", two,
+                               "--rendezvous", rdv]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    a, b = open(one, "rb").read(), open(two, "rb").read()
+    assert len(a) > 100000 and a == b
+
+
+def test_gather_matches_two_ranks_over_nccl(tmp_path):
+    """vsf_gather_matches under torchrun on 2 GPUs: every rank ends up with every rank's device
+    match lists, equal to the oracle's for that rank's pose."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611",
+                        os.path.join(root, "tools", "nccl_gather_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert p.stdout.count("gather ok") == 2

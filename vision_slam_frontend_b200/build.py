@@ -15,6 +15,9 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "libvsf_cuda.so")
 FRONTEND_LIB = os.path.join(PKG, "libvsf_frontend.so")
+NCCL_LIB = os.path.join(PKG, "libvsf_nccl.so")
+DRIVER_BIN = os.path.join(PKG, "vsf_sequence_driver")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 CUDA_SOURCES = ["knn2_kernel.cu", "knn2_tc_kernel.cu", "knn2_tc64_kernel.cu", "stereo_kernels.cu", "sort_kernel.cu",
                 "aux_kernels.cu", "vsf_api.cu"]
@@ -72,12 +75,38 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_nccl(force: bool = False) -> str:
+    """libvsf_nccl.so: the result gathers of the sharded path (include/vsf_nccl.h)."""
+    src = os.path.join(CSRC, "nccl", "vsf_nccl.cc")
+    if force or _stale(NCCL_LIB, [src, os.path.join(INCLUDE, "vsf_nccl.h"), os.path.join(INCLUDE, "vsf.h"), LIB]):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", INCLUDE,
+               "-I", os.path.join(CUDA_HOME, "include"), "-o", NCCL_LIB + ".tmp", src,
+               "-L", PKG, "-lvsf_cuda", "-L", os.path.join(CUDA_HOME, "lib64"), "-lcudart", "-lnccl",
+               "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+        os.replace(NCCL_LIB + ".tmp", NCCL_LIB)
+    return NCCL_LIB
+
+
+def build_driver(force: bool = False) -> str:
+    """vsf_sequence_driver: synthetic stereo source -> sharded slam::Frontend -> one SLAMProblem."""
+    src = os.path.join(CSRC, "frontend", "sequence_driver.cc")
+    if force or _stale(DRIVER_BIN, [src, FRONTEND_LIB, NCCL_LIB]):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", INCLUDE, "-I", os.path.join(CSRC, "frontend"),
+               "-o", DRIVER_BIN + ".tmp", src, "-L", PKG, "-lvsf_frontend", "-lvsf_nccl", "-lvsf_cuda",
+               "-Wl,-rpath,$ORIGIN", "-lpthread"]
+        subprocess.check_call(cmd)
+        os.replace(DRIVER_BIN + ".tmp", DRIVER_BIN)
+    return DRIVER_BIN
+
+
 def build_frontend(force: bool = False) -> str:
     """C++ host mirror of slam::Frontend on top of the C ABI."""
     fdir = os.path.join(CSRC, "frontend")
     if not os.path.isdir(fdir):
         return ""
-    srcs = [os.path.join(fdir, f) for f in sorted(os.listdir(fdir)) if f.endswith(".cc")]
+    srcs = [os.path.join(fdir, f) for f in sorted(os.listdir(fdir))
+            if f.endswith(".cc") and f != "sequence_driver.cc"]
     hdrs = [os.path.join(fdir, f) for f in os.listdir(fdir) if f.endswith(".h")]
     if not srcs:
         return ""
@@ -91,7 +120,10 @@ def build_frontend(force: bool = False) -> str:
 
 
 def build_all(force: bool = False, verbose: bool = False) -> dict:
-    return {"cuda": build_cuda(force, verbose), "frontend": build_frontend(force)}
+    out = {"cuda": build_cuda(force, verbose), "frontend": build_frontend(force)}
+    out["nccl"] = build_nccl(force)
+    out["driver"] = build_driver(force)
+    return out
 
 
 if __name__ == "__main__":

@@ -45,7 +45,12 @@ class _ObserveOut(C.Structure):
                 ("n_frames", C.c_int), ("frame_ids", C.c_void_p),
                 ("window_counts", C.c_void_p), ("window_matches", C.c_void_p),
                 ("n_tri", C.c_int), ("tri_matches", C.c_void_p),
-                ("tri_X4", C.c_void_p), ("cap", C.c_int)]
+                ("tri_X4", C.c_void_p), ("cap", C.c_int), ("xy_undist", C.c_void_p)]
+
+
+class _ObserveParams(C.Structure):
+    _fields_ = [("fundamental", C.c_void_p), ("P_left", C.c_void_p), ("P_right", C.c_void_p),
+                ("K_left", C.c_void_p), ("dist_left", C.c_void_p), ("nn_match_ratio", C.c_double)]
 
 
 def library_path() -> str:
@@ -105,6 +110,11 @@ def load_library():
         "vsf_window_run_sequence": ([vp, vp, i, i, C.c_longlong, i, d, f, i, i, vp, vp, i, i,
                                      C.POINTER(sz), C.POINTER(sz)], i),
         "vsf_synth_sequence_device": ([vp, vp, i, i, i, i, u64], i),
+        "vsf_device_match_lists": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), C.POINTER(i)], i),
+        "vsf_stream": ([vp], vp),
+        "vsf_observe_submit": ([vp, u64, vp, vp, i, sz, vp, vp, i, sz, C.POINTER(_ObserveParams)], i),
+        "vsf_observe_collect": ([vp, C.POINTER(u64), C.POINTER(_ObserveOut)], i),
+        "vsf_observe_in_flight": ([vp], i),
         "vsf_probe_pipe": ([vp, i, i, C.POINTER(d)], i),
         "vsf_device_sm_count": ([vp], i),
         "vsf_debug_tc_trace": ([vp, vp, i, C.POINTER(i)], i),
@@ -130,7 +140,8 @@ EXPORTED_SYMBOLS = [
     "vsf_get_stereo_threshold", "vsf_set_option", "vsf_get_option", "vsf_triangulate", "vsf_undistort_points", "vsf_observe_features",
     "vsf_device_row_bytes", "vsf_window_match_device", "vsf_fetch_window",
     "vsf_window_match_block_device", "vsf_window_run_sequence",
-    "vsf_synth_sequence_device", "vsf_probe_pipe", "vsf_device_sm_count",
+    "vsf_synth_sequence_device", "vsf_device_match_lists", "vsf_stream", "vsf_observe_submit",
+    "vsf_observe_collect", "vsf_observe_in_flight", "vsf_probe_pipe", "vsf_device_sm_count",
     "vsf_debug_tc_trace", "vsf_debug_kernel_trace", "vsf_debug_tc_plan", "vsf_debug_sort_prefix",
 ]
 
@@ -395,7 +406,7 @@ class Context:
         tm = np.zeros(cap, DMATCH_DTYPE)
         X4 = np.zeros((cap, 4), np.float32)
         o = _ObserveOut(_ptr(kept_l), _ptr(kept_r), 0, 0.0, 0, _ptr(fids), _ptr(wc), _ptr(wm),
-                        0, _ptr(tm), _ptr(X4), cap)
+                        0, _ptr(tm), _ptr(X4), cap, None)
         self._check(self._L.vsf_observe_features(
             self._h, frame_id, _ptr(kl), _ptr(dl), len(kl), dl.strides[0], _ptr(kr), _ptr(dr),
             len(kr), dr.strides[0], _ptr(F), _ptr(P1), _ptr(P2), float(ratio), C.byref(o)))
@@ -404,6 +415,47 @@ class Context:
             stereo_threshold_next=np.float32(o.stereo_threshold_next),
             window=[(int(fids[j]), wm[j, :wc[j]].copy()) for j in range(o.n_frames)],
             tri_matches=tm[:o.n_tri].copy(), tri_X4=X4[:o.n_tri].copy())
+
+    # pipelined form: submit whole frames ahead, collect them in order
+    def observe_submit(self, frame_id: int, kp_left, desc_left, kp_right, desc_right, F, P_left,
+                       P_right, K_left, dist_left, ratio: float):
+        """K_left / dist_left may be None (no undistorted pixels are produced then)."""
+        kl = np.ascontiguousarray(kp_left, KEYPOINT_DTYPE)
+        kr = np.ascontiguousarray(kp_right, KEYPOINT_DTYPE)
+        dl, dr = _u8rows(desc_left, self.desc_bytes), _u8rows(desc_right, self.desc_bytes)
+        arrs = [np.ascontiguousarray(F, np.float32).reshape(9),
+                np.ascontiguousarray(P_left, np.float32).reshape(12),
+                np.ascontiguousarray(P_right, np.float32).reshape(12),
+                None if K_left is None else np.ascontiguousarray(K_left, np.float32).reshape(9),
+                None if dist_left is None else np.ascontiguousarray(dist_left, np.float32).reshape(5)]
+        prm = _ObserveParams(*[_ptr(a) for a in arrs], float(ratio))
+        self._check(self._L.vsf_observe_submit(
+            self._h, frame_id, _ptr(kl), _ptr(dl), len(kl), dl.strides[0], _ptr(kr), _ptr(dr),
+            len(kr), dr.strides[0], C.byref(prm)))
+
+    def observe_in_flight(self) -> int:
+        return self._L.vsf_observe_in_flight(self._h)
+
+    def observe_collect(self) -> dict:
+        cap = self.max_features
+        W = self.window
+        kept_l, kept_r = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        fids, wc = np.zeros(W, np.uint64), np.zeros(W, np.int32)
+        wm = np.zeros((W, cap), DMATCH_DTYPE)
+        tm = np.zeros(cap, DMATCH_DTYPE)
+        X4 = np.zeros((cap, 4), np.float32)
+        xyu = np.full((cap, 2), np.nan, np.float32)
+        o = _ObserveOut(_ptr(kept_l), _ptr(kept_r), 0, 0.0, 0, _ptr(fids), _ptr(wc), _ptr(wm),
+                        0, _ptr(tm), _ptr(X4), cap, _ptr(xyu))
+        fid = C.c_uint64(0)
+        self._check(self._L.vsf_observe_collect(self._h, C.byref(fid), C.byref(o)))
+        return dict(
+            frame_id=int(fid.value),
+            kept_left=kept_l[:o.n_kept].copy(), kept_right=kept_r[:o.n_kept].copy(),
+            stereo_threshold_next=np.float32(o.stereo_threshold_next),
+            window=[(int(fids[j]), wm[j, :wc[j]].copy()) for j in range(o.n_frames)],
+            tri_matches=tm[:o.n_tri].copy(), tri_X4=X4[:o.n_tri].copy(),
+            xy_undist=xyu[:o.n_kept].copy())
 
     # -- device-resident entry points -------------------------------------------------------
     def window_match_device(self, d_queries: Sequence[int], nq: Sequence[int], d_train: int,

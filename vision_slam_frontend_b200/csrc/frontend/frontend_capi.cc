@@ -1,10 +1,14 @@
 // extern "C" handles onto slam::Frontend so that the Python tests (ctypes) can drive
 // the C++ host mirror.  Not part of the product ABI (that is include/vsf.h); it exists
 // for tests/test_gpu_frontend.py and as an example of embedding the Frontend.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 #include "slam_frontend.h"
+#include "synthetic_source.h"
 
 namespace {
 struct Handle {
@@ -181,5 +185,125 @@ size_t vsff_serialize_problem(void* p, uint8_t* buf, size_t cap) {
   if (buf && cap >= h->wire.size()) std::memcpy(buf, h->wire.data(), h->wire.size());
   return h->wire.size();
 }
+
+
+// ---- pipelined calls and shards -------------------------------------------------------------
+// 1 = frame submitted, 0 = odometry gate said no, -1 = error.  The descriptor rows are copied:
+// the Python caller's arrays need not outlive the call.
+int vsff_submit_features(void* p, const vsf_keypoint* kl, const uint8_t* dl, int nl, const vsf_keypoint* kr,
+                         const uint8_t* dr, int nr, int desc_bytes, double time) {
+  Handle* h = static_cast<Handle*>(p);
+  try {
+    std::vector<cv::KeyPoint> lk(nl), rk(nr);
+    if (nl) std::memcpy(static_cast<void*>(lk.data()), kl, size_t(nl) * sizeof(vsf_keypoint));
+    if (nr) std::memcpy(static_cast<void*>(rk.data()), kr, size_t(nr) * sizeof(vsf_keypoint));
+    cv::Mat ld = cv::Mat(nl, desc_bytes, CV_8U, const_cast<uint8_t*>(dl)).clone();
+    cv::Mat rd = cv::Mat(nr, desc_bytes, CV_8U, const_cast<uint8_t*>(dr)).clone();
+    return h->fe->SubmitFeatures(lk, ld, rk, rd, time) ? 1 : 0;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return -1;
+  }
+}
+
+int vsff_collect_features(void* p) {
+  Handle* h = static_cast<Handle*>(p);
+  try {
+    return h->fe->CollectFeatures() ? 1 : 0;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return -1;
+  }
+}
+
+int vsff_in_flight(void* p) { return static_cast<Handle*>(p)->fe->InFlight(); }
+
+int vsff_start_shard(void* p, uint64_t halo_first, uint64_t first) {
+  Handle* h = static_cast<Handle*>(p);
+  try {
+    h->fe->StartShard(halo_first, first);
+    return 0;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return -1;
+  }
+}
+
+// ---- synthetic frame source (csrc/frontend/synthetic_source.h) --------------------------------
+static slam::FrontendConfig SynthRig(int device, int features, int desc_bytes, int frame_life, int exact) {
+  return slam::SyntheticRig(device, features, desc_bytes, frame_life, exact != 0);
+}
+
+// The rig of the synthetic runs (P_left 12, P_right 12, fundamental 9, K_left 9, dist_left 5).
+void vsff_synthetic_rig(float* P_left, float* P_right, float* fundamental, float* K_left, float* dist_left) {
+  const slam::FrontendConfig cfg = slam::SyntheticRig(0, 1, 32, 10, true);
+  std::memcpy(P_left, cfg.projection_left, 12 * sizeof(float));
+  std::memcpy(P_right, cfg.projection_right, 12 * sizeof(float));
+  std::memcpy(fundamental, cfg.fundamental, 9 * sizeof(float));
+  std::memcpy(K_left, cfg.camera_matrix_left, 9 * sizeof(float));
+  std::memcpy(dist_left, cfg.distortion_coeffs_left, 5 * sizeof(float));
+}
+
+// One frame + its odometry message (kl / kr: features records, dl / dr: features x desc_bytes).
+int vsff_synth_frame(int features, int desc_bytes, uint64_t seed, uint64_t pose, vsf_keypoint* kl, uint8_t* dl,
+                     vsf_keypoint* kr, uint8_t* dr, float* odom_t3, float* odom_q_wxyz, double* timestamp) {
+  try {
+    slam::SyntheticStereoConfig sc;
+    sc.features = features;
+    sc.landmark_stride = std::max(1, features / 10);
+    sc.seed = seed;
+    slam::SyntheticStereoSource src(SynthRig(0, features, desc_bytes, 10, 1), sc);
+    std::vector<cv::KeyPoint> lk, rk;
+    cv::Mat ld, rd;
+    src.Frame(pose, &lk, &ld, &rk, &rd);
+    std::memcpy(static_cast<void*>(kl), lk.data(), lk.size() * sizeof(vsf_keypoint));
+    std::memcpy(static_cast<void*>(kr), rk.data(), rk.size() * sizeof(vsf_keypoint));
+    for (int i = 0; i < features; ++i) {
+      std::memcpy(dl + size_t(i) * desc_bytes, ld.ptr(i), size_t(desc_bytes));
+      std::memcpy(dr + size_t(i) * desc_bytes, rd.ptr(i), size_t(desc_bytes));
+    }
+    Eigen::Vector3f t;
+    Eigen::Quaternionf q;
+    src.Odometry(pose, &t, &q, timestamp);
+    odom_t3[0] = t.x(); odom_t3[1] = t.y(); odom_t3[2] = t.z();
+    odom_q_wxyz[0] = q.w(); odom_q_wxyz[1] = q.x(); odom_q_wxyz[2] = q.y(); odom_q_wxyz[3] = q.z();
+    return 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
+
+// Poses [0, n_poses) of the synthetic sequence run as `world` shards - one after the other in
+// this process, each on a fresh Frontend with its halo, exactly what the ranks of
+// vsf_sequence_driver do - and merged into ONE SLAMProblem message.  Returns the byte count and
+// a malloc'ed buffer (vsff_free), 0 on error (message in err, up to err_cap bytes).
+size_t vsff_run_synthetic_sequence(int device, int features, int desc_bytes, int frame_life, int n_poses, int world,
+                                   int in_flight, uint64_t seed, int exact, uint8_t** out, char* err, int err_cap) {
+  try {
+    slam::FrontendConfig rig = SynthRig(device, features, desc_bytes, frame_life, exact);
+    slam::SyntheticStereoConfig sc;
+    sc.features = features;
+    sc.landmark_stride = std::max(1, features / 10);
+    sc.seed = seed;
+    slam::SyntheticStereoSource src(rig, sc);
+    std::vector<slam::SLAMProblemPiece> pieces;
+    for (int r = 0; r < world; ++r) {
+      const uint64_t base = uint64_t(n_poses) / world, rem = uint64_t(n_poses) % world;
+      const uint64_t first = r * base + std::min<uint64_t>(r, rem), last = first + base + (uint64_t(r) < rem ? 1 : 0);
+      // through Pack / Unpack, the form a piece travels in between ranks
+      const std::vector<uint8_t> blob = slam::RunSequenceShard(rig, src, first, last, in_flight).Pack();
+      pieces.push_back(slam::SLAMProblemPiece::Unpack(blob.data(), blob.size()));
+    }
+    const std::vector<uint8_t> wire = slam::MergeSLAMProblemPieces(pieces);
+    *out = static_cast<uint8_t*>(std::malloc(wire.size() ? wire.size() : 1));
+    std::memcpy(*out, wire.data(), wire.size());
+    return wire.size();
+  } catch (const std::exception& e) {
+    if (err && err_cap > 0) std::snprintf(err, size_t(err_cap), "%s", e.what());
+    return 0;
+  }
+}
+
+void vsff_free(void* p) { std::free(p); }
 
 }  // extern "C"

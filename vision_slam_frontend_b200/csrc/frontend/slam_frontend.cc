@@ -205,7 +205,7 @@ Frontend::Frontend(const std::string& config_path)
       init_odom_translation_(0.f, 0.f, 0.f), init_odom_rotation_(1.f, 0.f, 0.f, 0.f),
       prev_odom_translation_(0.f, 0.f, 0.f), prev_odom_rotation_(1.f, 0.f, 0.f, 0.f),
       odom_translation_(0.f, 0.f, 0.f), odom_rotation_(1.f, 0.f, 0.f, 0.f),
-      odom_timestamp_(0), ctx_(nullptr), curr_frame_ID_(0) {
+      odom_timestamp_(0), ctx_(nullptr), curr_frame_ID_(0), first_output_ID_(0) {
   // The reference ignores its argument (src/slam_frontend.cc:188-190); a non-empty
   // path is honoured here through FrontendConfig::Load.
   if (!config_path.empty()) config_.Load(config_path);
@@ -218,7 +218,7 @@ Frontend::Frontend(const FrontendConfig& config)
       init_odom_translation_(0.f, 0.f, 0.f), init_odom_rotation_(1.f, 0.f, 0.f, 0.f),
       prev_odom_translation_(0.f, 0.f, 0.f), prev_odom_rotation_(1.f, 0.f, 0.f, 0.f),
       odom_translation_(0.f, 0.f, 0.f), odom_rotation_(1.f, 0.f, 0.f, 0.f),
-      odom_timestamp_(0), config_(config), ctx_(nullptr), curr_frame_ID_(0) {
+      odom_timestamp_(0), config_(config), ctx_(nullptr), curr_frame_ID_(0), first_output_ID_(0) {
   Check(vsf_create(config_.cuda_device, config_.max_features, config_.descriptor_bytes,
                    int(config_.frame_life_), &ctx_), "vsf_create");
 }
@@ -375,9 +375,31 @@ bool Frontend::ObserveImage(const cv::Mat& left_image, const cv::Mat& right_imag
   return ObserveFeatures(kl, dl, kr, dr, time);
 }
 
+void Frontend::StartShard(uint64_t halo_first, uint64_t first) {
+  if (!nodes_.empty() || !frame_list_.empty() || !pending_.empty() || halo_first > first)
+    throw std::runtime_error("Frontend::StartShard: call on a fresh Frontend, halo_first <= first");
+  curr_frame_ID_ = halo_first;
+  first_output_ID_ = first;
+}
+
+uint64_t Frontend::ShardHaloStart(uint64_t first, uint32_t frame_life) {
+  const uint64_t halo = uint64_t(frame_life) + 1;
+  return first > halo ? first - halo : 0;
+}
+
 bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, const cv::Mat& left_descriptors,
                                const std::vector<cv::KeyPoint>& right_keypoints,
-                               const cv::Mat& right_descriptors, double /*time*/) {
+                               const cv::Mat& right_descriptors, double time) {
+  if (!pending_.empty())
+    throw std::runtime_error("Frontend::ObserveFeatures: frames of SubmitFeatures are still pending (CollectFeatures)");
+  if (!SubmitFeatures(left_keypoints, left_descriptors, right_keypoints, right_descriptors, time)) return false;
+  CollectFeatures();
+  return true;
+}
+
+bool Frontend::SubmitFeatures(const std::vector<cv::KeyPoint>& left_keypoints, const cv::Mat& left_descriptors,
+                              const std::vector<cv::KeyPoint>& right_keypoints, const cv::Mat& right_descriptors,
+                              double /*time*/) {
   if (!OdomCheck()) return false;                                     // src/slam_frontend.cc:404
   const int nl = int(left_keypoints.size()), nr = int(right_keypoints.size());
   if (left_descriptors.rows != nl || right_descriptors.rows != nr)
@@ -386,9 +408,53 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
       (nr > 0 && right_descriptors.cols != config_.descriptor_bytes))
     throw std::runtime_error("Frontend::ObserveFeatures: descriptor width differs from FrontendConfig::descriptor_bytes");
   // host-side consistency checks come BEFORE the device call, which commits the frame
-  if (vsf_window_size(ctx_) != int(frame_list_.size()))
+  if (int(pending_.size()) >= MaxInFlight())
+    throw std::runtime_error("Frontend::SubmitFeatures: MaxInFlight() frames pending, call CollectFeatures first");
+  const int expect = int(std::min<size_t>(frame_list_.size() + pending_.size(), config_.frame_life_));
+  if (vsf_window_size(ctx_) != expect)
     throw std::runtime_error("Frontend::ObserveFeatures: device window out of sync with frame_list_");
   static_assert(sizeof(cv::KeyPoint) == sizeof(vsf_keypoint), "KeyPoint layout");
+  vsf_observe_params prm;
+  prm.fundamental = config_.fundamental;
+  prm.P_left = config_.projection_left;
+  prm.P_right = config_.projection_right;
+  prm.K_left = config_.camera_matrix_left;              // N1 on the device, in the triangulation launch
+  prm.dist_left = config_.distortion_coeffs_left;
+  prm.nn_match_ratio = double(config_.nn_match_ratio_);
+  // One fused device pass: stereo L->R kNN + ratio (:414-416), RemoveAmbigStereo (:417),
+  // window kNN (:424-434), R'->L' kNN + triangulation (:437), undistortion (:443), window push
+  // (:467-470).
+  Check(vsf_observe_submit(ctx_, curr_frame_ID_, reinterpret_cast<const vsf_keypoint*>(left_keypoints.data()),
+                           left_descriptors.data, nl, left_descriptors.step,
+                           reinterpret_cast<const vsf_keypoint*>(right_keypoints.data()), right_descriptors.data, nr,
+                           right_descriptors.step, &prm),
+        "vsf_observe_submit");
+  Pending pd;
+  pd.left_keypoints = left_keypoints;
+  pd.right_keypoints = right_keypoints;
+  pd.left_descriptors = left_descriptors;      // shared, like cv::Mat: the caller keeps the rows alive
+  pd.right_descriptors = right_descriptors;
+  pd.frame_ID = curr_frame_ID_;
+  pd.odom_translation = odom_translation_;
+  pd.odom_rotation = odom_rotation_;
+  pd.prev_odom_translation = prev_odom_translation_;
+  pd.prev_odom_rotation = prev_odom_rotation_;
+  pd.odom_timestamp = odom_timestamp_;
+  pending_.push_back(std::move(pd));
+  // :455-457 - what the next frame's odometry gate compares against does not depend on results
+  prev_odom_rotation_ = odom_rotation_;
+  prev_odom_translation_ = odom_translation_;
+  curr_frame_ID_++;
+  return true;
+}
+
+bool Frontend::CollectFeatures() {
+  if (pending_.empty()) return false;
+  Pending pd = std::move(pending_.front());
+  pending_.pop_front();
+  const std::vector<cv::KeyPoint>& left_keypoints = pd.left_keypoints;
+  const std::vector<cv::KeyPoint>& right_keypoints = pd.right_keypoints;
+  const int nl = int(left_keypoints.size());
   const int W = int(config_.frame_life_);
   // a window list has one entry per row of the PAST frame at most: size for the largest
   // resident frame as well as for this one
@@ -401,6 +467,7 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
   window_matches_.resize(size_t(W) * cap);
   tri_matches_.resize(cap);
   tri_X4_.resize(size_t(cap) * 4);
+  xy_undist_.resize(size_t(cap) * 2);
   vsf_observe_out out;
   std::memset(&out, 0, sizeof(out));
   out.kept_left = kept_left_.data();
@@ -410,16 +477,11 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
   out.window_matches = window_matches_.data();
   out.tri_matches = tri_matches_.data();
   out.tri_X4 = tri_X4_.data();
+  out.xy_undist = xy_undist_.data();
   out.cap = cap;
-  // One fused device pass: stereo L->R kNN + ratio (:414-416), RemoveAmbigStereo (:417),
-  // window kNN (:424-434), R'->L' kNN + triangulation (:437), window push (:467-470).
-  Check(vsf_observe_features(ctx_, curr_frame_ID_,
-                             reinterpret_cast<const vsf_keypoint*>(left_keypoints.data()), left_descriptors.data,
-                             nl, left_descriptors.step,
-                             reinterpret_cast<const vsf_keypoint*>(right_keypoints.data()), right_descriptors.data,
-                             nr, right_descriptors.step, config_.fundamental, config_.projection_left,
-                             config_.projection_right, double(config_.nn_match_ratio_), &out),
-        "vsf_observe_features");
+  uint64_t fid = 0;
+  Check(vsf_observe_collect(ctx_, &fid, &out), "vsf_observe_collect");
+  if (fid != pd.frame_ID) throw std::runtime_error("Frontend::CollectFeatures: frames collected out of order");
 
   // Host copies of the compacted frames (src/slam_frontend.cc:386-389, :396-397).
   const int M = out.n_kept;
@@ -429,11 +491,13 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
   for (int i = 0; i < M; ++i) {
     lk[i] = left_keypoints[kept_left_[i]];
     rk[i] = right_keypoints[kept_right_[i]];
-    std::memcpy(ld.ptr(i), left_descriptors.ptr(kept_left_[i]), size_t(wbytes));
-    std::memcpy(rd.ptr(i), right_descriptors.ptr(kept_right_[i]), size_t(wbytes));
+    std::memcpy(ld.ptr(i), pd.left_descriptors.ptr(kept_left_[i]), size_t(wbytes));
+    std::memcpy(rd.ptr(i), pd.right_descriptors.ptr(kept_right_[i]), size_t(wbytes));
   }
-  Frame curr_frame(lk, ld, curr_frame_ID_);
-  Frame right_temp_frame(rk, rd, curr_frame_ID_);
+  Frame curr_frame(lk, ld, pd.frame_ID);
+  Frame right_temp_frame(rk, rd, pd.frame_ID);
+  // halo frames of a shard (StartShard) only rebuild the window and the threshold
+  const bool output = pd.frame_ID >= first_output_ID_;
 
   // Window loop (:424-434): one VisionFactor per resident past frame, oldest first,
   // pushed unconditionally.
@@ -444,8 +508,8 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
     const vsf_dmatch* src = window_matches_.data() + size_t(j) * cap;
     std::vector<cv::DMatch> matches(static_cast<size_t>(window_counts_[j]));
     if (!matches.empty()) std::memcpy(static_cast<void*>(matches.data()), src, matches.size() * sizeof(vsf_dmatch));
-    vision_factors_.push_back(
-        FinishFeatureMatches(&matches, config_.best_percent_, &past_frame, &curr_frame, nullptr));
+    VisionFactor factor = FinishFeatureMatches(&matches, config_.best_percent_, &past_frame, &curr_frame, nullptr);
+    if (output) vision_factors_.push_back(std::move(factor));
   }
 
   // Calculate3DPoints (:117-173): GetFeatureMatches(right, left) with best_percent 1.0,
@@ -466,23 +530,25 @@ bool Frontend::ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, 
     }
   }
 
-  // :438-442.  The reference indexes points[i] by keypoint index although `points` is in
-  // sorted-match order and may be shorter (out-of-bounds read); NaN where it is missing.
+  // :438-443.  The reference indexes points[i] by keypoint index although `points` is in
+  // sorted-match order and may be shorter (out-of-bounds read); NaN where it is missing.  The
+  // pixel is the undistorted one (UndistortFeaturePoints, :443), computed on the device for the
+  // compacted left keypoints.
   std::vector<VisionFeature> features;
   features.reserve(M);
   const float nan = std::numeric_limits<float>::quiet_NaN();
   for (int i = 0; i < M; ++i) {
     const Eigen::Vector3f p = (size_t(i) < points.size()) ? points[i] : Eigen::Vector3f(nan, nan, nan);
-    features.push_back(VisionFeature(i, Eigen::Vector2f(curr_frame.keypoints_[i].pt.x, curr_frame.keypoints_[i].pt.y), p));
+    features.push_back(VisionFeature(i, Eigen::Vector2f(xy_undist_[2 * i], xy_undist_[2 * i + 1]), p));
   }
-  UndistortFeaturePoints(&features);                                                    // :443
-  const Eigen::Vector3f loc = init_odom_rotation_.inverse() * (odom_translation_ - init_odom_translation_);
-  const Eigen::Quaternionf angle = odom_rotation_ * init_odom_rotation_.inverse();     // :444-446
-  nodes_.push_back(SLAMNode(curr_frame_ID_, odom_timestamp_, RobotPose(loc, angle), features));
-  if (curr_frame_ID_ > 0) AddOdometryFactor();                                          // :452-454
-  prev_odom_rotation_ = odom_rotation_;
-  prev_odom_translation_ = odom_translation_;
-  curr_frame_ID_++;
+  const Eigen::Vector3f loc = init_odom_rotation_.inverse() * (pd.odom_translation - init_odom_translation_);
+  const Eigen::Quaternionf angle = pd.odom_rotation * init_odom_rotation_.inverse();   // :444-446
+  if (output) nodes_.push_back(SLAMNode(pd.frame_ID, pd.odom_timestamp, RobotPose(loc, angle), features));
+  if (output && pd.frame_ID > 0) {                                                      // :452-454
+    const Eigen::Vector3f translation = pd.prev_odom_rotation.inverse() * (pd.odom_translation - pd.prev_odom_translation);
+    const Eigen::Quaternionf rotation(pd.odom_rotation * pd.prev_odom_rotation.inverse());
+    odometry_factors_.push_back(OdometryFactor(pd.frame_ID - 1, pd.frame_ID, translation, rotation));
+  }
   if (frame_list_.size() >= config_.frame_life_) frame_list_.erase(frame_list_.begin());   // :467-469
   frame_list_.push_back(curr_frame);                                                    // :470
   return true;

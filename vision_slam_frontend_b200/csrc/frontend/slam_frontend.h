@@ -18,6 +18,7 @@
 #define VSF_SLAM_FRONTEND_H_
 
 #include <cstdint>
+#include <deque>
 #include <functional>
 #include <string>
 #include <unordered_map>
@@ -108,6 +109,27 @@ class Frontend {
   bool ObserveFeatures(const std::vector<cv::KeyPoint>& left_keypoints, const cv::Mat& left_descriptors,
                        const std::vector<cv::KeyPoint>& right_keypoints, const cv::Mat& right_descriptors,
                        double time);
+  // Pipelined form for frame streams (the bag loop of src/slam_frontend_main.cc:236-328):
+  // SubmitFeatures gates on the odometry exactly like ObserveFeatures, snapshots the odometry
+  // state, enqueues the frame on the device (vsf_observe_submit) and returns; CollectFeatures
+  // finishes the OLDEST submitted frame on the host (sort + cut, FeatureMatch book-keeping, node
+  // assembly) in submission order.  Up to MaxInFlight() frames may be pending; results are
+  // identical to calling ObserveFeatures frame by frame.
+  bool SubmitFeatures(const std::vector<cv::KeyPoint>& left_keypoints, const cv::Mat& left_descriptors,
+                      const std::vector<cv::KeyPoint>& right_keypoints, const cv::Mat& right_descriptors,
+                      double time);
+  bool CollectFeatures();                 // false when nothing is pending
+  int InFlight() const { return int(pending_.size()); }
+  static int MaxInFlight() { return VSF_OBSERVE_DEPTH; }
+  // Sharded sequences: this instance owns the poses from `first` on of a longer
+  // sequence.  Frames are numbered from halo_first; frames below `first` are the halo - they
+  // rebuild the sliding window and the adaptive stereo threshold and produce no nodes or factors.
+  // halo_first = ShardHaloStart(first, frame_life_) reproduces the unsharded state exactly:
+  // frame_life_ frames for the window (src/slam_frontend.cc:424-434) plus one whose only purpose
+  // is its `mean + 2` threshold (:392-394).  The caller feeds ObserveOdometry with the sequence's
+  // FIRST odometry message before the halo's (init_odom_* are relative to it, :252-256).
+  void StartShard(uint64_t halo_first, uint64_t first);
+  static uint64_t ShardHaloStart(uint64_t first, uint32_t frame_life);
   void ObserveOdometry(const Eigen::Vector3f& translation, const Eigen::Quaternionf& rotation,
                        double timestamp);
   void GetSLAMProblem(slam_types::SLAMProblem* problem) const;
@@ -148,12 +170,24 @@ class Frontend {
   FrontendConfig config_;
   vsf_ctx* ctx_;             // replaces cv::Ptr<cv::BFMatcher> matcher_
   uint64_t curr_frame_ID_;
+  uint64_t first_output_ID_;   // StartShard: frames below this id produce no nodes / factors
   std::vector<Frame> frame_list_;
   FeatureExtractor extractor_;
   std::vector<slam_types::VisionFactor> vision_factors_;
   std::vector<slam_types::SLAMNode> nodes_;
   std::vector<slam_types::OdometryFactor> odometry_factors_;
-  // scratch for vsf_observe_features
+  // a submitted frame waiting for its device results
+  struct Pending {
+    std::vector<cv::KeyPoint> left_keypoints, right_keypoints;
+    cv::Mat left_descriptors, right_descriptors;
+    uint64_t frame_ID;
+    Eigen::Vector3f odom_translation, prev_odom_translation;
+    Eigen::Quaternionf odom_rotation, prev_odom_rotation;
+    double odom_timestamp;
+  };
+  std::deque<Pending> pending_;
+  // scratch for vsf_observe_collect
+  std::vector<float> xy_undist_;
   std::vector<int32_t> kept_left_, kept_right_;
   std::vector<uint64_t> frame_ids_;
   std::vector<int> window_counts_;

@@ -23,7 +23,9 @@ struct StereoArgs {
   // compaction outputs
   int* kept_left;              // [M] indices into the raw left frame
   int* kept_right;
-  int* n_kept;                 // M
+  int* n_kept;                 // M (device: later kernels read it as a row count)
+  int* n_kept_host;            // optional mirrors in mapped host memory (pipelined frame path)
+  float* thresh_next_host;
   const uint32_t* desc_left;   // raw descriptors [n][words]
   const uint32_t* desc_right;
   uint32_t* desc_left_c;       // compacted descriptors [M][words] (a window ring slot)

@@ -78,6 +78,7 @@ stereo_residual_kernel(const __grid_constant__ StereoArgs a) {
     }
     if (lane == 0) {
       *a.n_kept = int(run);
+      if (a.n_kept_host) *a.n_kept_host = int(run);
       *a.ticket = 0u;
     }
   }
@@ -115,6 +116,7 @@ __device__ void stereo_threshold_cta(const StereoArgs& a, float* s_buf) {
     float next = __fadd_rn(__fdiv_rn(avg, float(n)), 2.0f);
     if (n == 0 && a.hold_on_empty) next = *a.thresh_cur;
     *a.thresh_next = next;
+    if (a.thresh_next_host) *a.thresh_next_host = next;
   }
 }
 

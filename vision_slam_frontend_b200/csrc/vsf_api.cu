@@ -108,7 +108,8 @@ struct vsf_ctx {
   float* d_resid = nullptr;
   unsigned *d_chunk_keep = nullptr, *d_chunk_off = nullptr, *d_ticket = nullptr;
   int opt_residual_order = 0, opt_hold_on_empty = 0;   // vsf_set_option
-  int *d_kept_left = nullptr, *d_kept_right = nullptr, *d_n_kept = nullptr;
+  int *d_kept_left = nullptr, *d_kept_right = nullptr;
+  int* d_slot_rows = nullptr;   // [ring_slots] device-side row count of every ring slot (compacted frames)
   float* d_thresh = nullptr;  // [2], ping-pong
   int thresh_cur = 0;
   float4* d_X4 = nullptr;
@@ -133,7 +134,8 @@ struct vsf_ctx {
   vsf_feature_match* h_fm = nullptr;
   uint32_t* h_keys = nullptr;   // plain host scratch for the host sort (allocated on first use)
   // sliding window (frame_list_) state
-  std::vector<int> slot_count;
+  std::vector<int> slot_count;      // rows of the frame in a ring slot (an upper bound while slot_dev)
+  std::vector<char> slot_dev;       // the exact count is only on the device yet (d_slot_rows)
   std::vector<uint64_t> slot_frame;
   std::deque<int> live;   // slot indices, oldest first
   std::deque<int> free_slots;   // FIFO: a slot evicted at frame t is reused for frame t+2, so the
@@ -198,6 +200,28 @@ struct vsf_ctx {
   bool flights_ready = false;
   int flight_head = 0, flight_count = 0;   // FIFO: oldest = flights[flight_head]
 
+  // pipelined full-frame path (vsf_observe_submit / vsf_observe_collect): per frame in flight one
+  // upload block and one block of mapped host memory the kernels store their results into
+  struct ObsFlight {
+    cudaEvent_t ev_up = nullptr, ev_done = nullptr;
+    uint8_t *h_in = nullptr, *d_in = nullptr;
+    uint8_t* h_out = nullptr;           // mapped; the pointers below carve it up (h_* host view, dm_* device view)
+    int *h_kept_left = nullptr, *dm_kept_left = nullptr, *h_kept_right = nullptr, *dm_kept_right = nullptr;
+    vsf_dmatch *h_lists = nullptr, *dm_lists = nullptr;   // [window + 1][rows_pad]
+    int *h_counts = nullptr, *dm_counts = nullptr;        // [kMaxProblems] list lengths, [kMaxProblems] = M
+    float *h_scalar = nullptr, *dm_scalar = nullptr;      // threshold after this frame
+    float4 *h_X4 = nullptr, *dm_X4 = nullptr;
+    float2 *h_xyu = nullptr, *dm_xyu = nullptr;
+    int nf = 0, nl = 0, slot = 0, undistort = 0;
+    uint64_t frame_id = 0;
+    uint64_t fids[kMaxProblems];
+    int bounds[kMaxProblems];
+  };
+  ObsFlight obs[VSF_OBSERVE_DEPTH];
+  bool obs_ready = false;
+  int obs_head = 0, obs_count = 0;
+  cudaStream_t obs_up_stream = nullptr;
+
   vsf_dmatch* match_base = nullptr;   // d_matches, or the device buffer of a pipelined submission
   uint8_t* slot_ptr(int s) const { return d_ring + size_t(s) * rows_pad * row_bytes; }
   vsf_dmatch* region_ptr(int r) const { return match_base + size_t(r) * rows_pad; }
@@ -231,6 +255,7 @@ static void commit_staging(vsf_ctx* c, uint64_t frame_id, int count) {
     c->live.pop_front();
   }
   c->slot_count[c->staging_slot] = count;
+  c->slot_dev[c->staging_slot] = 0;
   c->slot_frame[c->staging_slot] = frame_id;
   c->live.push_back(c->staging_slot);
   c->staging_slot = c->free_slots.front();
@@ -510,7 +535,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
   void* dev[] = {c->d_ring, c->d_raw_left, c->d_raw_right, c->d_right_c, c->d_xy_left, c->d_xy_right,
                  c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
-                 c->d_chunk_keep, c->d_chunk_off, c->d_ticket, c->d_kept_left, c->d_kept_right, c->d_n_kept, c->d_thresh, c->d_X4,
+                 c->d_chunk_keep, c->d_chunk_off, c->d_ticket, c->d_kept_left, c->d_kept_right, c->d_slot_rows, c->d_thresh, c->d_X4,
                  c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1], c->d_tc_trace,
                  c->d_ktrace};
   for (void* p : dev)
@@ -533,6 +558,15 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
       if (e) cudaEventDestroy(e);
     std::free(f.keys);
   }
+  if (c->obs_up_stream) cudaStreamSynchronize(c->obs_up_stream);
+  for (vsf_ctx::ObsFlight& f : c->obs) {
+    if (f.h_in) cudaFreeHost(f.h_in);
+    if (f.h_out) cudaFreeHost(f.h_out);
+    if (f.d_in) cudaFree(f.d_in);
+    for (cudaEvent_t e : {f.ev_up, f.ev_done})
+      if (e) cudaEventDestroy(e);
+  }
+  if (c->obs_up_stream) cudaStreamDestroy(c->obs_up_stream);
   if (c->ev_main) cudaEventDestroy(c->ev_main);
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
   if (c->down_stream) cudaStreamDestroy(c->down_stream);
@@ -629,7 +663,8 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   cudaMemset(c->d_ticket, 0, sizeof(unsigned));
   VSF_ALLOC(c, c->d_kept_left, N * sizeof(int));
   VSF_ALLOC(c, c->d_kept_right, N * sizeof(int));
-  VSF_ALLOC(c, c->d_n_kept, sizeof(int));
+  VSF_ALLOC(c, c->d_slot_rows, (window + 2) * sizeof(int));
+  cudaMemset(c->d_slot_rows, 0, (window + 2) * sizeof(int));
   VSF_ALLOC(c, c->d_thresh, 2 * sizeof(float));
   VSF_ALLOC(c, c->d_X4, N * sizeof(float4));
   VSF_ALLOC(c, c->d_tri_io, N * 8 * sizeof(float));
@@ -674,6 +709,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
     if (v >= 0 && v <= 3 && (v < 3 || c->words == 8)) c->engine = v;
   }
   c->slot_count.assign(c->ring_slots, 0);
+  c->slot_dev.assign(c->ring_slots, 0);
   c->slot_frame.assign(c->ring_slots, 0);
   c->slot_last_chain.assign(c->ring_slots, nullptr);
   reset_ring(c);
@@ -701,6 +737,7 @@ extern "C" int vsf_set_stream(vsf_ctx* c, void* cuda_stream) {
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->up_stream));
   if (c->down_stream) VSF_CUDA(c, cudaStreamSynchronize(c->down_stream));
+  if (c->obs_up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->obs_up_stream));
   c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
   return VSF_OK;
 }
@@ -868,7 +905,8 @@ static int window_launch(vsf_ctx* c, const uint8_t* desc, int n, size_t stride, 
   std::vector<ProblemSpec> specs;
   int j = 0;
   for (int s : c->live)
-    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, c->slot_ptr(c->staging_slot), n, nullptr, j++});
+    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], c->slot_dev[s] ? c->d_slot_rows + s : nullptr,
+                                c->slot_ptr(c->staging_slot), n, nullptr, j++});
   return run_knn(c, specs, ratio, mirror);
 }
 
@@ -1197,7 +1235,8 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   std::vector<ProblemSpec> specs;
   for (int j = 0; j < nf; ++j) {
     const int s = c->live[j];
-    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, c->slot_ptr(S), n, nullptr, j});
+    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], c->slot_dev[s] ? c->d_slot_rows + s : nullptr,
+                                c->slot_ptr(S), n, nullptr, j});
     if (pre_expand) {
       specs.back().t_exp = f.d_train_exp;
       specs.back().t_exp_int8 = exp_int8;
@@ -1324,7 +1363,7 @@ static void fill_stereo_args(vsf_ctx* c, StereoArgs& a, const float* F) {
   a.hold_on_empty = c->opt_hold_on_empty;
   a.kept_left = c->d_kept_left;
   a.kept_right = c->d_kept_right;
-  a.n_kept = c->d_n_kept;
+  a.n_kept = c->d_slot_rows + c->staging_slot;
   a.desc_left = reinterpret_cast<const uint32_t*>(c->d_raw_left);
   a.desc_right = reinterpret_cast<const uint32_t*>(c->d_raw_right);
   a.desc_left_c = reinterpret_cast<uint32_t*>(c->slot_ptr(c->staging_slot));
@@ -1334,10 +1373,25 @@ static void fill_stereo_args(vsf_ctx* c, StereoArgs& a, const float* F) {
   a.words = c->words;
 }
 
-// upload both frames, L->R kNN + ratio, epipolar filter + compaction (all async)
-// The ctx's threshold ping-pong (thresh_cur) is NOT advanced here: the caller flips it once
-// every stage of its call has been launched successfully, so a failed call leaves the adaptive
-// threshold as it was.  with_threshold = false: the caller places the threshold sum itself.
+// L->R kNN + ratio, epipolar filter + compaction on frames that are already on the device (all
+// async).  The ctx's threshold ping-pong (thresh_cur) is NOT advanced here: the caller flips it
+// once every stage of its call has been launched successfully, so a failed call leaves the
+// adaptive threshold as it was.  with_threshold = false: the caller places the threshold sum.
+static int stereo_launch(vsf_ctx* c, const uint8_t* d_dl, int nl, const uint8_t* d_dr, int nr, const float2* d_xyl,
+                         const float2* d_xyr, const float* F, double ratio, bool with_threshold, StereoArgs* a) {
+  std::vector<ProblemSpec> specs(1);
+  specs[0] = ProblemSpec{d_dl, nl, nullptr, d_dr, nr, nullptr, c->window + 1};
+  int rc;
+  if ((rc = run_knn(c, specs, ratio))) return rc;
+  fill_stereo_args(c, *a, F);
+  a->desc_left = reinterpret_cast<const uint32_t*>(d_dl);
+  a->desc_right = reinterpret_cast<const uint32_t*>(d_dr);
+  a->xy_left = d_xyl;
+  a->xy_right = d_xyr;
+  return VSF_OK;
+}
+
+// upload both frames, then stereo_launch + the filter kernels
 static int stereo_stage(vsf_ctx* c, const vsf_keypoint* kpl, const uint8_t* dl, int nl, size_t sl,
                         const vsf_keypoint* kpr, const uint8_t* dr, int nr, size_t sr, const float* F,
                         double ratio, bool with_threshold, StereoArgs* args_out = nullptr) {
@@ -1352,11 +1406,10 @@ static int stereo_stage(vsf_ctx* c, const vsf_keypoint* kpl, const uint8_t* dl, 
   if ((rc = upload_desc(c, 1, dr, nr, sr, c->d_raw_right))) return rc;
   if ((rc = upload_xy(c, 0, kpl, nl, c->d_xy_left))) return rc;
   if ((rc = upload_xy(c, 1, kpr, nr, c->d_xy_right))) return rc;
-  std::vector<ProblemSpec> specs(1);
-  specs[0] = ProblemSpec{c->d_raw_left, nl, nullptr, c->d_raw_right, nr, nullptr, c->window + 1};
-  if ((rc = run_knn(c, specs, ratio))) return rc;
   StereoArgs a;
-  fill_stereo_args(c, a, F);
+  if ((rc = stereo_launch(c, c->d_raw_left, nl, c->d_raw_right, nr, c->d_xy_left, c->d_xy_right, F, ratio,
+                          with_threshold, &a)))
+    return rc;
   VSF_CUDA(c, launch_stereo_filter(a, std::max(nl, 1), with_threshold, c->stream));
   if (args_out) *args_out = a;
   return VSF_OK;
@@ -1372,7 +1425,7 @@ extern "C" int vsf_stereo_filter(vsf_ctx* c, const vsf_keypoint* kpl, const uint
   if (rc) return rc;
   c->thresh_cur ^= 1;
   const int region = c->window + 1;
-  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_slot_rows + c->staging_slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_match_count + region, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   const int M = c->h_counts[0], ns = c->h_counts[1];
@@ -1472,13 +1525,199 @@ extern "C" int vsf_undistort_points(vsf_ctx* c, const float* K, const float* dis
   return VSF_OK;
 }
 
+static int obs_init(vsf_ctx* c) {
+  if (c->obs_ready) return VSF_OK;
+  cudaSetDevice(c->device);
+  const size_t N = size_t(c->rows_pad);
+  const size_t in_bytes = 2 * N * c->row_bytes + 2 * N * sizeof(float2) + 512;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_kl = 0, o_kr = up(o_kl + N * 4), o_li = up(o_kr + N * 4);
+  const size_t o_ct = up(o_li + size_t(c->window + 1) * N * sizeof(vsf_dmatch));
+  const size_t o_sc = up(o_ct + (kMaxProblems + 8) * sizeof(int)), o_x4 = up(o_sc + 64);
+  const size_t o_xu = up(o_x4 + N * sizeof(float4)), out_bytes = up(o_xu + N * sizeof(float2));
+  VSF_CUDA(c, cudaStreamCreateWithFlags(&c->obs_up_stream, cudaStreamNonBlocking));
+  for (vsf_ctx::ObsFlight& f : c->obs) {
+    VSF_CUDA(c, cudaEventCreateWithFlags(&f.ev_up, cudaEventDisableTiming));
+    VSF_CUDA(c, cudaEventCreateWithFlags(&f.ev_done, cudaEventDisableTiming));
+    VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_in), in_bytes));
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_in), in_bytes));
+    VSF_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&f.h_out), out_bytes, cudaHostAllocMapped));
+    std::memset(f.h_out, 0, out_bytes);
+    uint8_t* dm = nullptr;
+    VSF_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&dm), f.h_out, 0));
+    f.h_kept_left = reinterpret_cast<int*>(f.h_out + o_kl);      f.dm_kept_left = reinterpret_cast<int*>(dm + o_kl);
+    f.h_kept_right = reinterpret_cast<int*>(f.h_out + o_kr);     f.dm_kept_right = reinterpret_cast<int*>(dm + o_kr);
+    f.h_lists = reinterpret_cast<vsf_dmatch*>(f.h_out + o_li);   f.dm_lists = reinterpret_cast<vsf_dmatch*>(dm + o_li);
+    f.h_counts = reinterpret_cast<int*>(f.h_out + o_ct);         f.dm_counts = reinterpret_cast<int*>(dm + o_ct);
+    f.h_scalar = reinterpret_cast<float*>(f.h_out + o_sc);       f.dm_scalar = reinterpret_cast<float*>(dm + o_sc);
+    f.h_X4 = reinterpret_cast<float4*>(f.h_out + o_x4);          f.dm_X4 = reinterpret_cast<float4*>(dm + o_x4);
+    f.h_xyu = reinterpret_cast<float2*>(f.h_out + o_xu);         f.dm_xyu = reinterpret_cast<float2*>(dm + o_xu);
+  }
+  c->obs_ready = true;
+  return VSF_OK;
+}
+
+extern "C" int vsf_observe_in_flight(const vsf_ctx* c) { return c ? c->obs_count : 0; }
+
+extern "C" int vsf_observe_submit(vsf_ctx* c, uint64_t frame_id, const vsf_keypoint* kpl, const uint8_t* dl, int nl,
+                                  size_t sl, const vsf_keypoint* kpr, const uint8_t* dr, int nr, size_t sr,
+                                  const vsf_observe_params* p) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!p || !p->fundamental || !p->P_left || !p->P_right) return fail(c, VSF_ERR_BAD_ARG, "null observe parameters");
+  if ((p->K_left == nullptr) != (p->dist_left == nullptr)) return fail(c, VSF_ERR_BAD_ARG, "K_left and dist_left go together");
+  if (nl < 0 || nr < 0 || (nl > 0 && (!kpl || !dl)) || (nr > 0 && (!kpr || !dr)))
+    return fail(c, VSF_ERR_BAD_ARG, "bad stereo arguments");
+  if ((nl > 0 && sl < size_t(c->desc_bytes)) || (nr > 0 && sr < size_t(c->desc_bytes)))
+    return fail(c, VSF_ERR_BAD_ARG, "row stride smaller than desc_bytes");
+  if (nl > c->max_features || nr > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
+  if (c->obs_count >= VSF_OBSERVE_DEPTH)
+    return fail(c, VSF_ERR_STATE, "VSF_OBSERVE_DEPTH frames already in flight: call vsf_observe_collect first");
+  int rc = obs_init(c);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  vsf_ctx::ObsFlight& f = c->obs[(c->obs_head + c->obs_count) % VSF_OBSERVE_DEPTH];
+  const int rb = c->row_bytes;
+  // ---- one upload: [left rows | right rows | left pixels | right pixels], packed into the
+  // flight's pinned block (it was last read by the frame collected VSF_OBSERVE_DEPTH submits ago)
+  auto up = [](size_t v) { return (v + 127) / 128 * 128; };
+  const size_t o_dl = 0, o_dr = up(size_t(nl) * rb), o_xl = up(o_dr + size_t(nr) * rb);
+  const size_t o_xr = up(o_xl + size_t(nl) * sizeof(float2)), total = o_xr + size_t(nr) * sizeof(float2);
+  auto pack = [&](uint8_t* dst, const uint8_t* src, int n, size_t stride) {
+    if (n == 0) return;
+    if (stride == size_t(rb) && c->desc_bytes == rb) {
+      std::memcpy(dst, src, size_t(n) * rb);
+    } else {
+      for (int i = 0; i < n; ++i) {
+        std::memcpy(dst + size_t(i) * rb, src + size_t(i) * stride, c->desc_bytes);
+        if (c->desc_bytes < rb) std::memset(dst + size_t(i) * rb + c->desc_bytes, 0, rb - c->desc_bytes);
+      }
+    }
+  };
+  pack(f.h_in + o_dl, dl, nl, sl);
+  pack(f.h_in + o_dr, dr, nr, sr);
+  float2* hxl = reinterpret_cast<float2*>(f.h_in + o_xl);
+  float2* hxr = reinterpret_cast<float2*>(f.h_in + o_xr);
+  for (int i = 0; i < nl; ++i) hxl[i] = make_float2(kpl[i].x, kpl[i].y);
+  for (int i = 0; i < nr; ++i) hxr[i] = make_float2(kpr[i].x, kpr[i].y);
+  if (total > 0) VSF_CUDA(c, cudaMemcpyAsync(f.d_in, f.h_in, total, cudaMemcpyHostToDevice, c->obs_up_stream));
+  VSF_CUDA(c, cudaEventRecord(f.ev_up, c->obs_up_stream));
+  VSF_CUDA(c, cudaStreamWaitEvent(c->stream, f.ev_up, 0));
+  // ---- main stream.  a5: stereo L->R + filter; the compacted left frame lands in the ring's
+  // staging slot, its row count in d_slot_rows[slot]
+  const int nf = int(c->live.size());
+  f.nf = nf;
+  f.nl = nl;
+  f.slot = c->staging_slot;
+  f.frame_id = frame_id;
+  f.undistort = p->K_left != nullptr;
+  StereoArgs sa;
+  if ((rc = stereo_launch(c, f.d_in + o_dl, nl, f.d_in + o_dr, nr, reinterpret_cast<const float2*>(f.d_in + o_xl),
+                          reinterpret_cast<const float2*>(f.d_in + o_xr), p->fundamental, p->nn_match_ratio, false, &sa)))
+    return rc;
+  sa.kept_left = f.dm_kept_left;      // straight into mapped host memory
+  sa.kept_right = f.dm_kept_right;
+  sa.n_kept_host = f.dm_counts + kMaxProblems;
+  sa.thresh_next_host = f.dm_scalar;
+  VSF_CUDA(c, launch_stereo_filter(sa, std::max(nl, 1), false, c->stream));
+  // a4 + a6 matching in one launch sequence: every resident past frame vs the compacted left
+  // frame, and compacted right (query) vs compacted left (train); lists and counts are mirrored
+  // into the flight's mapped memory by the compaction
+  int* d_m = c->d_slot_rows + c->staging_slot;
+  std::vector<ProblemSpec> specs;
+  uint8_t* cur = c->slot_ptr(c->staging_slot);
+  for (int j = 0; j < nf; ++j) {
+    const int s = c->live[j];
+    f.fids[j] = c->slot_frame[s];
+    f.bounds[j] = c->slot_count[s];
+    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], c->slot_dev[s] ? c->d_slot_rows + s : nullptr, cur, nl, d_m, j});
+  }
+  const int tri_region = c->window;
+  specs.push_back(ProblemSpec{c->d_right_c, nl, d_m, cur, nl, d_m, tri_region});
+  c->mir_dm = f.dm_lists;
+  c->mir_dcounts = f.dm_counts;
+  c->mir_hcounts = f.h_counts;
+  rc = run_knn(c, specs, p->nn_match_ratio, true);
+  c->mir_dm = c->dm_matches;
+  c->mir_dcounts = c->dm_region_counts;
+  c->mir_hcounts = c->h_region_counts;
+  if (rc) return rc;
+  // triangulation; thread i also undistorts compacted left keypoint i (N1) and the extra CTA
+  // carries the stereo stage's sequential threshold sum, which nothing in this frame waits for
+  TriExtras ex;
+  std::memset(&ex, 0, sizeof(ex));
+  ex.do_threshold = 1;
+  ex.stereo = sa;
+  if (f.undistort) {
+    ex.do_undistort = 1;
+    ex.und = make_undistort_args(p->K_left, p->dist_left);
+    ex.n_kept = d_m;
+    ex.xy_undist = f.dm_xyu;
+  }
+  VSF_CUDA(c, launch_triangulate_matches(p->P_left, p->P_right, c->region_ptr(tri_region), c->d_match_count + tri_region, nl,
+                                         c->d_xy_left_c, c->d_xy_right_c, f.dm_X4, &ex, c->stream));
+  VSF_CUDA(c, cudaEventRecord(f.ev_done, c->stream));
+  // every stage is enqueued: advance the adaptive threshold and the window together.  The
+  // frame's row count M is only on the device yet; the host keeps the bound nl until collect.
+  c->thresh_cur ^= 1;
+  const int slot = c->staging_slot;
+  commit_staging(c, frame_id, nl);
+  c->slot_dev[slot] = 1;
+  ++c->obs_count;
+  return VSF_OK;
+}
+
+extern "C" int vsf_observe_collect(vsf_ctx* c, uint64_t* frame_id, vsf_observe_out* out) {
+  if (!c) return VSF_ERR_BAD_ARG;
+  if (!out) return fail(c, VSF_ERR_BAD_ARG, "null output");
+  if (c->obs_count == 0) return fail(c, VSF_ERR_STATE, "no submitted frame to collect");
+  cudaSetDevice(c->device);
+  vsf_ctx::ObsFlight& f = c->obs[c->obs_head];
+  const cudaError_t werr = cudaEventSynchronize(f.ev_done);
+  c->obs_head = (c->obs_head + 1) % VSF_OBSERVE_DEPTH;   // the flight is consumed whatever happens next
+  --c->obs_count;
+  VSF_CUDA(c, werr);
+  const int M = f.h_counts[kMaxProblems];
+  const int tri_region = c->window;
+  const int n_tri = f.h_counts[tri_region];
+  // the exact row count replaces the bound while the frame is still resident
+  if (c->slot_frame[f.slot] == f.frame_id && c->slot_dev[f.slot]) {
+    for (int s : c->live)
+      if (s == f.slot) {
+        c->slot_count[s] = M;
+        c->slot_dev[s] = 0;
+      }
+  }
+  if (frame_id) *frame_id = f.frame_id;
+  int need = std::max(M, n_tri);
+  for (int k = 0; k < f.nf; ++k) need = std::max(need, f.h_counts[k]);
+  if (out->cap < need) return fail(c, VSF_ERR_CAPACITY, "vsf_observe_out.cap is smaller than one of this frame's lists");
+  out->n_kept = M;
+  out->stereo_threshold_next = f.h_scalar[0];
+  out->n_frames = f.nf;
+  out->n_tri = n_tri;
+  if (M > 0 && out->kept_left) std::memcpy(out->kept_left, f.h_kept_left, size_t(M) * sizeof(int));
+  if (M > 0 && out->kept_right) std::memcpy(out->kept_right, f.h_kept_right, size_t(M) * sizeof(int));
+  for (int k = 0; k < f.nf; ++k) {
+    if (out->frame_ids) out->frame_ids[k] = f.fids[k];
+    if (out->window_counts) out->window_counts[k] = f.h_counts[k];
+    if (out->window_matches && f.h_counts[k] > 0)
+      std::memcpy(out->window_matches + size_t(k) * out->cap, f.h_lists + size_t(k) * c->rows_pad,
+                  size_t(f.h_counts[k]) * sizeof(vsf_dmatch));
+  }
+  if (n_tri > 0 && out->tri_matches)
+    std::memcpy(out->tri_matches, f.h_lists + size_t(tri_region) * c->rows_pad, size_t(n_tri) * sizeof(vsf_dmatch));
+  if (n_tri > 0 && out->tri_X4) std::memcpy(out->tri_X4, f.h_X4, size_t(n_tri) * sizeof(float4));
+  if (M > 0 && out->xy_undist && f.undistort) std::memcpy(out->xy_undist, f.h_xyu, size_t(M) * sizeof(float2));
+  return VSF_OK;
+}
+
 extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_keypoint* kpl, const uint8_t* dl,
                                     int nl, size_t sl, const vsf_keypoint* kpr, const uint8_t* dr, int nr,
                                     size_t sr, const float* F, const float* P_left, const float* P_right,
                                     double ratio, vsf_observe_out* out) {
   if (!c) return VSF_ERR_BAD_ARG;
-  if (!out || !P_left || !P_right) return fail(c, VSF_ERR_BAD_ARG, "null argument");
-  const int nf = int(c->live.size());
+  if (!out || !P_left || !P_right || !F) return fail(c, VSF_ERR_BAD_ARG, "null argument");
+  if (c->obs_count != 0) return fail(c, VSF_ERR_STATE, "frames of vsf_observe_submit are still in flight");
   // a window list holds at most one entry per row of the PAST frame, the stereo / triangulation
   // lists at most one per row of this frame: refuse before anything is launched, so that a
   // failed call leaves the window and the adaptive threshold untouched
@@ -1486,64 +1725,16 @@ extern "C" int vsf_observe_features(vsf_ctx* c, uint64_t frame_id, const vsf_key
   for (int s : c->live) need = std::max(need, c->slot_count[s]);
   if (out->cap < need)
     return fail(c, VSF_ERR_CAPACITY, "vsf_observe_out.cap must be >= n_left and >= the row count of every resident frame");
-  // a5: stereo L->R + filter; the compacted left frame lands in the ring's staging slot
-  StereoArgs sa;
-  int rc = stereo_stage(c, kpl, dl, nl, sl, kpr, dr, nr, sr, F, ratio, false, &sa);
+  vsf_observe_params p;
+  p.fundamental = F;
+  p.P_left = P_left;
+  p.P_right = P_right;
+  p.K_left = nullptr;
+  p.dist_left = nullptr;
+  p.nn_match_ratio = ratio;
+  int rc = vsf_observe_submit(c, frame_id, kpl, dl, nl, sl, kpr, dr, nr, sr, &p);
   if (rc) return rc;
-  // a4 + a6 matching in one launch: every resident past frame vs the compacted left
-  // frame, and compacted right (query) vs compacted left (train)
-  std::vector<ProblemSpec> specs;
-  int j = 0;
-  uint8_t* cur = c->slot_ptr(c->staging_slot);
-  for (int s : c->live)
-    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], nullptr, cur, nl, c->d_n_kept, j++});
-  const int tri_region = c->window;
-  specs.push_back(ProblemSpec{c->d_right_c, nl, c->d_n_kept, cur, nl, c->d_n_kept, tri_region});
-  if ((rc = run_knn(c, specs, ratio, true))) return rc;
-  // triangulation; its extra CTA carries the stereo stage's sequential threshold sum, which
-  // nothing on this frame's critical path waits for
-  TriExtras ex;
-  std::memset(&ex, 0, sizeof(ex));
-  ex.do_threshold = 1;
-  ex.stereo = sa;
-  VSF_CUDA(c, launch_triangulate_matches(P_left, P_right, c->region_ptr(tri_region),
-                                         c->d_match_count + tri_region, nl, c->d_xy_left_c,
-                                         c->d_xy_right_c, c->d_X4, &ex, c->stream));
-  // match lists and their counts arrive in mapped host memory with the kernels; the rest is
-  // sized by two scalars, so: scalars, sync, exactly-sized copies, sync
-  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts + kMaxProblems, c->d_n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VSF_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_thresh + (c->thresh_cur ^ 1), sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (int k = 0; k <= c->window; ++k) c->h_counts[k] = c->h_region_counts[k];
-  const int M = c->h_counts[kMaxProblems];
-  const int n_tri = c->h_counts[tri_region];
-  if (M > 0) {
-    VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[0], c->d_kept_left, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    VSF_CUDA(c, cudaMemcpyAsync(c->h_kept[1], c->d_kept_right, size_t(M) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  }
-  if (n_tri > 0)
-    VSF_CUDA(c, cudaMemcpyAsync(c->h_X4, c->d_X4, size_t(n_tri) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  if (M > 0 || n_tri > 0) VSF_CUDA(c, cudaStreamSynchronize(c->stream));
-  out->n_kept = M;
-  out->stereo_threshold_next = c->h_scalar[0];
-  out->n_frames = nf;
-  out->n_tri = n_tri;
-  if (M > 0 && out->kept_left) std::memcpy(out->kept_left, c->h_kept[0], size_t(M) * sizeof(int));
-  if (M > 0 && out->kept_right) std::memcpy(out->kept_right, c->h_kept[1], size_t(M) * sizeof(int));
-  for (int k = 0; k < nf; ++k) {
-    if (out->frame_ids) out->frame_ids[k] = c->slot_frame[c->live[k]];
-    if (out->window_counts) out->window_counts[k] = c->h_counts[k];
-    if (out->window_matches && c->h_counts[k] > 0)
-      std::memcpy(out->window_matches + size_t(k) * out->cap, c->h_matches + size_t(k) * c->rows_pad,
-                  size_t(c->h_counts[k]) * sizeof(vsf_dmatch));
-  }
-  if (n_tri > 0 && out->tri_matches)
-    std::memcpy(out->tri_matches, c->h_matches + size_t(tri_region) * c->rows_pad, size_t(n_tri) * sizeof(vsf_dmatch));
-  if (n_tri > 0 && out->tri_X4) std::memcpy(out->tri_X4, c->h_X4, size_t(n_tri) * sizeof(float4));
-  // every stage succeeded: advance the adaptive threshold and the window together
-  c->thresh_cur ^= 1;
-  commit_staging(c, frame_id, M);
-  return VSF_OK;
+  return vsf_observe_collect(c, nullptr, out);
 }
 
 // ----------------------------------------------------------------- device-resident entry points
@@ -1634,6 +1825,18 @@ extern "C" int vsf_fetch_window(vsf_ctx* c, int n_frames, int* counts, vsf_dmatc
   }
   return VSF_OK;
 }
+
+extern "C" int vsf_device_match_lists(vsf_ctx* c, const vsf_dmatch** d_lists, const int** d_counts, int* stride,
+                                      int* regions) {
+  if (!c || !d_lists || !d_counts || !stride || !regions) return VSF_ERR_BAD_ARG;
+  *d_lists = c->d_matches;
+  *d_counts = c->d_match_count;
+  *stride = c->rows_pad;
+  *regions = c->window;
+  return VSF_OK;
+}
+
+extern "C" void* vsf_stream(vsf_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 
 extern "C" int vsf_synth_sequence_device(vsf_ctx* c, void* d_out, int n, int first_pose, int n_poses, int stride,
                                          uint64_t seed) {

@@ -47,6 +47,15 @@ def load_frontend_library():
     L.vsff_odometry_factor.argtypes = [vp, i, vp, vp, vp, vp]
     L.vsff_serialize_problem.argtypes = [vp, vp, C.c_size_t]
     L.vsff_serialize_problem.restype = C.c_size_t
+    L.vsff_submit_features.argtypes = [vp, vp, vp, i, vp, vp, i, i, d]
+    L.vsff_collect_features.argtypes = [vp]
+    L.vsff_in_flight.argtypes = [vp]
+    L.vsff_start_shard.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.vsff_synth_frame.argtypes = [i, i, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, C.POINTER(d)]
+    L.vsff_run_synthetic_sequence.argtypes = [i, i, i, i, i, i, i, C.c_uint64, i, C.POINTER(vp), C.c_char_p, i]
+    L.vsff_run_synthetic_sequence.restype = C.c_size_t
+    L.vsff_free.argtypes = [vp]
+    L.vsff_synthetic_rig.argtypes = [vp] * 5
     _LIB = L
     return L
 
@@ -56,6 +65,16 @@ def default_config() -> dict:
     P1, P2 = np.zeros(12, np.float32), np.zeros(12, np.float32)
     F, K, D = np.zeros(9, np.float32), np.zeros(9, np.float32), np.zeros(5, np.float32)
     L.vsff_default_config(P1.ctypes.data, P2.ctypes.data, F.ctypes.data, K.ctypes.data, D.ctypes.data)
+    return dict(P_left=P1.reshape(3, 4), P_right=P2.reshape(3, 4), fundamental=F.reshape(3, 3),
+                K_left=K.reshape(3, 3), dist_left=D)
+
+
+def synthetic_rig() -> dict:
+    """The rig vsf_sequence_driver / run_synthetic_sequence use (SyntheticRig)."""
+    L = load_frontend_library()
+    P1, P2 = np.zeros(12, np.float32), np.zeros(12, np.float32)
+    F, K, D = np.zeros(9, np.float32), np.zeros(9, np.float32), np.zeros(5, np.float32)
+    L.vsff_synthetic_rig(P1.ctypes.data, P2.ctypes.data, F.ctypes.data, K.ctypes.data, D.ctypes.data)
     return dict(P_left=P1.reshape(3, 4), P_right=P2.reshape(3, 4), fundamental=F.reshape(3, 3),
                 K_left=K.reshape(3, 3), dist_left=D)
 
@@ -117,6 +136,31 @@ class Frontend:
             raise RuntimeError(self._L.vsff_last_error(self._h).decode())
         return bool(rc)
 
+    # pipelined form (Frontend::SubmitFeatures / CollectFeatures)
+    def submit_features(self, kp_left, desc_left, kp_right, desc_right, time: float = 0.0) -> bool:
+        kl = np.ascontiguousarray(kp_left, KEYPOINT_DTYPE)
+        kr = np.ascontiguousarray(kp_right, KEYPOINT_DTYPE)
+        dl, dr = self._desc(desc_left), self._desc(desc_right)
+        rc = self._L.vsff_submit_features(self._h, kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data,
+                                          dr.ctypes.data, len(kr), self.desc_bytes, float(time))
+        if rc < 0:
+            raise RuntimeError(self._L.vsff_last_error(self._h).decode())
+        return bool(rc)
+
+    def collect_features(self) -> bool:
+        rc = self._L.vsff_collect_features(self._h)
+        if rc < 0:
+            raise RuntimeError(self._L.vsff_last_error(self._h).decode())
+        return bool(rc)
+
+    @property
+    def in_flight(self) -> int:
+        return self._L.vsff_in_flight(self._h)
+
+    def start_shard(self, halo_first: int, first: int):
+        if self._L.vsff_start_shard(self._h, halo_first, first) < 0:
+            raise RuntimeError(self._L.vsff_last_error(self._h).decode())
+
     def get_matches(self, Q, T, ratio: float) -> np.ndarray:
         Q, T = self._desc(Q), self._desc(T)
         out = np.zeros(max(len(Q), 1), DMATCH_DTYPE)
@@ -169,6 +213,38 @@ class Frontend:
         buf = (C.c_uint8 * max(n, 1))()
         self._L.vsff_serialize_problem(self._h, buf, n)
         return bytes(buf[:n])
+
+
+def synth_frame(features: int, desc_bytes: int, seed: int, pose: int):
+    """One frame of the C++ synthetic stereo source (csrc/frontend/synthetic_source.h) and its
+    odometry message: (kp_left, desc_left, kp_right, desc_right, translation, quat_wxyz, timestamp)."""
+    L = load_frontend_library()
+    kl, kr = np.zeros(features, KEYPOINT_DTYPE), np.zeros(features, KEYPOINT_DTYPE)
+    dl, dr = np.zeros((features, desc_bytes), np.uint8), np.zeros((features, desc_bytes), np.uint8)
+    t, q = np.zeros(3, np.float32), np.zeros(4, np.float32)
+    ts = C.c_double(0)
+    rc = L.vsff_synth_frame(features, desc_bytes, seed, pose, kl.ctypes.data, dl.ctypes.data, kr.ctypes.data,
+                            dr.ctypes.data, t.ctypes.data, q.ctypes.data, C.byref(ts))
+    if rc:
+        raise RuntimeError("vsff_synth_frame failed")
+    return kl, dl, kr, dr, t, q, ts.value
+
+
+def run_synthetic_sequence(features: int, desc_bytes: int, frame_life: int, n_poses: int, world: int = 1,
+                           in_flight: int = 1, seed: int = 1, exact: bool = True, device: int = 0) -> bytes:
+    """The SLAMProblem message (ROS1 wire bytes) of poses [0, n_poses) of the synthetic sequence,
+    run as `world` shards one after the other in this process and merged - what the ranks of
+    vsf_sequence_driver do, minus the NCCL transport of the pieces."""
+    L = load_frontend_library()
+    out = C.c_void_p()
+    err = C.create_string_buffer(512)
+    n = L.vsff_run_synthetic_sequence(device, features, desc_bytes, frame_life, n_poses, world, in_flight, seed,
+                                      int(exact), C.byref(out), err, 512)
+    if n == 0:
+        raise RuntimeError(err.value.decode() or "vsff_run_synthetic_sequence failed")
+    data = C.string_at(out, n)
+    L.vsff_free(out)
+    return data
 
 
 def parse_slam_problem(wire: bytes) -> dict:
