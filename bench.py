@@ -542,7 +542,8 @@ def measure_e2e(a, ctx, seq, n, W, K, WU, B, world, dist, torch, host_threads):
       pipelined  vsf_window_run_sequence = the loop vsf_window_submit(t) ... vsf_window_collect(t - lag)
                  written in C++ like a caller of the C ABI would: the host sorts frame t-lag while the
                  device matches frame t (headline; host std::sort = reference order).  All K steps
-                 (K x B frames) in one timed region
+                 (K x B frames) in one timed region.  sort_mode 2 = the same order, replayed on
+                 the device (no host cores); sort_mode 0 = stable device sort
       sync       vsf_window_feature_matches + vsf_window_commit, one blocking call per frame
                  (bounded: 300 frames)"""
     from vision_slam_frontend_b200 import PIPELINE_DEPTH, capi
@@ -570,7 +571,8 @@ def measure_e2e(a, ctx, seq, n, W, K, WU, B, world, dist, torch, host_threads):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for sort_mode, key in ((1, "pipelined_exact_stdsort"), (0, "pipelined_device_sort")):
+    for sort_mode, key in ((1, "pipelined_exact_stdsort"), (2, "pipelined_exact_device_sort"),
+                           (0, "pipelined_device_sort")):
         ctx.window_clear()
         for p in range(W):
             ctx.window_push(p, hp[p][:, :a.desc_bytes] if a.desc_bytes != rb else hp[p])
@@ -737,6 +739,15 @@ def extra_workloads(a, torch, stream):
                      "cpu_triangulated_points_per_s": None if cpu_t is None else len(x1) / cpu_t, "cpu_threads": ncpu}
     except Exception as e:      # noqa: BLE001
         out["C3"] = {"error": repr(e)}
+
+    # ---- C2 / C3 as a C++ caller sees them (vsf_latency_probe: no Python between the calls)
+    try:
+        exe = os.path.join(ROOT, "vision_slam_frontend_b200", "vsf_latency_probe")
+        pr = subprocess.run([exe, "0", "2000", "32", "1"], capture_output=True, text=True, timeout=120)
+        out["cxx_latency"] = json.loads(pr.stdout.strip().splitlines()[-1]) if pr.returncode == 0 else \
+            {"error": "rc %d: %s" % (pr.returncode, pr.stderr[-300:])}
+    except Exception as e:      # noqa: BLE001
+        out["cxx_latency"] = {"error": repr(e)}
 
     # ---- C5 sample
     try:

@@ -177,7 +177,11 @@ int vsf_window_match(vsf_ctx* ctx, const uint8_t* desc, int n, size_t stride,
  * sort_mode 0: the sort runs on the device and is stable, i.e. ordered by
  * (distance, queryIdx); sort_mode 1: the library calls std::sort on the host
  * exactly as the reference does (its order inside equal-distance groups is
- * libstdc++-specific).  The two differ only inside groups of equal distance. */
+ * libstdc++-specific); sort_mode 2: the same order as sort_mode 1, bit for bit,
+ * produced on the device by replaying libstdc++'s introsort (csrc/sort_kernel.cu) -
+ * no host cores needed, only the kept FeatureMatches cross PCIe; needs
+ * max_features <= 24576 (VSF_ERR_CAPACITY otherwise).  Modes 0 and 1 / 2 differ
+ * only inside groups of equal distance. */
 int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
                                size_t stride, double nn_match_ratio,
                                float best_percent, int sort_mode,
@@ -268,7 +272,8 @@ int vsf_get_stereo_threshold(vsf_ctx* ctx, float* value);
  *   (src/slam_frontend.cc:392-394); 1 = such a frame leaves the threshold unchanged. */
 enum {
   VSF_OPT_RESIDUAL_ORDER = 1,
-  VSF_OPT_HOLD_THRESHOLD_ON_EMPTY = 2
+  VSF_OPT_HOLD_THRESHOLD_ON_EMPTY = 2,
+  VSF_OPT_DEBUG_SORT_DEPTH = 100   /* tests: depth limit of sort_mode 2's introsort replay, -1 = 2 * floor(lg n) */
 };
 int vsf_set_option(vsf_ctx* ctx, int option, int value);
 int vsf_get_option(const vsf_ctx* ctx, int option, int* value);
@@ -432,6 +437,15 @@ int vsf_device_sm_count(const vsf_ctx* ctx);
  * (distance << 22 | position); afterwards keys[0 .. keep) are what std::sort by distance leaves
  * there (csrc/exact_sort.h). */
 int vsf_debug_sort_prefix(uint32_t* keys, int n, int keep);
+/* The same with introsort's depth limit (normally 2 * floor(lg n)) forced to `depth`, which makes
+ * the heapsort fallback reachable in tests. */
+int vsf_debug_sort_prefix_depth(uint32_t* keys, int n, int keep, int depth);
+
+/* The device sort + cut of sort_mode 0 / 2 on a caller-supplied list (tests): `n` matches in, the
+ * first int(n * best_percent) FeatureMatches in the order of the mode out (exact = 1: the
+ * reference's std::sort order, csrc/sort_kernel.cu).  n <= max_features. */
+int vsf_debug_sort_device(vsf_ctx* ctx, const vsf_dmatch* matches, int n, float best_percent,
+                          int exact, vsf_feature_match* out, int* n_out);
 
 /* Host-side planner of the tensor engine's work partition, no device needed (CPU tests): for a
  * launch of query_blocks 256-query blocks against train_tiles 256-row tiles on sm_count SMs,

@@ -170,7 +170,7 @@ def test_window_match_sequence_against_oracle():
         assert sum(len(m) for _, m in got) > 1000
 
 
-@pytest.mark.parametrize("sort_mode", [0, 1])
+@pytest.mark.parametrize("sort_mode", [0, 1, 2])
 def test_window_feature_matches(sort_mode):
     n, W = 1200, 3
     frames = [synth.synth_pose(n, p, 120, 5) for p in range(5)]
@@ -185,7 +185,7 @@ def test_window_feature_matches(sort_mode):
                 m = native.get_matches(past, D, RATIO)
                 keep = restate.num_good_matches(len(m), bp)
                 assert len(pairs) == keep
-                order = restate.sort_order_stdsort(m) if sort_mode == 1 else restate.sort_order_stable(m)
+                order = restate.sort_order_stdsort(m) if sort_mode >= 1 else restate.sort_order_stable(m)
                 exp = m[order][:keep]
                 np.testing.assert_array_equal(pairs[:, 0], exp["queryIdx"].astype(np.uint64))
                 np.testing.assert_array_equal(pairs[:, 1], exp["trainIdx"].astype(np.uint64))
@@ -197,7 +197,7 @@ def test_window_feature_matches(sort_mode):
 
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("engine", [1, 2])
-@pytest.mark.parametrize("sort_mode", [0, 1])
+@pytest.mark.parametrize("sort_mode", [0, 1, 2])
 def test_window_pipelined_submit_collect(sort_mode, engine, pinned):
     """vsf_window_submit / vsf_window_collect with several frames in flight return, frame by
     frame, what the reference's loop (src/slam_frontend.cc:424-434, :467-470) produces."""
@@ -227,7 +227,7 @@ def test_window_pipelined_submit_collect(sort_mode, engine, pinned):
                 m = native.get_matches(past, D, RATIO)
                 keep = restate.num_good_matches(len(m), bp)
                 assert len(pairs) == keep
-                order = restate.sort_order_stdsort(m) if sort_mode == 1 else restate.sort_order_stable(m)
+                order = restate.sort_order_stdsort(m) if sort_mode >= 1 else restate.sort_order_stable(m)
                 exp = m[order][:keep]
                 np.testing.assert_array_equal(pairs[:, 0], exp["queryIdx"].astype(np.uint64))
                 np.testing.assert_array_equal(pairs[:, 1], exp["trainIdx"].astype(np.uint64))

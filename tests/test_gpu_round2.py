@@ -319,7 +319,7 @@ def test_window_match_block_device(width):
     assert sum(len(m) for m in got) > 1000
 
 
-@pytest.mark.parametrize("sort_mode", [0, 1])
+@pytest.mark.parametrize("sort_mode", [0, 1, 2])
 def test_window_run_sequence_equals_per_frame_calls(sort_mode):
     import torch
     from vision_slam_frontend_b200 import capi
@@ -339,7 +339,7 @@ def test_window_run_sequence_equals_per_frame_calls(sort_mode):
         for j, past in enumerate(live):
             m = native.get_matches(past, D, RATIO)
             keep = restate.num_good_matches(len(m), BP)
-            order = restate.sort_order_stdsort(m) if sort_mode == 1 else restate.sort_order_stable(m)
+            order = restate.sort_order_stdsort(m) if sort_mode >= 1 else restate.sort_order_stable(m)
             exp = m[order][:keep]
             assert counts[k, j] == keep
             np.testing.assert_array_equal(out[k, j, :keep]["feature_idx_initial"], exp["queryIdx"].astype(np.uint64))
@@ -513,3 +513,77 @@ def test_gather_matches_two_ranks_over_nccl(tmp_path):
                         os.path.join(root, "tools", "nccl_gather_check.py")], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("gather ok") == 2
+
+
+# ------------------------------------ sort_mode 2: libstdc++'s std::sort order, replayed on the device
+
+def _dmatch_list(dist):
+    import vision_slam_frontend_b200 as vsf
+    m = np.zeros(len(dist), vsf.DMATCH_DTYPE)
+    m["queryIdx"] = np.arange(len(dist)) * 3 + 1            # not the position: the kernel must carry the record
+    m["trainIdx"] = (np.arange(len(dist)) * 7 + 5) % 100003
+    m["distance"] = np.asarray(dist, np.float32)
+    return m
+
+
+@pytest.mark.parametrize("best_percent", [0.3, 1.0, 0.05, 0.77])
+def test_device_exact_sort_equals_std_sort(best_percent):
+    """The corpus of tests/test_exact_sort.py (sizes around the 16-element threshold, powers of
+    two, C4 / C5 list lengths; from all-equal to 257 distinct distances) through the device
+    replay: the kept prefix is the real std::sort's (oracle/stdsort_oracle.cc), ties included."""
+    rng = np.random.default_rng(int(best_percent * 1000) + 11)
+    sizes = list(range(0, 70)) + [100, 255, 256, 257, 500, 1000, 2500, 4500, 5000, 12000, 20000]
+    with new_ctx(max_features=20000, window=2) as ctx:
+        for n in sizes:
+            for spread in (1, 2, 7, 40, 257):
+                dist = rng.integers(0, spread, size=n)
+                m = _dmatch_list(dist)
+                keep = restate.num_good_matches(n, np.float32(best_percent))
+                exp = m[restate.sort_order_stdsort(m)][:keep]
+                got = ctx.debug_sort_device(m, best_percent, exact=True)
+                assert len(got) == keep, (n, spread)
+                np.testing.assert_array_equal(got[:, 0], exp["queryIdx"].astype(np.uint64), err_msg=str((n, spread)))
+                np.testing.assert_array_equal(got[:, 1], exp["trainIdx"].astype(np.uint64))
+                # and the stable mode on the same list
+                exp0 = m[restate.sort_order_stable(m)][:keep]
+                got0 = ctx.debug_sort_device(m, best_percent, exact=False)
+                np.testing.assert_array_equal(got0[:, 0], exp0["queryIdx"].astype(np.uint64))
+
+
+def test_device_exact_sort_sorted_and_adversarial_inputs():
+    rng = np.random.default_rng(4)
+    cases = [np.arange(3000) // 12, (np.arange(3000) // 12)[::-1], np.tile([5, 1, 9, 1, 5], 700),
+             np.concatenate([np.full(2000, 30), rng.integers(0, 30, 1500)]),
+             np.where(np.arange(4096) % 2 == 0, 7, rng.integers(0, 200, 4096))]
+    with new_ctx(max_features=8192, window=2) as ctx:
+        for dist in cases:
+            m = _dmatch_list(dist)
+            for bp in (0.3, 1.0):
+                keep = restate.num_good_matches(len(m), np.float32(bp))
+                exp = m[restate.sort_order_stdsort(m)][:keep]
+                got = ctx.debug_sort_device(m, bp, exact=True)
+                np.testing.assert_array_equal(got[:, 0], exp["queryIdx"].astype(np.uint64))
+
+
+@pytest.mark.parametrize("depth", [0, 1, 2, 4])
+def test_device_exact_sort_heapsort_fallback(depth):
+    """Introsort's depth limit forced low on both sides (VSF_OPT_DEBUG_SORT_DEPTH /
+    vsf_debug_sort_prefix_depth): the ranges that hit it go through libstdc++'s heapsort, whose
+    sift order the kernel replays too."""
+    import vision_slam_frontend_b200 as vsf
+    from vision_slam_frontend_b200 import capi
+    rng = np.random.default_rng(depth)
+    lib = vsf.load_library()
+    with new_ctx(max_features=8192, window=2) as ctx:
+        ctx.set_option(capi.OPT_DEBUG_SORT_DEPTH, depth)
+        for n in (17, 40, 100, 1000, 4500):
+            for spread in (2, 40, 300):
+                dist = rng.integers(0, spread, size=n)
+                m = _dmatch_list(dist)
+                keep = int(np.float32(n) * np.float32(0.3))
+                keys = np.ascontiguousarray((dist.astype(np.uint32) << 22) | np.arange(n, dtype=np.uint32))
+                assert lib.vsf_debug_sort_prefix_depth(keys.ctypes.data, n, keep, depth) == 0
+                exp = m[(keys[:keep] & np.uint32((1 << 22) - 1)).astype(np.int64)]
+                got = ctx.debug_sort_device(m, 0.3, exact=True)
+                np.testing.assert_array_equal(got[:, 0], exp["queryIdx"].astype(np.uint64), err_msg=str((n, spread)))
+        ctx.set_option(capi.OPT_DEBUG_SORT_DEPTH, -1)

@@ -17,6 +17,7 @@ LIB = os.path.join(PKG, "libvsf_cuda.so")
 FRONTEND_LIB = os.path.join(PKG, "libvsf_frontend.so")
 NCCL_LIB = os.path.join(PKG, "libvsf_nccl.so")
 DRIVER_BIN = os.path.join(PKG, "vsf_sequence_driver")
+PROBE_BIN = os.path.join(PKG, "vsf_latency_probe")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 CUDA_SOURCES = ["knn2_kernel.cu", "knn2_tc_kernel.cu", "knn2_tc64_kernel.cu", "stereo_kernels.cu", "sort_kernel.cu",
@@ -97,6 +98,12 @@ def build_driver(force: bool = False) -> str:
                "-Wl,-rpath,$ORIGIN", "-lpthread"]
         subprocess.check_call(cmd)
         os.replace(DRIVER_BIN + ".tmp", DRIVER_BIN)
+    psrc = os.path.join(CSRC, "frontend", "latency_probe.cc")
+    if force or _stale(PROBE_BIN, [psrc, FRONTEND_LIB]):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", INCLUDE, "-I", os.path.join(CSRC, "frontend"),
+               "-o", PROBE_BIN + ".tmp", psrc, "-L", PKG, "-lvsf_frontend", "-lvsf_cuda", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+        os.replace(PROBE_BIN + ".tmp", PROBE_BIN)
     return DRIVER_BIN
 
 
@@ -106,7 +113,7 @@ def build_frontend(force: bool = False) -> str:
     if not os.path.isdir(fdir):
         return ""
     srcs = [os.path.join(fdir, f) for f in sorted(os.listdir(fdir))
-            if f.endswith(".cc") and f != "sequence_driver.cc"]
+            if f.endswith(".cc") and f not in ("sequence_driver.cc", "latency_probe.cc")]
     hdrs = [os.path.join(fdir, f) for f in os.listdir(fdir) if f.endswith(".h")]
     if not srcs:
         return ""

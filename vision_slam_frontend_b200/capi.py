@@ -19,6 +19,7 @@ _LIB = None
 # cv::DMatch / cv::KeyPoint / slam_types::FeatureMatch layouts (include/vsf.h)
 OPT_RESIDUAL_ORDER = 1            # VSF_OPT_RESIDUAL_ORDER
 OPT_HOLD_THRESHOLD_ON_EMPTY = 2   # VSF_OPT_HOLD_THRESHOLD_ON_EMPTY
+OPT_DEBUG_SORT_DEPTH = 100        # VSF_OPT_DEBUG_SORT_DEPTH
 PIPELINE_DEPTH = 8   # VSF_PIPELINE_DEPTH (include/vsf.h): frames vsf_window_submit keeps in flight
 
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"),
@@ -121,6 +122,8 @@ def load_library():
         "vsf_debug_kernel_trace": ([vp, vp, i, C.POINTER(i)], i),
         "vsf_debug_tc_plan": ([i, i, i, i, C.c_longlong, C.c_longlong, vp], i),
         "vsf_debug_sort_prefix": ([vp, i, i], i),
+        "vsf_debug_sort_prefix_depth": ([vp, i, i, i], i),
+        "vsf_debug_sort_device": ([vp, vp, i, f, i, vp, C.POINTER(i)], i),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)   # AttributeError if the library lacks a declared symbol
@@ -143,6 +146,7 @@ EXPORTED_SYMBOLS = [
     "vsf_synth_sequence_device", "vsf_device_match_lists", "vsf_stream", "vsf_observe_submit",
     "vsf_observe_collect", "vsf_observe_in_flight", "vsf_probe_pipe", "vsf_device_sm_count",
     "vsf_debug_tc_trace", "vsf_debug_kernel_trace", "vsf_debug_tc_plan", "vsf_debug_sort_prefix",
+    "vsf_debug_sort_prefix_depth", "vsf_debug_sort_device",
 ]
 
 
@@ -497,6 +501,16 @@ class Context:
                               stride: int, seed: int):
         self._check(self._L.vsf_synth_sequence_device(self._h, C.c_void_p(int(d_out)), n,
                                                       first_pose, n_poses, stride, seed))
+
+    def debug_sort_device(self, matches: np.ndarray, best_percent: float, exact: bool) -> np.ndarray:
+        """Device sort + cut of a DMATCH list -> (keep, 2) uint64 [initial, current]."""
+        m = np.ascontiguousarray(matches, DMATCH_DTYPE)
+        out = np.zeros(max(len(m), 1), FEATURE_MATCH_DTYPE)
+        n = C.c_int(0)
+        self._check(self._L.vsf_debug_sort_device(self._h, _ptr(m), len(m), float(best_percent), int(exact),
+                                                  _ptr(out), C.byref(n)))
+        fm = out[:n.value]
+        return np.stack([fm["feature_idx_initial"], fm["feature_idx_current"]], 1).reshape(-1, 2)
 
     def probe_pipe(self, kind: int, iters: int = 4096) -> float:
         v = C.c_double(0)

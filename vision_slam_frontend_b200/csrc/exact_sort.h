@@ -61,12 +61,13 @@ inline void introsort_prefix_loop(uint32_t* first, uint32_t* last, long depth_li
 // After the call keys[0 .. keep) hold exactly what std::sort(keys, keys + n, KeyLess<SHIFT>())
 // leaves there; the rest of the array is the remaining elements in unspecified order.
 template <int SHIFT>
-inline void sort_prefix(uint32_t* keys, long n, long keep) {
+inline void sort_prefix(uint32_t* keys, long n, long keep, long depth_limit = -1) {
   if (n <= 0 || keep <= 0) return;
 #ifdef VSF_EXACT_SORT_LIBSTDCXX
   auto comp = __gnu_cxx::__ops::__iter_comp_iter(KeyLess<SHIFT>());
   uint32_t* sorted_end = keys + n;
-  introsort_prefix_loop(keys, keys + n, std::__lg(n) * 2, keys + std::min(keep, n), &sorted_end, comp);
+  introsort_prefix_loop(keys, keys + n, depth_limit >= 0 ? depth_limit : std::__lg(n) * 2, keys + std::min(keep, n),
+                        &sorted_end, comp);
   std::__final_insertion_sort(keys, sorted_end, comp);
 #else
   std::sort(keys, keys + n, KeyLess<SHIFT>());      // another standard library: its own order

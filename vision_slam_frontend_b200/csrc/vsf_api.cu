@@ -47,7 +47,9 @@ cudaError_t launch_undistort_points(const float2* in, int n, const float* K9, co
                                     cudaStream_t stream);
 cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* counts,
                             int n_problems, float best_percent, vsf_feature_match* out,
-                            int out_stride, int* out_counts, int bins, cudaStream_t stream);
+                            int out_stride, int* out_counts, int bins, int max_rows, int exact,
+                            int depth_override, cudaStream_t stream);
+int sort_exact_max_rows();
 }  // namespace vsf
 
 
@@ -108,6 +110,7 @@ struct vsf_ctx {
   float* d_resid = nullptr;
   unsigned *d_chunk_keep = nullptr, *d_chunk_off = nullptr, *d_ticket = nullptr;
   int opt_residual_order = 0, opt_hold_on_empty = 0;   // vsf_set_option
+  int sort_depth_override = -1;                        // VSF_OPT_DEBUG_SORT_DEPTH (tests)
   int *d_kept_left = nullptr, *d_kept_right = nullptr;
   int* d_slot_rows = nullptr;   // [ring_slots] device-side row count of every ring slot (compacted frames)
   float* d_thresh = nullptr;  // [2], ping-pong
@@ -994,12 +997,14 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
                                           vsf_feature_match* out, int cap_per_frame, int* n_frames) {
   if (!c) return VSF_ERR_BAD_ARG;
   if (!n_frames || !counts || cap_per_frame < 0 || (cap_per_frame > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
-  if (sort_mode != 0 && sort_mode != 1) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 or 1");
+  if (sort_mode < 0 || sort_mode > 2) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0, 1 or 2");
+  if (sort_mode == 2 && c->rows_pad > sort_exact_max_rows())
+    return fail(c, VSF_ERR_CAPACITY, "sort_mode 2 (reference order on the device) needs max_features <= 24576; use sort_mode 1");
   int rc = window_launch(c, desc, n, stride, ratio, sort_mode == 1);
   if (rc) return rc;
   const int nf = int(c->live.size());
   *n_frames = nf;
-  if (sort_mode == 0) {
+  if (sort_mode != 1) {
     // device: stable counting sort by distance + best_percent cut, only survivors come back
     std::vector<const vsf_dmatch*> mp(nf);
     std::vector<const int*> cp(nf);
@@ -1011,7 +1016,8 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
     }
     if (nf > 0) {
       VSF_CUDA(c, launch_sort_cut(mp.data(), cp.data(), nf, best_percent, c->d_fm, c->rows_pad,
-                                  c->d_fm_count, 8 * c->row_bytes + 1, c->stream));
+                                  c->d_fm_count, 8 * c->row_bytes + 1, max_matches, sort_mode == 2,
+                                  c->sort_depth_override, c->stream));
       VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_fm_count, nf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       VSF_CUDA(c, cudaStreamSynchronize(c->stream));
       for (int j = 0; j < nf; ++j)
@@ -1174,7 +1180,9 @@ extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_cou
 extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* desc, int n, size_t stride,
                                  double ratio, float best_percent, int sort_mode, int flags) {
   if (!c) return VSF_ERR_BAD_ARG;
-  if (sort_mode != 0 && sort_mode != 1) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 or 1");
+  if (sort_mode < 0 || sort_mode > 2) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0, 1 or 2");
+  if (sort_mode == 2 && c->rows_pad > sort_exact_max_rows())
+    return fail(c, VSF_ERR_CAPACITY, "sort_mode 2 (reference order on the device) needs max_features <= 24576; use sort_mode 1");
   if (n < 0 || (n > 0 && !desc) || (n > 0 && stride < size_t(c->desc_bytes))) return fail(c, VSF_ERR_BAD_ARG, "bad frame");
   if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more rows than max_features");
   if (c->flight_count >= VSF_PIPELINE_DEPTH)
@@ -1247,15 +1255,17 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   c->mir_dcounts = f.dm_counts;
   c->mir_hcounts = f.h_counts;
   rc = run_knn(c, specs, ratio, sort_mode == 1);
-  if (rc == VSF_OK && sort_mode == 0 && nf > 0) {
-    // stable device sort + cut; the kept counts go to the flight's mapped counters
+  if (rc == VSF_OK && sort_mode != 1 && nf > 0) {
+    // device sort (stable, or the replay of the reference's std::sort) + cut; the kept counts go
+    // to the flight's mapped counters
     const vsf_dmatch* mp[kMaxProblems];
     const int* cp[kMaxProblems];
     for (int j = 0; j < nf; ++j) {
       mp[j] = c->region_ptr(j);
       cp[j] = c->d_match_count + j;
     }
-    const cudaError_t e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, 8 * c->row_bytes + 1, c->stream);
+    const cudaError_t e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, 8 * c->row_bytes + 1,
+                                          max_cnt, sort_mode == 2, c->sort_depth_override, c->stream);
     if (e != cudaSuccess) {
       c->err = std::string("launch_sort_cut: ") + cudaGetErrorString(e);
       rc = VSF_ERR_CUDA;
@@ -1277,7 +1287,7 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   f.d2h_bytes = size_t(nf) * sizeof(int);
   if (nf > 0 && max_cnt > 0) {
     const size_t pitch = size_t(c->rows_pad) * 16;
-    const int rows = sort_mode == 1 ? max_cnt : std::min(max_cnt, int(float(size_t(max_cnt)) * best_percent) + 1);
+    const int rows = sort_mode == 1 ? max_cnt : std::min(max_cnt, int(float(size_t(max_cnt)) * best_percent) + 1);   // modes 0, 2: the kept part
     if (rows > 0) {
       VSF_CUDA(c, cudaMemcpy2DAsync(sort_mode == 1 ? static_cast<void*>(f.h_matches) : static_cast<void*>(f.h_fm), pitch,
                                     sort_mode == 1 ? static_cast<const void*>(f.d_matches) : static_cast<const void*>(f.d_fm), pitch,
@@ -1325,7 +1335,7 @@ extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* fram
   c->last_h2d = f.h2d_bytes;
   c->last_d2h = f.d2h_bytes;
   for (int j = 0; j < nf; ++j) {
-    const int keep = f.sort_mode == 0 ? f.h_counts[j] : f.keep[j];
+    const int keep = f.sort_mode != 1 ? f.h_counts[j] : f.keep[j];
     if (keep > cap_per_frame) return fail(c, VSF_ERR_CAPACITY, "cap_per_frame too small");
     counts[j] = keep;
     if (frame_ids) frame_ids[j] = f.fids[j];
@@ -1458,6 +1468,11 @@ extern "C" int vsf_set_stereo_threshold(vsf_ctx* c, float value) {
 
 extern "C" int vsf_set_option(vsf_ctx* c, int option, int value) {
   if (!c) return VSF_ERR_BAD_ARG;
+  if (option == VSF_OPT_DEBUG_SORT_DEPTH) {
+    if (value < -1 || value > 64) return fail(c, VSF_ERR_BAD_ARG, "sort depth must be -1 .. 64");
+    c->sort_depth_override = value;
+    return VSF_OK;
+  }
   if (value != 0 && value != 1) return fail(c, VSF_ERR_BAD_ARG, "option value must be 0 or 1");
   switch (option) {
     case VSF_OPT_RESIDUAL_ORDER: c->opt_residual_order = value; return VSF_OK;
@@ -1471,6 +1486,7 @@ extern "C" int vsf_get_option(const vsf_ctx* c, int option, int* value) {
   switch (option) {
     case VSF_OPT_RESIDUAL_ORDER: *value = c->opt_residual_order; return VSF_OK;
     case VSF_OPT_HOLD_THRESHOLD_ON_EMPTY: *value = c->opt_hold_on_empty; return VSF_OK;
+    case VSF_OPT_DEBUG_SORT_DEPTH: *value = c->sort_depth_override; return VSF_OK;
     default: return VSF_ERR_BAD_ARG;
   }
 }
@@ -1852,6 +1868,41 @@ extern "C" int vsf_synth_sequence_device(vsf_ctx* c, void* d_out, int n, int fir
 extern "C" int vsf_debug_sort_prefix(uint32_t* keys, int n, int keep) {
   if (n < 0 || keep < 0 || keep > n || (n > 0 && !keys)) return VSF_ERR_BAD_ARG;
   vsf_exact_sort::sort_prefix<kIdxBits>(keys, n, keep);
+  return VSF_OK;
+}
+
+extern "C" int vsf_debug_sort_prefix_depth(uint32_t* keys, int n, int keep, int depth) {
+  if (n < 0 || keep < 0 || keep > n || (n > 0 && !keys) || depth < 0) return VSF_ERR_BAD_ARG;
+  vsf_exact_sort::sort_prefix<kIdxBits>(keys, n, keep, depth);
+  return VSF_OK;
+}
+
+extern "C" int vsf_debug_sort_device(vsf_ctx* c, const vsf_dmatch* matches, int n, float best_percent, int exact,
+                                     vsf_feature_match* out, int* n_out) {
+  if (!c || n < 0 || (n > 0 && (!matches || !out)) || !n_out) return VSF_ERR_BAD_ARG;
+  if (n > c->max_features) return fail(c, VSF_ERR_CAPACITY, "more matches than max_features");
+  if (exact && c->rows_pad > sort_exact_max_rows()) return fail(c, VSF_ERR_CAPACITY, "exact device sort needs max_features <= 24576");
+  cudaSetDevice(c->device);
+  *n_out = 0;
+  if (n == 0) return VSF_OK;
+  std::memcpy(c->h_matches, matches, size_t(n) * sizeof(vsf_dmatch));
+  c->h_counts[0] = n;
+  VSF_CUDA(c, cudaMemcpyAsync(c->d_matches, c->h_matches, size_t(n) * sizeof(vsf_dmatch), cudaMemcpyHostToDevice, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->d_match_count, c->h_counts, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  const vsf_dmatch* mp[1] = {c->d_matches};
+  const int* cp[1] = {c->d_match_count};
+  VSF_CUDA(c, launch_sort_cut(mp, cp, 1, best_percent, c->d_fm, c->rows_pad, c->d_fm_count, 8 * c->row_bytes + 1, n,
+                              exact, c->sort_depth_override, c->stream));
+  VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_fm_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int keep = c->h_counts[0];
+  if (keep < 0 || keep > n) return fail(c, VSF_ERR_CUDA, "sort kernel reported a bad count");
+  if (keep > 0) {
+    VSF_CUDA(c, cudaMemcpyAsync(c->h_fm, c->d_fm, size_t(keep) * sizeof(vsf_feature_match), cudaMemcpyDeviceToHost, c->stream));
+    VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(out, c->h_fm, size_t(keep) * sizeof(vsf_feature_match));
+  }
+  *n_out = keep;
   return VSF_OK;
 }
 
