@@ -103,7 +103,8 @@ int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
  * csrc/knn2_tc_kernel.cu), 3 = tensor cores, e4m3 operands (kind::f8f6f4).
  * Engine 2 exists for every descriptor width (csrc/knn2_tc64_kernel.cu for 33..64
  * bytes), engine 3 for desc_bytes <= 32 only.  Every engine produces bit-identical
- * results.  flags: pass 0; 16 / 32 record the per-CTA / per-kernel
+ * results.  flags: pass 0; 64 keeps the device sort of the pipelined frame stream (sort_mode 0 / 2)
+ * on the main stream instead of a side stream with reserved SMs (A/B timing); 16 / 32 record the per-CTA / per-kernel
  * timelines read by vsf_debug_tc_trace / vsf_debug_kernel_trace (16, and the
  * timing-only flags 2 / 4, exist only in libraries built with VSF_TC_TRACE /
  * VSF_TC_BRINGUP, see vision_slam_frontend_b200/build.py). */
@@ -180,8 +181,15 @@ int vsf_window_match(vsf_ctx* ctx, const uint8_t* desc, int n, size_t stride,
  * libstdc++-specific); sort_mode 2: the same order as sort_mode 1, bit for bit,
  * produced on the device by replaying libstdc++'s introsort (csrc/sort_kernel.cu) -
  * no host cores needed, only the kept FeatureMatches cross PCIe; needs
- * max_features <= 24576 (VSF_ERR_CAPACITY otherwise).  Modes 0 and 1 / 2 differ
- * only inside groups of equal distance. */
+ * max_features <= 24576 (VSF_ERR_CAPACITY otherwise); sort_mode 3: the reference
+ * order wherever it is cheaper - on the host (mode 1) when the ctx may use at least 8
+ * host threads (vsf_set_host_threads) or max_features > 24576, on the device (mode 2)
+ * otherwise, e.g. when the ranks of a many-GPU node share its cores.  Modes 0 and
+ * 1 / 2 / 3 differ only inside groups of equal distance. */
+#define VSF_SORT_STABLE_DEVICE 0
+#define VSF_SORT_EXACT_HOST 1
+#define VSF_SORT_EXACT_DEVICE 2
+#define VSF_SORT_EXACT_AUTO 3
 int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
                                size_t stride, double nn_match_ratio,
                                float best_percent, int sort_mode,

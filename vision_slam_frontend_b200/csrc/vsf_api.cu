@@ -48,8 +48,9 @@ cudaError_t launch_undistort_points(const float2* in, int n, const float* K9, co
 cudaError_t launch_sort_cut(const vsf_dmatch* const* matches, const int* const* counts,
                             int n_problems, float best_percent, vsf_feature_match* out,
                             int out_stride, int* out_counts, int bins, int max_rows, int exact,
-                            int depth_override, cudaStream_t stream);
+                            int depth_override, void* gscratch, cudaStream_t stream, long long* trace = nullptr);
 int sort_exact_max_rows();
+size_t sort_exact_global_scratch(int max_rows);
 }  // namespace vsf
 
 
@@ -111,6 +112,7 @@ struct vsf_ctx {
   unsigned *d_chunk_keep = nullptr, *d_chunk_off = nullptr, *d_ticket = nullptr;
   int opt_residual_order = 0, opt_hold_on_empty = 0;   // vsf_set_option
   int sort_depth_override = -1;                        // VSF_OPT_DEBUG_SORT_DEPTH (tests)
+  uint8_t* d_sort_scratch = nullptr;                   // sort_mode 2 on lists too long for shared memory
   int *d_kept_left = nullptr, *d_kept_right = nullptr;
   int* d_slot_rows = nullptr;   // [ring_slots] device-side row count of every ring slot (compacted frames)
   float* d_thresh = nullptr;  // [2], ping-pong
@@ -157,6 +159,8 @@ struct vsf_ctx {
     cudaEvent_t ev_up = nullptr;        // upload stream: the frame's rows are in the ring
     cudaEvent_t ev_chain = nullptr;     // main stream: the kernels of this frame have finished
     cudaEvent_t done = nullptr;         // download stream: the lists are in host memory
+    cudaEvent_t ev_sort = nullptr;      // sort stream: the device sort + cut of this frame has finished
+    int* d_counts = nullptr;            // device: [kMaxProblems] survivor counts of this frame
     uint8_t* h_desc = nullptr;          // pinned staging of the submitted frame
     uint8_t* d_train_exp = nullptr;     // device: the frame expanded to +-1 bytes on the upload stream
     vsf_dmatch* d_matches = nullptr;    // device: [window][rows_pad] ratio survivors of this frame
@@ -226,6 +230,13 @@ struct vsf_ctx {
   cudaStream_t obs_up_stream = nullptr;
 
   vsf_dmatch* match_base = nullptr;   // d_matches, or the device buffer of a pipelined submission
+  int* count_base = nullptr;          // d_match_count, or the device counters of a pipelined submission
+  // the device sort of the pipelined path runs on its own stream beside the next frame's distance
+  // kernel, on SMs that kernel leaves free (a persistent CTA per SM otherwise)
+  cudaStream_t sort_stream[2] = {nullptr, nullptr};   // alternate frames: the sorts of two frames may overlap
+  unsigned sort_rr = 0;
+  int reserve_sms = 0;
+  int reserve_override = -1;    // VSF_RESERVE_SMS (tuning)
   uint8_t* slot_ptr(int s) const { return d_ring + size_t(s) * rows_pad * row_bytes; }
   vsf_dmatch* region_ptr(int r) const { return match_base + size_t(r) * rows_pad; }
 };
@@ -379,7 +390,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     p.nq = s.nq;
     p.nt = s.nt;
     p.matches = c->region_ptr(s.region);
-    p.match_count = c->d_match_count + s.region;
+    p.match_count = c->count_base + s.region;
     p.row0 = row0;
     p.qb0 = qb0;
     p.region = s.region;
@@ -392,7 +403,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   if (max_nq == 0) {
     // nothing to match: every problem reports zero survivors
     for (int i = 0; i < b.num_problems; ++i) {
-      VSF_CUDA(c, cudaMemsetAsync(c->d_match_count + specs[i].region, 0, sizeof(int), c->stream));
+      VSF_CUDA(c, cudaMemsetAsync(c->count_base + specs[i].region, 0, sizeof(int), c->stream));
       if (mirror) c->mir_hcounts[specs[i].region] = 0;   // no kernel will write it
     }
     return VSF_OK;
@@ -468,7 +479,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       tb.trace = c->d_tc_trace;
     }
     // (64-byte rows store 4 partial key pairs per query and segment, 32-byte rows 2)
-    plan_tc_partition(&tb, qblocks, c->sm_count, c->force_split, size_t(row0) * (wide ? 2 : 1), c->partial_cap);
+    plan_tc_partition(&tb, qblocks, std::max(1, c->sm_count - c->reserve_sms), c->force_split,
+                      size_t(row0) * (wide ? 2 : 1), c->partial_cap);
     b.split = tb.slots;
     if (wide)
       VSF_CUDA(c, launch_knn2_tc64(b, tb, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
@@ -513,6 +525,18 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   return VSF_OK;
 }
 
+// Global scratch of the exact device sort (lists longer than its shared-memory capacity only).
+// (two halves: the sorts of two consecutive frames of the pipelined path may run side by side)
+static int sort_scratch(vsf_ctx* c, int exact, void** out, unsigned half = 0) {
+  *out = nullptr;
+  if (!exact) return VSF_OK;
+  const size_t per = sort_exact_global_scratch(c->rows_pad) * size_t(std::max(c->window, 1));
+  if (per == 0) return VSF_OK;
+  if (!c->d_sort_scratch) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_sort_scratch), 2 * per));
+  *out = c->d_sort_scratch + size_t(half & 1u) * per;
+  return VSF_OK;
+}
+
 // ------------------------------------------------------------------------------------ context
 
 extern "C" const char* vsf_version(void) { return VSF_VERSION_STRING; }
@@ -540,7 +564,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
                  c->d_chunk_keep, c->d_chunk_off, c->d_ticket, c->d_kept_left, c->d_kept_right, c->d_slot_rows, c->d_thresh, c->d_X4,
                  c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1], c->d_tc_trace,
-                 c->d_ktrace};
+                 c->d_ktrace, c->d_sort_scratch};
   for (void* p : dev)
     if (p) cudaFree(p);
   void* host[] = {c->h_desc[0], c->h_desc[1], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches, c->h_region_counts,
@@ -550,6 +574,8 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
     if (p) cudaFreeHost(p);
   if (c->up_stream) cudaStreamSynchronize(c->up_stream);
   if (c->down_stream) cudaStreamSynchronize(c->down_stream);
+  for (cudaStream_t st : c->sort_stream)
+    if (st) cudaStreamSynchronize(st);
   for (vsf_ctx::Flight& f : c->flights) {
     void* fh[] = {f.h_desc, f.h_matches, f.h_fm, f.h_counts};
     for (void* p : fh)
@@ -557,7 +583,8 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
     if (f.d_matches) cudaFree(f.d_matches);
     if (f.d_train_exp) cudaFree(f.d_train_exp);
     if (f.d_fm) cudaFree(f.d_fm);
-    for (cudaEvent_t e : {f.ev_up, f.ev_chain, f.done})
+    if (f.d_counts) cudaFree(f.d_counts);
+    for (cudaEvent_t e : {f.ev_up, f.ev_chain, f.done, f.ev_sort})
       if (e) cudaEventDestroy(e);
     std::free(f.keys);
   }
@@ -573,6 +600,8 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
   if (c->ev_main) cudaEventDestroy(c->ev_main);
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
   if (c->down_stream) cudaStreamDestroy(c->down_stream);
+  for (cudaStream_t st : c->sort_stream)
+    if (st) cudaStreamDestroy(st);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (cudaEvent_t e : c->pev)
@@ -659,6 +688,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   c->match_base = c->d_matches;
   VSF_ALLOC(c, c->d_match_count, kMaxProblems * sizeof(int));
   cudaMemset(c->d_match_count, 0, kMaxProblems * sizeof(int));
+  c->count_base = c->d_match_count;
   VSF_ALLOC(c, c->d_resid, N * sizeof(float));
   VSF_ALLOC(c, c->d_chunk_keep, (N / 256 + 2) * sizeof(unsigned));
   VSF_ALLOC(c, c->d_chunk_off, (N / 256 + 2) * sizeof(unsigned));
@@ -707,6 +737,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC_HOST(c, c->h_tri_io, N * 8 * sizeof(float));
   VSF_ALLOC_HOST(c, c->h_scalar, 16 * sizeof(float));
   VSF_ALLOC_HOST(c, c->h_fm, size_t(window) * N * sizeof(vsf_feature_match));
+  if (const char* e = std::getenv("VSF_RESERVE_SMS")) c->reserve_override = std::atoi(e);
   if (const char* e = std::getenv("VSF_ENGINE")) {   // test / bench override of the automatic choice
     const int v = std::atoi(e);
     if (v >= 0 && v <= 3 && (v < 3 || c->words == 8)) c->engine = v;
@@ -740,6 +771,8 @@ extern "C" int vsf_set_stream(vsf_ctx* c, void* cuda_stream) {
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->up_stream));
   if (c->down_stream) VSF_CUDA(c, cudaStreamSynchronize(c->down_stream));
+  for (cudaStream_t st : c->sort_stream)
+    if (st) VSF_CUDA(c, cudaStreamSynchronize(st));
   if (c->obs_up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->obs_up_stream));
   c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
   return VSF_OK;
@@ -751,6 +784,8 @@ extern "C" int vsf_synchronize(vsf_ctx* c) {
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->up_stream));
   if (c->down_stream) VSF_CUDA(c, cudaStreamSynchronize(c->down_stream));
+  for (cudaStream_t st : c->sort_stream)
+    if (st) VSF_CUDA(c, cudaStreamSynchronize(st));
   return VSF_OK;
 }
 
@@ -997,7 +1032,9 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
                                           vsf_feature_match* out, int cap_per_frame, int* n_frames) {
   if (!c) return VSF_ERR_BAD_ARG;
   if (!n_frames || !counts || cap_per_frame < 0 || (cap_per_frame > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
-  if (sort_mode < 0 || sort_mode > 2) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0, 1 or 2");
+  if (sort_mode < 0 || sort_mode > 3) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 .. 3");
+  if (sort_mode == VSF_SORT_EXACT_AUTO)
+    sort_mode = (c->host_threads >= 8 || c->rows_pad > sort_exact_max_rows()) ? VSF_SORT_EXACT_HOST : VSF_SORT_EXACT_DEVICE;
   if (sort_mode == 2 && c->rows_pad > sort_exact_max_rows())
     return fail(c, VSF_ERR_CAPACITY, "sort_mode 2 (reference order on the device) needs max_features <= 24576; use sort_mode 1");
   int rc = window_launch(c, desc, n, stride, ratio, sort_mode == 1);
@@ -1015,9 +1052,12 @@ extern "C" int vsf_window_feature_matches(vsf_ctx* c, const uint8_t* desc, int n
       max_matches = std::max(max_matches, c->slot_count[c->live[j]]);
     }
     if (nf > 0) {
+      void* gs = nullptr;
+      if ((rc = sort_scratch(c, sort_mode == 2, &gs))) return rc;
+      // (the scratch is sized for rows_pad: pass that bound so the kernel's strides match)
       VSF_CUDA(c, launch_sort_cut(mp.data(), cp.data(), nf, best_percent, c->d_fm, c->rows_pad,
-                                  c->d_fm_count, 8 * c->row_bytes + 1, max_matches, sort_mode == 2,
-                                  c->sort_depth_override, c->stream));
+                                  c->d_fm_count, 8 * c->row_bytes + 1, gs ? c->rows_pad : max_matches, sort_mode == 2,
+                                  c->sort_depth_override, gs, c->stream));
       VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_fm_count, nf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       VSF_CUDA(c, cudaStreamSynchronize(c->stream));
       for (int j = 0; j < nf; ++j)
@@ -1140,11 +1180,15 @@ static int flights_init(vsf_ctx* c) {
   const size_t list_bytes = size_t(c->window) * N * 16;   // vsf_dmatch and vsf_feature_match: 16 B
   VSF_CUDA(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
   VSF_CUDA(c, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+  for (cudaStream_t& st : c->sort_stream) VSF_CUDA(c, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   VSF_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
   for (vsf_ctx::Flight& f : c->flights) {
     VSF_CUDA(c, cudaEventCreateWithFlags(&f.ev_up, cudaEventDisableTiming));
     VSF_CUDA(c, cudaEventCreateWithFlags(&f.ev_chain, cudaEventDisableTiming));
     VSF_CUDA(c, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    VSF_CUDA(c, cudaEventCreateWithFlags(&f.ev_sort, cudaEventDisableTiming));
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_counts), kMaxProblems * sizeof(int)));
+    VSF_CUDA(c, cudaMemset(f.d_counts, 0, kMaxProblems * sizeof(int)));
     VSF_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&f.h_desc), N * c->row_bytes));
     VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_matches), list_bytes));
     VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&f.d_train_exp), size_t(round_up(c->max_features, kTcTileRows)) * size_t(c->row_bytes) * 8));
@@ -1180,7 +1224,9 @@ extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_cou
 extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* desc, int n, size_t stride,
                                  double ratio, float best_percent, int sort_mode, int flags) {
   if (!c) return VSF_ERR_BAD_ARG;
-  if (sort_mode < 0 || sort_mode > 2) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0, 1 or 2");
+  if (sort_mode < 0 || sort_mode > 3) return fail(c, VSF_ERR_BAD_ARG, "sort_mode must be 0 .. 3");
+  if (sort_mode == VSF_SORT_EXACT_AUTO)
+    sort_mode = (c->host_threads >= 8 || c->rows_pad > sort_exact_max_rows()) ? VSF_SORT_EXACT_HOST : VSF_SORT_EXACT_DEVICE;
   if (sort_mode == 2 && c->rows_pad > sort_exact_max_rows())
     return fail(c, VSF_ERR_CAPACITY, "sort_mode 2 (reference order on the device) needs max_features <= 24576; use sort_mode 1");
   if (n < 0 || (n > 0 && !desc) || (n > 0 && stride < size_t(c->desc_bytes))) return fail(c, VSF_ERR_BAD_ARG, "bad frame");
@@ -1250,11 +1296,23 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
       specs.back().t_exp_int8 = exp_int8;
     }
   }
+  // A device sort (modes 0, 2) runs on its own stream while the main stream goes on with the next
+  // frame; that frame's persistent distance kernel then leaves a few SMs to it (one sort CTA per
+  // list, at most sm_count / 14 SMs), which costs the distance kernel a few per cent and takes
+  // the sort off the frame stream's critical path
+  const bool side_sort = sort_mode != 1 && nf > 0 && !(c->engine_flags & 64);
+  c->reserve_sms = side_sort ? std::min(nf, std::max(1, c->sm_count / 14)) : 0;
+  if (side_sort && c->reserve_override >= 0) c->reserve_sms = std::min(c->reserve_override, c->sm_count - 1);
   c->match_base = f.d_matches;
+  c->count_base = f.d_counts;
   c->mir_dm = nullptr;
   c->mir_dcounts = f.dm_counts;
   c->mir_hcounts = f.h_counts;
   rc = run_knn(c, specs, ratio, sort_mode == 1);
+  c->reserve_sms = 0;
+  const unsigned half = (c->sort_rr++) & 1u;
+  cudaStream_t side = c->sort_stream[half];
+  cudaStream_t sort_on = side_sort ? side : c->stream;
   if (rc == VSF_OK && sort_mode != 1 && nf > 0) {
     // device sort (stable, or the replay of the reference's std::sort) + cut; the kept counts go
     // to the flight's mapped counters
@@ -1262,16 +1320,27 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
     const int* cp[kMaxProblems];
     for (int j = 0; j < nf; ++j) {
       mp[j] = c->region_ptr(j);
-      cp[j] = c->d_match_count + j;
+      cp[j] = c->count_base + j;
     }
-    const cudaError_t e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, 8 * c->row_bytes + 1,
-                                          max_cnt, sort_mode == 2, c->sort_depth_override, c->stream);
-    if (e != cudaSuccess) {
-      c->err = std::string("launch_sort_cut: ") + cudaGetErrorString(e);
-      rc = VSF_ERR_CUDA;
+    void* gs = nullptr;
+    if ((rc = sort_scratch(c, sort_mode == 2, &gs, half)) == VSF_OK) {
+      cudaError_t e = cudaSuccess;
+      if (side_sort) {
+        e = cudaEventRecord(c->ev_main, c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, c->ev_main, 0);
+      }
+      if (e == cudaSuccess)
+        e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, 8 * c->row_bytes + 1,
+                            gs ? c->rows_pad : max_cnt, sort_mode == 2, c->sort_depth_override, gs, sort_on);
+      if (e == cudaSuccess && side_sort) e = cudaEventRecord(f.ev_sort, side);
+      if (e != cudaSuccess) {
+        c->err = std::string("launch_sort_cut: ") + cudaGetErrorString(e);
+        rc = VSF_ERR_CUDA;
+      }
     }
   }
   c->match_base = c->d_matches;
+  c->count_base = c->d_match_count;
   c->mir_dm = c->dm_matches;
   c->mir_dcounts = c->dm_region_counts;
   c->mir_hcounts = c->h_region_counts;
@@ -1283,7 +1352,7 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   // ---- download stream: the lists leave through the copy engine while the main stream goes on
   // with the next frame.  Their lengths are only known on the device, so each list is copied up
   // to its bound (a past frame's row count, cut by best_percent for the sorted lists).
-  VSF_CUDA(c, cudaStreamWaitEvent(c->down_stream, f.ev_chain, 0));
+  VSF_CUDA(c, cudaStreamWaitEvent(c->down_stream, (side_sort && nf > 0) ? f.ev_sort : f.ev_chain, 0));
   f.d2h_bytes = size_t(nf) * sizeof(int);
   if (nf > 0 && max_cnt > 0) {
     const size_t pitch = size_t(c->rows_pad) * 16;
@@ -1891,8 +1960,24 @@ extern "C" int vsf_debug_sort_device(vsf_ctx* c, const vsf_dmatch* matches, int 
   VSF_CUDA(c, cudaMemcpyAsync(c->d_match_count, c->h_counts, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   const vsf_dmatch* mp[1] = {c->d_matches};
   const int* cp[1] = {c->d_match_count};
-  VSF_CUDA(c, launch_sort_cut(mp, cp, 1, best_percent, c->d_fm, c->rows_pad, c->d_fm_count, 8 * c->row_bytes + 1, n,
-                              exact, c->sort_depth_override, c->stream));
+  void* gs = nullptr;
+  int rcs = sort_scratch(c, exact, &gs);
+  if (rcs) return rcs;
+  long long* d_trace = nullptr;
+  if (std::getenv("VSF_SORT_TRACE")) {
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&d_trace), 16 * sizeof(long long)));
+    VSF_CUDA(c, cudaMemset(d_trace, 0, 16 * sizeof(long long)));
+  }
+  VSF_CUDA(c, launch_sort_cut(mp, cp, 1, best_percent, c->d_fm, c->rows_pad, c->d_fm_count, 8 * c->row_bytes + 1,
+                              gs ? c->rows_pad : n, exact, c->sort_depth_override, gs, c->stream, d_trace));
+  if (d_trace) {
+    long long t[16];
+    VSF_CUDA(c, cudaStreamSynchronize(c->stream));
+    VSF_CUDA(c, cudaMemcpy(t, d_trace, sizeof(t), cudaMemcpyDeviceToHost));
+    cudaFree(d_trace);
+    std::fprintf(stderr, "sort trace n=%d exact=%d: P1 %lld P2 %lld P3 %lld P4 %lld P5 %lld P6 %lld load %lld total %lld levels %lld n_eff %lld\n",
+                 n, exact, t[0], t[1], t[2], t[3], t[4], t[5], t[7], t[8], t[9], t[11]);
+  }
   VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_fm_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   const int keep = c->h_counts[0];
