@@ -94,6 +94,11 @@ struct vsf_ctx {
   // automatic mode: tensor cores from this many comparisons per batch (measured crossover,
   // tools/engine_crossover.py: 1e6 POPC 12 us vs 20; 4e6 18 vs 14; 2.5e7 52 vs 24)
   double tc_auto_min_cmp = 3e6;
+  // the same for blocking one-frame calls (vsf_knn2 / vsf_get_matches / vsf_observe_*).  Measured
+  // (tools latency probe, C2 2000 x 2000): a higher threshold does NOT pay - the single POPC
+  // launch saves ~15 us of host launch time but its kernel is ~15 us longer, 40 us either way, and
+  // the whole C3 frame gets slower (99 vs 90 us) - so both thresholds are the same.
+  double tc_auto_min_cmp_latency = 3e6;
   uint8_t* d_train_exp[kTcMaxTrains] = {nullptr, nullptr};  // +-1 expanded train images
 
   int rows_pad = 0;    // max_features rounded up to 128
@@ -358,7 +363,10 @@ static void plan_tc_partition(TcBatch* tbp, int qblocks, int sm, int force_split
 
 // Build the batch, choose (R, split) and launch kernel 1.
 // mirror: also store the match lists / counts into the mapped host buffers (host-API calls)
-static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio, bool mirror = false) {
+// latency: the call is a blocking / one-frame-at-a-time one (its own automatic-engine threshold,
+// see tc_auto_min_cmp_latency).
+static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio, bool mirror = false,
+                   bool latency = false) {
   if (specs.empty()) return VSF_OK;
   c->main_dirty = true;
   if (int(specs.size()) > kMaxProblems) return fail(c, VSF_ERR_CAPACITY, "too many problems in one batch");
@@ -429,7 +437,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       train_of[i] = k;
     }
   }
-  if (engine == 0) engine = (tc_ok && double(total_q) * double(max_nt) >= c->tc_auto_min_cmp) ? 2 : 1;
+  const double auto_min = latency ? c->tc_auto_min_cmp_latency : c->tc_auto_min_cmp;
+  if (engine == 0) engine = (tc_ok && double(total_q) * double(max_nt) >= auto_min) ? 2 : 1;
   if (engine >= 2 && !tc_ok) engine = 1;
   c->last_engine = engine;
 
@@ -861,11 +870,15 @@ static int knn_pair(vsf_ctx* c, const uint8_t* q, int nq, size_t qs, const uint8
                     double ratio, bool mirror = false) {
   cudaSetDevice(c->device);
   int rc;
+  static const bool timing = std::getenv("VSF_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   if ((rc = upload_desc(c, 0, q, nq, qs, c->d_raw_left))) return rc;
   if ((rc = upload_desc(c, 1, t, nt, ts, c->d_raw_right))) return rc;
+  if (timing) std::fprintf(stderr, "  knn_pair: staging + 2 cudaMemcpyAsync %.1f us\n",
+                           std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
   std::vector<ProblemSpec> specs(1);
   specs[0] = ProblemSpec{c->d_raw_left, nq, nullptr, c->d_raw_right, nt, nullptr, c->window + 1};
-  return run_knn(c, specs, ratio, mirror);
+  return run_knn(c, specs, ratio, mirror, true);
 }
 
 extern "C" int vsf_knn2(vsf_ctx* c, const uint8_t* q, int nq, size_t q_stride, const uint8_t* t, int nt,
@@ -894,13 +907,22 @@ extern "C" int vsf_get_matches(vsf_ctx* c, const uint8_t* q, int nq, size_t q_st
   if (!n_out || cap < 0 || (cap > 0 && !out)) return fail(c, VSF_ERR_BAD_ARG, "null output");
   *n_out = 0;
   if (nq == 0) return VSF_OK;
+  static const bool timing = std::getenv("VSF_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   if ((rc = knn_pair(c, q, nq, q_stride, t, nt, t_stride, ratio, true))) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   const int region = c->window + 1;
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));   // survivors + count are already in mapped host memory
+  const auto t2 = std::chrono::steady_clock::now();
   const int n = c->h_region_counts[region];
   if (n > cap) return fail(c, VSF_ERR_CAPACITY, "output capacity too small");
   if (n > 0) std::memcpy(out, c->h_matches + size_t(region) * c->rows_pad, size_t(n) * sizeof(vsf_dmatch));
   *n_out = n;
+  if (timing) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    std::fprintf(stderr, "vsf_get_matches: enqueue %.1f us, wait %.1f us, copy out %.1f us\n", us(t0, t1), us(t1, t2), us(t2, t3));
+  }
   return VSF_OK;
 }
 
@@ -1461,7 +1483,7 @@ static int stereo_launch(vsf_ctx* c, const uint8_t* d_dl, int nl, const uint8_t*
   std::vector<ProblemSpec> specs(1);
   specs[0] = ProblemSpec{d_dl, nl, nullptr, d_dr, nr, nullptr, c->window + 1};
   int rc;
-  if ((rc = run_knn(c, specs, ratio))) return rc;
+  if ((rc = run_knn(c, specs, ratio, false, true))) return rc;
   fill_stereo_args(c, *a, F);
   a->desc_left = reinterpret_cast<const uint32_t*>(d_dl);
   a->desc_right = reinterpret_cast<const uint32_t*>(d_dr);
@@ -1721,7 +1743,7 @@ extern "C" int vsf_observe_submit(vsf_ctx* c, uint64_t frame_id, const vsf_keypo
   c->mir_dm = f.dm_lists;
   c->mir_dcounts = f.dm_counts;
   c->mir_hcounts = f.h_counts;
-  rc = run_knn(c, specs, p->nn_match_ratio, true);
+  rc = run_knn(c, specs, p->nn_match_ratio, true, true);
   c->mir_dm = c->dm_matches;
   c->mir_dcounts = c->dm_region_counts;
   c->mir_hcounts = c->h_region_counts;
