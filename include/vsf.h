@@ -103,7 +103,8 @@ int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
  * csrc/knn2_tc_kernel.cu), 3 = tensor cores, e4m3 operands (kind::f8f6f4).
  * Engine 2 exists for every descriptor width (csrc/knn2_tc64_kernel.cu for 33..64
  * bytes), engine 3 for desc_bytes <= 32 only.  Every engine produces bit-identical
- * results.  flags: pass 0; 64 keeps the device sort of the pipelined frame stream (sort_mode 0 / 2)
+ * results.  flags: pass 0; 128 keeps 33..64-byte rows on the single-CTA tensor kernel instead of
+ * CTA pairs (A/B timing); 64 keeps the device sort of the pipelined frame stream (sort_mode 0 / 2)
  * on the main stream instead of a side stream with reserved SMs (A/B timing); 16 / 32 record the per-CTA / per-kernel
  * timelines read by vsf_debug_tc_trace / vsf_debug_kernel_trace (16, and the
  * timing-only flags 2 / 4, exist only in libraries built with VSF_TC_TRACE /

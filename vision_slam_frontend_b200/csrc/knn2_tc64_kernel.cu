@@ -359,6 +359,305 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same engine on CTA PAIRS (cta_group::2): two SMs of one TPC share every MMA.
+//   work unit  256 queries: CTA r of the pair holds queries [128 r, 128 r + 128) (its A image)
+//   train tile 256 rows:    CTA r loads image tile 2j + r (its half of B, 64 KB per stage)
+//   MMA        M = 256, N = 256, K = 32, issued by the pair's rank-0 CTA for both; each CTA gets
+//              its 128 queries x 256 train rows in its own TMEM (two accumulators of 256 columns)
+// so one 64 KB tile a CTA pulls from L2 now feeds 256 queries instead of 128 and every SM reads
+// half of B from its partner's shared memory instead of its own: the two limits of the
+// single-CTA kernel (L2 -> SM tile traffic, shared-memory operand bandwidth) both halve.
+// Barriers: TMA -> MMA per CTA (the partner's "tile landed" is relayed to rank 0 by the partner's
+// otherwise idle MMA warp), MMA -> TMA / MMA -> epilogue by multicast commits, epilogue -> MMA and
+// "queries expanded" by remote arrivals on rank 0's barriers.
+namespace pair {
+
+constexpr int kQP = 2 * kQ;              // queries per unit (pair)
+constexpr int kTP = 2 * kT;              // train rows per pair tile
+constexpr int kBarriersP = 3 * kStages + 5;
+constexpr int kSmemBytesP = kABytes + kStages * kBBytes + kBarriersP * 8 + 16 + 128;
+
+__device__ __forceinline__ Walk walk_begin_pair(const TcBatch& tc) {
+  Walk w;
+  const long long pair_id = blockIdx.x >> 1;
+  w.p = 0;
+  w.x = pair_id * tc.total / tc.grid;
+  w.end = (pair_id + 1) * tc.total / tc.grid;
+  const long long gqb = w.x / tc.pieces;
+  w.gqb = int(gqb);
+  w.t0 = int(w.x - gqb * tc.pieces);
+  w.slot = int(pair_id) - tc_owner(gqb * tc.pieces, tc.total, tc.grid);
+  return w;
+}
+__device__ __forceinline__ Unit walk_unit_pair(const KnnBatch& batch, const TcBatch& tc, const Walk& w) {
+  Unit U;
+  U.len = int(min((long long)(tc.pieces - w.t0), w.end - w.x));
+  int p = w.p;
+  while (w.gqb >= tc.qb_begin[p + 1]) ++p;
+  U.problem = p;
+  U.qb = w.gqb - tc.qb_begin[p];
+  U.slot = w.slot;
+  const KnnProblem& P = batch.p[p];
+  int nq = P.nq, nt = P.nt;
+  if (P.nq_dev) nq = min(nq, *P.nq_dev);
+  if (P.nt_dev) nt = min(nt, *P.nt_dev);
+  U.nq = nq;
+  U.nt = nt;
+  U.q0 = U.qb * kQP;
+  U.skip = U.q0 >= nq;
+  const int tile0 = min(tc.tiles, w.t0 * tc.tiles_per_piece);
+  const int tile1 = min(tc.tiles, (w.t0 + U.len) * tc.tiles_per_piece);
+  U.t_begin = min(nt, tile0 * kTP);
+  U.t_end = min(nt, tile1 * kTP);
+  U.ntiles = (U.t_end - U.t_begin + kTP - 1) / kTP;
+  return U;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kStages * kBBytes);
+  uint64_t* full = bars;                   // [kStages] this CTA's TMA -> (rank 0: MMA, rank 1: relay)
+  uint64_t* empty = bars + kStages;        // [kStages] MMA -> TMA, both CTAs (multicast commit)
+  uint64_t* pfull = bars + 2 * kStages;    // [kStages] rank 0 only: the partner's tile has landed
+  uint64_t* tfull = bars + 3 * kStages;    // [2] MMA -> epilogue, both CTAs (multicast commit)
+  uint64_t* tempty = tfull + 2;            // [2] rank 0 only: both CTAs' epilogues -> MMA
+  uint64_t* aready = tempty + 2;           // [1] rank 0 only: both CTAs' queries are expanded
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kBarriersP);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&pfull[s], 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps);          // 8 local + 8 remote warps per accumulator
+    }
+    mbar_init(aready, 2 * kEpiWarps);
+    mbar_fence_init();
+  }
+  if (warp == kEpiWarps + 1) tc::tmem_alloc_2cta<kTmemCols>(s_tmem);
+  tc::fence_before_sync();
+  tc::cluster_sync();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  Walk wk = walk_begin_pair(tc);
+  const uint32_t lbo = uint32_t(kQ * 16);   // = kT * 16: K-chunk stride of both operand images
+  const uint32_t sbo = 128u;
+
+  if (warp == kEpiWarps) {
+    // ------------------------------ TMA producer (each CTA: its half of B) ------------------------------
+    Unit U;
+    if (lane == 0 && walk_more(wk)) U = walk_unit_pair(batch, tc, wk);
+    pdl_wait();
+    pdl_launch_dependents();
+    if (lane == 0) {
+      uint32_t it = 0;
+      while (walk_more(wk)) {
+        if (!U.skip) {
+          const uint8_t* src = tc.t_exp[U.problem] + (size_t(U.t_begin / kT) + rank) * kBBytes;
+          for (int k = 0; k < U.ntiles; ++k, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full[s], kBBytes);
+            tma_load_1d(sB + size_t(s) * kBBytes, src + size_t(2 * k) * kBBytes, kBBytes, &full[s]);
+          }
+        }
+        walk_next(wk, U);
+        if (walk_more(wk)) U = walk_unit_pair(batch, tc, wk);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kEpiWarps + 1) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (lane == 0 && rank == 0) {
+      // ------------------------------ MMA issuer (rank 0, for the pair) ------------------------------
+      uint32_t it = 0, unit_it = 0, acc_use[2] = {0u, 0u};
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      const uint32_t idesc = tc::instr_desc(true, 256, 256);
+      while (walk_more(wk)) {
+        const Unit U = walk_unit_pair(batch, tc, wk);
+        walk_next(wk, U);
+        if (U.skip || U.ntiles == 0) continue;
+        for (int k = 0; k < U.ntiles; ++k, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          const int a = k & 1;                       // accumulator of this tile
+          mbar_wait(&full[s], ph);
+          tc::mbar_wait_cluster(&pfull[s], ph);
+          if (k == 0) tc::mbar_wait_cluster(aready, unit_it & 1u);
+          tc::mbar_wait_cluster(&tempty[a], (acc_use[a] & 1u) ^ 1u);
+          tc::fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < kChunks / 2; ++kk) {   // one MMA consumes K = 32 bytes = 2 chunks
+            const uint64_t ad = tc::smem_desc(a_addr + uint32_t(kk) * 2u * (kQ * 16), lbo, sbo);
+            const uint64_t bd = tc::smem_desc(b_addr + s * kBBytes + uint32_t(kk) * 2u * (kT * 16), lbo, sbo);
+            tc::mma_ss_2cta<true>(tmem_base + uint32_t(a) * 256u, ad, bd, idesc, kk > 0 ? 1u : 0u);
+          }
+          tc::commit_2cta(&tfull[a], 3);
+          ++acc_use[a];
+          tc::commit_2cta(&empty[s], 3);
+        }
+        ++unit_it;
+      }
+    } else if (lane == 0) {
+      // ------------------------------ relay (rank 1): "my half of the tile has landed" -> rank 0 ------------------------------
+      uint32_t it = 0;
+      while (walk_more(wk)) {
+        const Unit U = walk_unit_pair(batch, tc, wk);
+        walk_next(wk, U);
+        if (U.skip || U.ntiles == 0) continue;
+        for (int k = 0; k < U.ntiles; ++k, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc::mbar_arrive_cluster(&pfull[s], 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ query expansion + epilogue ------------------------------
+    // warp = (column half ch) * 8 + (tile parity h) * 4 + (TMEM lane quarter); a warp reduces
+    // 128 of the 256 columns of its parity's accumulator
+    const int h = (warp >> 2) & 1;
+    const int ch = warp >> 3;
+    const int r = (warp & 3) * 32 + lane;          // TMEM lane = query row of this CTA's half of the unit
+    const int g = h * 2 + ch;                      // which 16 bytes of the query row this thread expands
+    const uint32_t taddr = tmem_base + (uint32_t((warp & 3) * 32) << 16) + uint32_t(h * 256 + ch * (kTP / 2));
+    constexpr int NB = kEpiCols / kTcBucket;       // buckets per 64-column load
+    constexpr int TB = kTP / kTcBucket;            // buckets per pair tile
+    constexpr int RPB = kTcBucket / 2;             // packed registers per bucket
+    uint32_t acc_use = 0;
+
+    auto load_query = [&](const Unit& V) -> uint4 {
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      const int q = V.q0 + int(rank) * kQ + r;
+      if (!V.skip && V.ntiles > 0 && q < V.nq)
+        w = __ldg(reinterpret_cast<const uint4*>(batch.p[V.problem].q + size_t(q) * 16) + g);
+      return w;
+    };
+    auto expand_query = [&](const uint4& qw) {
+      const uint32_t words[4] = {qw.x, qw.y, qw.z, qw.w};
+      uint8_t* dst = sA + size_t(r) * 16 + size_t(g * 8) * (kQ * 16);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t b16 = (words[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+        *reinterpret_cast<uint4*>(dst + size_t(c) * (kQ * 16)) = expand16(b16);
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(aready, 0);
+    };
+    Unit U;
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    bool expanded = false;
+    if (walk_more(wk)) {
+      U = walk_unit_pair(batch, tc, wk);
+      w = load_query(U);
+      if (!(U.skip || U.ntiles == 0)) {
+        expand_query(w);
+        expanded = true;
+      }
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    while (walk_more(wk)) {
+      walk_next(wk, U);
+      const bool more = walk_more(wk);
+      Unit Un;
+      uint4 wn = make_uint4(0u, 0u, 0u, 0u);
+      const KnnProblem& P = batch.p[U.problem];
+      const int q = U.q0 + int(rank) * kQ + r;
+      uint2* part = reinterpret_cast<uint2*>(batch.partial) +
+                    (size_t(P.row0 + q) * (tc.slots * kParts) + U.slot * kParts + g);
+      if (U.skip || U.ntiles == 0) {
+        if (!U.skip && q < U.nq) *part = make_uint2(uint32_t(kKeyNone), uint32_t(kKeyNone));
+        if (more) {
+          Un = walk_unit_pair(batch, tc, wk);
+          wn = load_query(Un);
+        }
+        U = Un; w = wn;
+        continue;
+      }
+      if (!expanded) expand_query(w);
+      expanded = false;
+      if (more) {
+        Un = walk_unit_pair(batch, tc, wk);
+        wn = load_query(Un);
+      }
+      int m1 = kKeyNone, m2 = kKeyNone;
+      for (int k = h; k < U.ntiles; k += 2, ++acc_use) {   // this warp's parity of the unit's tiles
+        mbar_wait(&tfull[h], acc_use & 1u);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {             // two loads of 64 packed columns
+          const int row0 = U.t_begin + k * kTP + ch * (kTP / 2) + half * kEpiCols;
+          const int kbase = kBucketIdMask - row0 / kTcBucket;
+          uint32_t v[32];
+          tc::tmem_ld_32x32_pack16(taddr + uint32_t(half * kEpiCols), v);
+          tc::tmem_ld_wait();
+          if (half == 1) {                                  // the accumulator may be overwritten now
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(&tempty[h], 0);
+          }
+          const bool full_tile = row0 + kEpiCols <= U.t_end;   // warp-uniform
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            uint32_t* b = &v[j * RPB];
+            if (!full_tile) {
+              const int valid = U.t_end - (row0 + j * kTcBucket);
+              if (valid <= 0) continue;
+              if (valid < kTcBucket) {
+#pragma unroll
+                for (int i = 0; i < RPB; ++i) {
+                  if (2 * i >= valid) b[i] = 0x80008000u;
+                  else if (2 * i + 1 >= valid) b[i] = (b[i] & 0xFFFFu) | 0x80000000u;
+                }
+              }
+            }
+            uint32_t mm = b[0];
+#pragma unroll
+            for (int i = 1; i < RPB; ++i) mm = __vmaxs2(mm, b[i]);
+            const int bm = max(int(short(mm & 0xFFFFu)), int(mm) >> 16);
+            const int key = bm * (1 << kBucketIdBits) + (kbase - j);
+            m2 = max(m2, min(m1, key));
+            m1 = max(m1, key);
+          }
+        }
+      }
+      if (q < U.nq) *part = make_uint2(uint32_t(m1), uint32_t(m2));
+      // every MMA of the unit has completed (in both CTAs: the commits are multicast) once both
+      // parities have seen their last tile: only then may the next unit's queries replace this one's
+      epi_barrier();
+      U = Un; w = wn;
+    }
+  }
+
+  tc::fence_before_sync();
+  tc::cluster_sync();          // nobody leaves while the partner may still arrive on its barriers
+  if (warp == kEpiWarps + 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc_2cta<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace pair
+
+// ---------------------------------------------------------------------------------------------
 // Refine: as knn2_tc_refine_kernel, for 16-word rows.  Two lanes per query (best / second-best
 // bucket); a warp stages 4 rows of every pair per pass (256 contiguous bytes per pair).
 constexpr int kRefineQB = 64;
@@ -406,7 +705,7 @@ knn2_tc64_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_con
   int key = kKeyNone;
   if (q < nq) {
     int b1 = kKeyNone, b2 = kKeyNone;
-    const int nseg = tc_block_segments(tc, tc.qb_begin[blockIdx.y] + q / kQ);
+    const int nseg = tc_block_segments(tc, tc.qb_begin[blockIdx.y] + q / tc.unit_q);
     const uint4* part = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(batch.partial) +
                                                         size_t(P.row0 + q) * (tc.slots * kParts));
     auto merge = [&](int a1, int a2) {
@@ -515,7 +814,15 @@ cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_n
   if (e != cudaSuccess) return e;
   const bool p = pdl != 0;
   if (ev) cudaEventRecord(ev[0], stream);
-  e = w64::launch_pdl(w64::knn2_tc64_kernel, dim3(tc.grid), dim3(w64::kThreads), w64::kSmemBytes, stream, p, batch, tc);
+  if (tc.unit_q == 2 * w64::kQ) {
+    // CTA pairs: tc.grid counts pairs; cluster dimensions are a compile-time attribute of the kernel
+    e = cudaFuncSetAttribute(w64::pair::knn2_tc64_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::pair::kSmemBytesP);
+    if (e != cudaSuccess) return e;
+    e = w64::launch_pdl(w64::pair::knn2_tc64_pair_kernel, dim3(2 * tc.grid), dim3(w64::kThreads), w64::pair::kSmemBytesP, stream, p,
+                        batch, tc);
+  } else {
+    e = w64::launch_pdl(w64::knn2_tc64_kernel, dim3(tc.grid), dim3(w64::kThreads), w64::kSmemBytes, stream, p, batch, tc);
+  }
   if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[1], stream);
   dim3 rgrid((max_nq + w64::kRefineQB - 1) / w64::kRefineQB, batch.num_problems);

@@ -445,8 +445,17 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   if (engine >= 2) {
     const int int8 = engine == 2;
     const bool wide = c->words == 16;                // 64-byte rows: knn2_tc64_kernel.cu
-    const int unit_q = wide ? 128 : kTcQ;            // queries per work unit
-    const int tile_rows = wide ? 128 : kTcTileRows;  // train rows per tile
+    // 64-byte rows run on CTA pairs (cta_group::2, 256 queries x 256 train rows per MMA) once the
+    // launch has work for every pair; engine flag 128 keeps the single-CTA kernel (A/B timing)
+    const int sm_avail = std::max(1, c->sm_count - c->reserve_sms);
+    bool pair = wide && !(c->engine_flags & 128) && sm_avail >= 2;
+    if (pair) {
+      long long slots = 0;
+      for (const ProblemSpec& sp : specs) slots += (long long)((sp.nq + 255) / 256) * ((max_nt + 255) / 256);
+      pair = slots >= sm_avail / 2;
+    }
+    const int unit_q = wide ? (pair ? 256 : 128) : kTcQ;            // queries per work unit
+    const int tile_rows = wide ? (pair ? 256 : 128) : kTcTileRows;  // train rows per tile
     const int pdl = (c->engine_flags & 8) ? 0 : 1;   // flag 8: ordinary launches (A/B timing)
     if (c->profile) VSF_CUDA(c, cudaEventRecord(c->pev[0], c->stream));
     long long* kt = nullptr;
@@ -488,7 +497,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       tb.trace = c->d_tc_trace;
     }
     // (64-byte rows store 4 partial key pairs per query and segment, 32-byte rows 2)
-    plan_tc_partition(&tb, qblocks, std::max(1, c->sm_count - c->reserve_sms), c->force_split,
+    tb.unit_q = unit_q;
+    plan_tc_partition(&tb, qblocks, pair ? sm_avail / 2 : sm_avail, c->force_split,
                       size_t(row0) * (wide ? 2 : 1), c->partial_cap);
     b.split = tb.slots;
     if (wide)

@@ -96,6 +96,7 @@ struct TcBatch {
   int grid;                            // G: CTAs of knn2_tc_kernel
   int slots;                           // partial segments stored per query row (max over blocks)
   long long total;                     // T = qb_begin[num_problems] * pieces
+  int unit_q;                          // 64-byte engine: queries per block (128: one CTA per unit, 256: a CTA pair per unit)
   int flags;                           // bring-up knobs (timing experiments; results invalid): 2 = skip the bucket reduction, 4 = skip the TMEM loads
   long long* trace;                    // flag 16 (builds with -DVSF_TC_TRACE): per-CTA timeline, kTcTraceSlots values per CTA
 };
