@@ -439,7 +439,7 @@ def run_b200(a):
             ops_per_cmp = 2.0 * 8 * row_bytes
             ops = ops_per_cmp * cmp_per_pose
             bf16 = float(peaks.get("bf16_tflops", 1590.0))
-            kname = ("vsf::w64::knn2_tc64_kernel" if wide else
+            kname = ("vsf::w64::pair::knn2_tc64_pair_kernel (cta_group::2)" if wide else
                      ("vsf::knn2_tc_kernel<int8>" if engine == 2 else "vsf::knn2_tc_kernel<e4m3>"))
             roofline = {
                 "bound": "tensor", "achieved": ops / main_s / 1e12, "peak": 2.0 * bf16, "unit": "TFLOP/s",
