@@ -667,8 +667,12 @@ constexpr int kRefinePitch = kRefineRows * 64 + 16;
 constexpr int kRefinePP = kRefineRows * 4;       // 16-byte pieces of one pair's run of rows (16)
 static_assert(kTcBucket % kRefineRows == 0 && 32 % kRefinePP == 0, "bucket must be a multiple of the refine pass");
 
+// (EXACT2 as in knn2_tc_refine_kernel: false = one lane per query, the second neighbour's distance
+// from the second-best bucket's exact maximum dot, dot = 512 - 2 * hamming)
+template <bool EXACT2>
 __global__ void __launch_bounds__(kRefineThreads)
 knn2_tc64_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
+  constexpr int kQB = EXACT2 ? kRefineQB : 2 * kRefineQB;      // queries per CTA
   __shared__ __align__(16) uint8_t s_stage[kRefineThreads / 32][32 * kRefinePitch];
   const KnnProblem& P = batch.p[blockIdx.y];
   const int tid = threadIdx.x;
@@ -677,9 +681,9 @@ knn2_tc64_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_con
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
   if (P.nt_dev) nt = min(nt, *P.nt_dev);
   const int qb = blockIdx.x;
-  const int q0 = qb * kRefineQB;
-  const int q = q0 + (tid >> 1);
-  const int c = tid & 1;
+  const int q0 = qb * kQB;
+  const int q = q0 + (EXACT2 ? (tid >> 1) : tid);
+  const int c = EXACT2 ? (tid & 1) : 0;
   uint32_t qw[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) qw[i] = 0u;
@@ -702,7 +706,7 @@ knn2_tc64_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_con
   }
   if (q0 >= nq) return;
 
-  int key = kKeyNone;
+  int key = kKeyNone, key2 = kKeyNone;
   if (q < nq) {
     int b1 = kKeyNone, b2 = kKeyNone;
     const int nseg = tc_block_segments(tc, tc.qb_begin[blockIdx.y] + q / tc.unit_q);
@@ -727,9 +731,14 @@ knn2_tc64_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_con
       }
     }
     key = c ? b2 : b1;
+    key2 = b2;
   }
   const int my_row0 = (key == kKeyNone) ? -1 : (kBucketIdMask - (key & kBucketIdMask)) * kTcBucket;
   uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
+  if (!EXACT2 && key2 != kKeyNone) {
+    const int dot = key2 >> kBucketIdBits;
+    k1 = (uint32_t((kRowBytes - dot) >> 1) << kIdxBits) + uint32_t((kBucketIdMask - (key2 & kBucketIdMask)) * kTcBucket);
+  }
   uint8_t* stage = s_stage[warp];
 #pragma unroll 1
   for (int r0 = 0; r0 < kTcBucket; r0 += kRefineRows) {
@@ -761,7 +770,7 @@ knn2_tc64_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_con
     }
     __syncwarp();
   }
-  {
+  if (EXACT2) {
     const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, 1), o2 = __shfl_xor_sync(0xffffffffu, k2, 1);
     top2_merge(k1, k2, o1, o2);
   }
@@ -774,8 +783,17 @@ knn2_tc64_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_con
     batch.knn_out[P.row0 + q] = make_uint4(uint32_t(i0), uint32_t(i1), uint32_t(d0), uint32_t(d1));
     pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
   }
-  const int npass = __syncthreads_count(pass);
-  if (tid == 0) batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
+  if (EXACT2) {
+    const int npass = __syncthreads_count(pass);
+    if (tid == 0) batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
+  } else {
+    const int n0 = __syncthreads_count(pass && tid < kRefineQB);
+    const int n1 = __syncthreads_count(pass && tid >= kRefineQB);
+    if (tid == 0) {
+      batch.qblock_pass[P.qb0 + 2 * qb] = unsigned(n0);
+      batch.qblock_pass[P.qb0 + 2 * qb + 1] = unsigned(n1);
+    }
+  }
 }
 
 template <typename... KArgs, typename... Args>
@@ -825,8 +843,13 @@ cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_n
   }
   if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[1], stream);
-  dim3 rgrid((max_nq + w64::kRefineQB - 1) / w64::kRefineQB, batch.num_problems);
-  e = w64::launch_pdl(w64::knn2_tc64_refine_kernel, rgrid, dim3(w64::kRefineThreads), 0, stream, p, batch, tc);
+  if (batch.exact_second) {
+    dim3 rgrid((max_nq + w64::kRefineQB - 1) / w64::kRefineQB, batch.num_problems);
+    e = w64::launch_pdl(w64::knn2_tc64_refine_kernel<true>, rgrid, dim3(w64::kRefineThreads), 0, stream, p, batch, tc);
+  } else {
+    dim3 rgrid((max_nq + 2 * w64::kRefineQB - 1) / (2 * w64::kRefineQB), batch.num_problems);
+    e = w64::launch_pdl(w64::knn2_tc64_refine_kernel<false>, rgrid, dim3(w64::kRefineThreads), 0, stream, p, batch, tc);
+  }
   if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[2], stream);
   e = launch_knn2_compact(batch, max_nq, p, stream);

@@ -545,8 +545,15 @@ constexpr int kRefinePitch = kRefineRows * 32 + 16;          // bytes per pair i
 constexpr int kRefinePP = kRefineRows * 2;                   // 16-byte pieces of one pair's run of rows
 static_assert(kTcBucket % kRefineRows == 0 && 32 % kRefinePP == 0, "bucket must be a multiple of the refine pass");
 
+// EXACT2 = true: two lanes per query as described (vsf_knn2 reports the second neighbour's index).
+// EXACT2 = false (every other entry point: only the second neighbour's DISTANCE matters, for the
+// ratio test): one lane per query rescans the best bucket and takes the second-best bucket's
+// best distance from its exact maximum dot, dot = 256 - 2 * hamming - half the rows to fetch,
+// half the lanes, 128 queries per CTA.
+template <bool EXACT2>
 __global__ void __launch_bounds__(kRefineThreads)
 knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
+  constexpr int kQB = EXACT2 ? kRefineQB : 2 * kRefineQB;      // queries per CTA
   __shared__ __align__(16) uint8_t s_stage[kRefineThreads / 32][32 * kRefinePitch];
   const KnnProblem& P = batch.p[blockIdx.y];
   const int tid = threadIdx.x;
@@ -558,9 +565,9 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
   if (P.nt_dev) nt = min(nt, *P.nt_dev);
   const int qb = blockIdx.x;
-  const int q0 = qb * kRefineQB;
-  const int q = q0 + (tid >> 1);
-  const int c = tid & 1;                       // 0: best bucket, 1: second-best bucket
+  const int q0 = qb * kQB;
+  const int q = q0 + (EXACT2 ? (tid >> 1) : tid);
+  const int c = EXACT2 ? (tid & 1) : 0;                       // 0: best bucket, 1: second-best bucket
   uint32_t qw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   if (q < nq) {
     const uint4* src = reinterpret_cast<const uint4*>(P.q + size_t(q) * 8);
@@ -580,7 +587,7 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   }
   if (q0 >= nq) return;
 
-  int key = kTcKeySentinel;
+  int key = kTcKeySentinel, key2 = kTcKeySentinel;
   if (q < nq) {
     int b1 = kTcKeySentinel, b2 = kTcKeySentinel;
     // the query block's tile slots were shared out to consecutive CTAs, one partial segment each
@@ -612,10 +619,17 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     }
     (void)np;
     key = c ? b2 : b1;
+    key2 = b2;
   }
   // first train row of this lane's candidate bucket, -1 = none
   const int my_row0 = (key == kTcKeySentinel) ? -1 : (kBucketIdMask - (key & kBucketIdMask)) * kTcBucket;
   uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
+  if (!EXACT2 && key2 != kTcKeySentinel) {
+    // the second-best bucket's best distance is exact (its maximum dot is); its first row stands
+    // in as the index, which nobody reads on this path
+    const int dot = key2 >> kBucketIdBits;
+    k1 = (uint32_t((kTcRowBytes - dot) >> 1) << kIdxBits) + uint32_t((kBucketIdMask - (key2 & kBucketIdMask)) * kTcBucket);
+  }
   uint8_t* stage = s_stage[warp];
 #pragma unroll 1
   for (int r0 = 0; r0 < kTcBucket; r0 += kRefineRows) {
@@ -645,7 +659,7 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     __syncwarp();
   }
   // merge the pair (both lanes end up with the query's exact top-2)
-  {
+  if (EXACT2) {
     const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, 1), o2 = __shfl_xor_sync(0xffffffffu, k2, 1);
     top2_merge(k1, k2, o1, o2);
   }
@@ -659,11 +673,19 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     batch.knn_out[P.row0 + q] = make_uint4(uint32_t(i0), uint32_t(i1), uint32_t(d0), uint32_t(d1));
     pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
   }
-  const int npass = __syncthreads_count(pass);
-  if (tid == 0) {
-    batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
-    ktrace_end(batch.ktrace, 2);
+  // survivor counts per block of kRefineQB (64) queries, which is what the compaction sums
+  if (EXACT2) {
+    const int npass = __syncthreads_count(pass);
+    if (tid == 0) batch.qblock_pass[P.qb0 + qb] = unsigned(npass);
+  } else {
+    const int n0 = __syncthreads_count(pass && tid < kRefineQB);
+    const int n1 = __syncthreads_count(pass && tid >= kRefineQB);
+    if (tid == 0) {
+      batch.qblock_pass[P.qb0 + 2 * qb] = unsigned(n0);
+      batch.qblock_pass[P.qb0 + 2 * qb + 1] = unsigned(n1);
+    }
   }
+  if (tid == 0) ktrace_end(batch.ktrace, 2);
 }
 
 // Ordered compaction of the ratio survivors, one CTA per block of 128 queries: the CTA's
@@ -804,9 +826,15 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
            : launch_pdl(knn2_tc_kernel<false>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
   if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[1], stream);
-  dim3 rgrid((max_nq + kRefineQB - 1) / kRefineQB, batch.num_problems);
   dim3 cgrid((max_nq + kCompactQB - 1) / kCompactQB, batch.num_problems);
-  if ((e = launch_pdl(knn2_tc_refine_kernel, rgrid, dim3(kRefineThreads), 0, stream, p, batch, tc)) != cudaSuccess) return e;
+  if (batch.exact_second) {
+    dim3 rgrid((max_nq + kRefineQB - 1) / kRefineQB, batch.num_problems);
+    e = launch_pdl(knn2_tc_refine_kernel<true>, rgrid, dim3(kRefineThreads), 0, stream, p, batch, tc);
+  } else {
+    dim3 rgrid((max_nq + 2 * kRefineQB - 1) / (2 * kRefineQB), batch.num_problems);
+    e = launch_pdl(knn2_tc_refine_kernel<false>, rgrid, dim3(kRefineThreads), 0, stream, p, batch, tc);
+  }
+  if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[2], stream);
   e = launch_pdl(knn2_compact_kernel, cgrid, dim3(kCompactQB), 0, stream, p, batch);
   if (ev) cudaEventRecord(ev[3], stream);

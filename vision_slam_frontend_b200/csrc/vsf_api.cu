@@ -91,6 +91,7 @@ struct vsf_ctx {
   long long* d_ktrace = nullptr;     // engine flag 32: kernel-level timeline, kKtracePoses records of [5][2]
   long long ktrace_n = 0;
   int last_engine = 0;    // engine the last kNN launch used
+  int want_second_index = 0;   // set around vsf_knn2's launch: the tensor engine's refine must produce the exact idx[1]
   // automatic mode: tensor cores from this many comparisons per batch (measured crossover,
   // tools/engine_crossover.py: 1e6 POPC 12 us vs 20; 4e6 18 vs 14; 2.5e7 52 vs 24)
   double tc_auto_min_cmp = 3e6;
@@ -374,6 +375,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   std::memset(&b, 0, sizeof(b));
   b.num_problems = int(specs.size());
   b.ratio = ratio;
+  b.exact_second = c->want_second_index;
   b.knn_out = c->d_knn_out;
   b.partial = c->d_partial;
   b.qblock_arrivals = c->d_qblock_arrivals;
@@ -897,7 +899,10 @@ extern "C" int vsf_knn2(vsf_ctx* c, const uint8_t* q, int nq, size_t q_stride, c
   if (rc) return rc;
   if (nq == 0) return VSF_OK;
   if (!idx || !dist) return fail(c, VSF_ERR_BAD_ARG, "null output");
-  if ((rc = knn_pair(c, q, nq, q_stride, t, nt, t_stride, 1.0))) return rc;
+  c->want_second_index = 1;
+  rc = knn_pair(c, q, nq, q_stride, t, nt, t_stride, 1.0);
+  c->want_second_index = 0;
+  if (rc) return rc;
   VSF_CUDA(c, cudaMemcpyAsync(c->h_knn, c->d_knn_out, size_t(nq) * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < nq; ++i) {

@@ -46,6 +46,9 @@ struct KnnBatch {
   int num_problems;
   int split;               // number of train-dimension splits (gridDim.z)
   double ratio;            // nn_match_ratio, compared in double like the reference
+  int exact_second;        // tensor engine's refine: 1 = rescan the second-best bucket too, so that the
+                           // second neighbour's INDEX is exact (vsf_knn2); 0 = take its distance from the
+                           // bucket's exact maximum dot, which is all the ratio test needs
   uint4* knn_out;          // [rows] {idx0, idx1, d0, d1}
   uint2* partial;          // [rows][split] partial top-2 keys (split > 1)
   unsigned* qblock_arrivals;  // [qblocks]   self-resetting counters
