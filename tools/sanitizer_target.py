@@ -62,4 +62,43 @@ with vsf.Context(device=0, max_features=2600, desc_bytes=61, window=2) as ctx:
         idx, dist = ctx.knn2(Q, T)
         ei, ed = native.knn2_hamming(Q, T)
         assert (idx == ei).all() and (dist == ed).all()
+# round 2: the CTA-pair kernel (enough work for every pair: 3600 x 3600 at 61 bytes), both refine variants
+with vsf.Context(device=0, max_features=3600, desc_bytes=61, window=2) as ctx:
+    ctx.set_engine(2, 0)
+    Q, T = synth.descriptor_pair(3600, 3500, width=61, seed=12)
+    idx, dist = ctx.knn2(Q, T)
+    ei, ed = native.knn2_hamming(Q, T)
+    assert (idx == ei).all() and (dist == ed).all()
+    assert (ctx.get_matches(Q, T, ratio) == native.get_matches(Q, T, ratio)).all()
+# round 2: the exact device sort (all three scratch paths: short list, shared-memory scratch, heapsort fallback),
+# the side-stream sort of the pipelined path, the pipelined whole-frame path
+from vision_slam_frontend_b200 import capi
+with vsf.Context(device=0, max_features=4096, desc_bytes=32, window=3) as ctx:
+    rng = np.random.default_rng(1)
+    for n in (10, 300, 4000):
+        m = np.zeros(n, vsf.DMATCH_DTYPE)
+        m["queryIdx"] = np.arange(n); m["trainIdx"] = np.arange(n); m["distance"] = rng.integers(0, 30, n).astype(np.float32)
+        ctx.debug_sort_device(m, 0.3, True)
+    ctx.set_option(capi.OPT_DEBUG_SORT_DEPTH, 1)
+    ctx.debug_sort_device(m, 0.3, True)
+    ctx.set_option(capi.OPT_DEBUG_SORT_DEPTH, -1)
+    frames = [synth.synth_pose(1300 - 53 * (p % 4), p, 130, 17) for p in range(10)]
+    for p, D in enumerate(frames):
+        if ctx.window_in_flight() == vsf.PIPELINE_DEPTH:
+            ctx.window_collect()
+        ctx.window_submit(100 + p, D, ratio, 0.3, 2, False)
+    while ctx.window_in_flight():
+        ctx.window_collect()
+K = synth.KITTI_K.astype(np.float32)
+with vsf.Context(device=0, max_features=2048, desc_bytes=32, window=3) as ctx:
+    for p, (kl, dl, kr, dr) in enumerate(synth.stereo_sequence(6, 900, seed=7)):
+        ctx.observe_submit(p, kl, dl, kr, dr, F, P1, P2, K, np.zeros(5, np.float32), ratio)
+        if ctx.observe_in_flight() >= 3:
+            ctx.observe_collect()
+    while ctx.observe_in_flight():
+        ctx.observe_collect()
+with vsf.Context(device=0, max_features=20000, desc_bytes=32, window=2) as ctx:   # exact sort with global scratch
+    m = np.zeros(18000, vsf.DMATCH_DTYPE)
+    m["queryIdx"] = np.arange(18000); m["distance"] = np.random.default_rng(2).integers(0, 40, 18000).astype(np.float32)
+    ctx.debug_sort_device(m, 0.3, True)
 print("sanitizer target ok")
