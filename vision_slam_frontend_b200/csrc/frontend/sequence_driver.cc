@@ -85,7 +85,8 @@ int main(int argc, char** argv) {
     }
 
     const auto t0 = std::chrono::steady_clock::now();
-    const slam::SLAMProblemPiece piece = slam::RunSequenceShard(rig, source, first, last, in_flight);
+    double host_us[3] = {0, 0, 0};
+    const slam::SLAMProblemPiece piece = slam::RunSequenceShard(rig, source, first, last, in_flight, host_us);
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
     std::vector<slam::SLAMProblemPiece> pieces;
@@ -107,8 +108,9 @@ int main(int argc, char** argv) {
     } else {
       pieces.push_back(piece);
     }
-    std::fprintf(stderr, "rank %d: poses [%llu, %llu) in %.3f s (%.1f poses/s incl. halo), %u nodes, %u vision factors\n",
-                 rank, first, last, el, double(last - first) / el, piece.n_nodes, piece.n_vision_factors);
+    std::fprintf(stderr, "rank %d: poses [%llu, %llu) in %.3f s incl. context creation, %u nodes, %u vision factors; host per frame: "
+                 "source %.0f us, SubmitFeatures %.0f us, CollectFeatures %.0f us\n",
+                 rank, first, last, el, piece.n_nodes, piece.n_vision_factors, host_us[0], host_us[1], host_us[2]);
     if (rank == 0) {
       const std::vector<uint8_t> wire = slam::MergeSLAMProblemPieces(pieces);
       std::ofstream f(out_path, std::ios::binary);

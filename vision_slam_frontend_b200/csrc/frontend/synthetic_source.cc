@@ -1,7 +1,10 @@
 #include "synthetic_source.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -194,7 +197,7 @@ SLAMProblemPiece SLAMProblemPiece::Unpack(const uint8_t* d, size_t n) {
 }
 
 SLAMProblemPiece RunSequenceShard(const FrontendConfig& rig, const SyntheticStereoSource& source, uint64_t first,
-                                  uint64_t last, int in_flight) {
+                                  uint64_t last, int in_flight, double* host_us) {
   Frontend fe(rig);
   const uint64_t halo_first = Frontend::ShardHaloStart(first, rig.frame_life_);
   fe.StartShard(halo_first, first);
@@ -206,14 +209,29 @@ SLAMProblemPiece RunSequenceShard(const FrontendConfig& rig, const SyntheticSter
   std::vector<cv::KeyPoint> lk, rk;
   cv::Mat ld, rd;
   const int depth = std::max(1, std::min(in_flight, Frontend::MaxInFlight()));
+  double t_gen = 0, t_submit = 0, t_collect = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (uint64_t p = halo_first; p < last; ++p) {
     source.Odometry(p, &t, &q, &ts);
     fe.ObserveOdometry(t, q, ts);
+    const double t0 = now();
     source.Frame(p, &lk, &ld, &rk, &rd);
-    if (!fe.SubmitFeatures(lk, ld, rk, rd, ts)) continue;
-    while (fe.InFlight() >= depth) fe.CollectFeatures();
+    const double t1 = now();
+    const bool ok = fe.SubmitFeatures(lk, ld, rk, rd, ts);
+    const double t2 = now();
+    if (ok)
+      while (fe.InFlight() >= depth) fe.CollectFeatures();
+    t_gen += t1 - t0;
+    t_submit += t2 - t1;
+    t_collect += now() - t2;
   }
   while (fe.CollectFeatures()) {
+  }
+  if (host_us) {
+    const double nfr = double(std::max<uint64_t>(last - halo_first, 1));
+    host_us[0] = 1e6 * t_gen / nfr;
+    host_us[1] = 1e6 * t_submit / nfr;
+    host_us[2] = 1e6 * t_collect / nfr;
   }
   slam_types::SLAMProblem problem;
   fe.GetSLAMProblem(&problem);

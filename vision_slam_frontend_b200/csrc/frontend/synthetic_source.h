@@ -60,8 +60,10 @@ struct SLAMProblemPiece {
 
 // Run poses [first, last) of the source's sequence through a fresh Frontend built from `rig`
 // (halo included, Frontend::StartShard), `in_flight` frames pipelined (1 = blocking calls).
+// host_us (optional, 3 values): mean microseconds per frame spent in the frame source, in
+// SubmitFeatures and in CollectFeatures.
 SLAMProblemPiece RunSequenceShard(const FrontendConfig& rig, const SyntheticStereoSource& source, uint64_t first,
-                                  uint64_t last, int in_flight);
+                                  uint64_t last, int in_flight, double* host_us = nullptr);
 // The whole message from the ranks' pieces, in rank order: byte-identical to
 // Frontend::SerializeSLAMProblem of an unsharded run over the same poses.
 std::vector<uint8_t> MergeSLAMProblemPieces(const std::vector<SLAMProblemPiece>& pieces);
