@@ -54,6 +54,48 @@ def partition_pivot(a, f, l):
     return cut
 
 
+def partition_pivot_ranked(a, f, l):
+    """The same step without the L list and without a search for k*: an element's own rank and
+    the number of candidates on its other side decide whether it is swapped (what
+    csrc/sort_kernel.cu does).  L element p of rank k (from the left) is swapped iff at least
+    k + 1 R elements lie to its right (R[k] > p); R element r of rank k (from the right) iff at
+    least k + 1 L elements lie to its left (L[k] < r).  The cut is the smallest position among
+    the L elements that are NOT swapped and the R elements that ARE."""
+    mid = f + (l - f) // 2
+    ia, ib, ic = f + 1, mid, l - 1
+    da, db, dc = a[ia] >> SHIFT, a[ib] >> SHIFT, a[ic] >> SHIFT
+    if da < db:
+        pick = ib if db < dc else (ic if da < dc else ia)
+    else:
+        pick = ia if da < dc else (ic if db < dc else ib)
+    a[f], a[pick] = a[pick], a[f]
+    piv = a[f] >> SHIFT
+    seg = a[f + 1:l] >> SHIFT
+    pos = np.arange(f + 1, l)
+    isL, isR = seg >= piv, seg <= piv
+    prefL = np.concatenate([[0], np.cumsum(isL)])          # L candidates in [f + 1, f + 1 + i)
+    prefR = np.concatenate([[0], np.cumsum(isR)])
+    totR = prefR[-1]
+    i = np.arange(len(seg))
+    rankL = prefL[i]                                       # rank from the left of an L element
+    r_after = totR - prefR[i + 1]                          # R candidates strictly to the right
+    rankR = r_after                                        # rank from the right of an R element
+    l_before = prefL[i]                                    # L candidates strictly to the left
+    swapL = isL & (r_after >= rankL + 1)
+    swapR = isR & (l_before >= rankR + 1)
+    cand = (isL & ~swapL) | swapR
+    assert cand.any()
+    cut = int(pos[cand].min())
+    Rpos = np.zeros(len(seg) + 1, np.int64)
+    Rpos[rankR[isR]] = pos[isR]                            # the R list, by rank from the right
+    li = pos[swapL]
+    ri = Rpos[rankL[swapL]]
+    tmp = a[li].copy()
+    a[li] = a[ri]
+    a[ri] = tmp
+    return cut
+
+
 def heapsort(a, f, l):
     """std::__partial_sort(first, last, last) = make_heap + sort_heap, libstdc++'s sift rules."""
     v = a[f:l].copy()
@@ -98,7 +140,8 @@ def heapsort(a, f, l):
     a[f:l] = v
 
 
-def sort_prefix_model(dist, keep, depth_limit=None):
+def sort_prefix_model(dist, keep, depth_limit=None, partition=None):
+    partition = partition or partition_pivot
     n = len(dist)
     a = (np.asarray(dist, np.int64) << SHIFT) | np.arange(n, dtype=np.int64)
     if n == 0 or keep <= 0:
@@ -117,7 +160,7 @@ def sort_prefix_model(dist, keep, depth_limit=None):
             if d == 0:
                 heapsort(a, f, l)
                 continue
-            cut = partition_pivot(a, f, l)
+            cut = partition(a, f, l)
             if cut < keep:
                 nxt.append((cut, l, d - 1))
             else:
@@ -158,6 +201,9 @@ if __name__ == "__main__":
                 got, lev = sort_prefix_model(dist, keep) if n and keep else (np.zeros(0, np.int32), 0)
                 exp = host(dist, keep)
                 assert np.array_equal(got, exp), (n, spread, bp)
+                if n and keep:
+                    got2, _ = sort_prefix_model(dist, keep, partition=partition_pivot_ranked)
+                    assert np.array_equal(got2, exp), ("ranked", n, spread, bp)
                 maxlev = max(maxlev, lev)
                 cases += 1
     print("model == host exact sort on", cases, "cases; max levels", maxlev)

@@ -38,7 +38,6 @@ namespace vsf {
 constexpr int kSortThreads = 1024;                 // the partition replay uses all 32 warps
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kCountWarps = 16;                    // the counting sort: 16 slices, 16 private histograms
-constexpr int kSortLeaf = 16;                      // (= std::_S_threshold) ranges this short would be finished serially (off: dependent chains in one thread are slower than two more parallel levels)
 constexpr int kBins = 513;
 constexpr int kSortThreshold = 16;          // std::_S_threshold
 constexpr int kSortMaxRows = 24576;         // exact mode: 16-bit positions; the keys must fit in shared memory
@@ -107,18 +106,23 @@ constexpr uint16_t kDeadPivot = 0xFFFFu;
 // The scratch of the partition phase, carved from `base` (shared memory, or global memory for
 // lists too long for it).  cap = a multiple of 32 >= n.
 struct PartScratch {
-  uint16_t *Ll, *Rl;        // [cap] the two position lists, range [f, l) uses entries f ..
-  uint16_t* seg_of;         // [cap] live range of every position at the current level
-  uint32_t *mL, *mR;        // [cap / 32 + 1] ballots: element not < pivot / not > pivot
-  uint32_t *cumL, *cumR;    // [cap / 32 + 1] counts, then exclusive prefix sums of the ballots
-  uint32_t* seg_fl[2];      // [max_seg] f | l << 16, current / next level
-  uint16_t *seg_piv, *seg_cut, *seg_ks;   // [max_seg]
-  uint32_t* seg_child;      // [max_seg] left child | right child << 16 (kNoSeg = none)
+  uint16_t* rk;             // [cap] rank (from the left, inside its range) of every L element
+  uint16_t* Rl;             // [cap] the R list: range [f, l) stores R[k] at entry f + k
+  uint16_t* seg_of;         // [cap] live range of every position
+  uint32_t *mL, *mR, *mS;   // [cap / 32 + 1] ballots: not < pivot / not > pivot / L element that is swapped
+  uint32_t *locL, *locR;    // [cap / 32 + 1] L / R elements in the chunks of the same warp before this one
+  uint32_t *wtotL, *wtotR;  // [32] L / R elements of every warp's chunks
+  // by level parity (separate members, selected with ?: - an array indexed at run time would push
+  // the whole struct into local memory and put a local load in front of every access)
+  uint32_t *seg_fl0, *seg_fl1;      // [max_seg] f | l << 16
+  int *seg_cut0, *seg_cut1;         // [max_seg] the cut (atomicMin over candidate positions)
+  uint32_t *seg_child0, *seg_child1;   // [max_seg] left child | right child << 16 (kNoSeg = none)
+  uint16_t* seg_piv;        // [max_seg]
 };
 __host__ __device__ inline int sort_max_seg(int cap) { return cap / (kSortThreshold + 1) + 2; }
 __host__ __device__ inline size_t sort_scratch_bytes(int cap) {
   const size_t nch = size_t(cap / 32 + 1), ms = size_t((sort_max_seg(cap) + 1) & ~1);
-  return size_t(cap) * 6 + nch * 16 + ms * (8 + 6 + 4) + 64;
+  return size_t(cap) * 6 + nch * 20 + 64 * 4 + ms * (6 * 4 + 2) + 64;
 }
 template <typename BYTE>
 __device__ __forceinline__ PartScratch carve_scratch(BYTE* base, int cap) {
@@ -127,35 +131,25 @@ __device__ __forceinline__ PartScratch carve_scratch(BYTE* base, int cap) {
   uint32_t* w = reinterpret_cast<uint32_t*>(base);
   S.mL = w; w += nch;
   S.mR = w; w += nch;
-  S.cumL = w; w += nch;
-  S.cumR = w; w += nch;
-  S.seg_fl[0] = w; w += ms;
-  S.seg_fl[1] = w; w += ms;
-  S.seg_child = w; w += ms;
+  S.mS = w; w += nch;
+  S.locL = w; w += nch;
+  S.locR = w; w += nch;
+  S.wtotL = w; w += 32;
+  S.wtotR = w; w += 32;
+  S.seg_fl0 = w; w += ms;
+  S.seg_fl1 = w; w += ms;
+  S.seg_cut0 = reinterpret_cast<int*>(w); w += ms;
+  S.seg_cut1 = reinterpret_cast<int*>(w); w += ms;
+  S.seg_child0 = w; w += ms;
+  S.seg_child1 = w; w += ms;
   uint16_t* h = reinterpret_cast<uint16_t*>(w);
-  S.Ll = h; h += cap;
+  S.rk = h; h += cap;
   S.Rl = h; h += cap;
   S.seg_of = h; h += cap;
-  S.seg_piv = h; h += ms;
-  S.seg_cut = h; h += ms;
-  S.seg_ks = h;
+  S.seg_piv = h;
   return S;
 }
 
-// number of flagged positions in [0, x)
-__device__ __forceinline__ uint32_t flag_prefix(const uint32_t* cum, const uint32_t* mask, int x) {
-  const int c = x >> 5;
-  return cum[c] + __popc(mask[c] & ((1u << (x & 31)) - 1u));
-}
-
-struct SortShared {
-  uint32_t start[kBins + 31];
-  int nseg_next[2], hi_next[2];   // per level parity: written by one level, reset during the next
-  int sorted_end;
-};
-
-// Replay of std::__introsort_loop on keys[0, n), restricted to ranges that reach below `keep`;
-// returns (to every thread) the position from which on the array is left unsorted.
 #define VSF_SORT_TR(k)                                   \
   do {                                                   \
     if (tr && tid == 0) {                                \
@@ -165,39 +159,66 @@ struct SortShared {
     }                                                    \
   } while (0)
 
+struct SortShared {
+  uint32_t start[kBins + 31];
+  int nseg_next[2], hi_next[2];   // per level parity: written by one level, reset during the next
+  int sorted_end;
+};
+
+// Replay of std::__introsort_loop on keys[0, n), restricted to ranges that reach below `keep`;
+// returns (to every thread) the position from which on the array is left unsorted.
+//
+// One recursion level = four barrier-separated phases over all live ranges at once:
+//   P1  one thread per range: median-of-3 to the front (or heapsort at the depth limit)
+//   P2  every element: move to the child range the previous level assigned, compare with the
+//       range's pivot; ballots, and per warp a running count over its contiguous chunks
+//   P4  every element: its rank from its own side (k) and the number of candidates on the other
+//       side beyond it, from the ballots' prefix sums (the 32 per-warp totals are scanned by
+//       every warp with shuffles - no scan phase): an L element is swapped iff at least k + 1 R
+//       elements lie to its right, an R element iff at least k + 1 L elements lie to its left;
+//       the R list is scattered by rank; the cut = the smallest position among the L elements
+//       that are not swapped and the R elements that are (atomicMin per range)
+//   P5  swapped L elements exchange with R[k]; one thread per range turns the cut into child ranges
 __device__ __forceinline__ int introsort_replay(uint32_t* keys, const PartScratch S, SortShared& sm, int n, int keep,
                                                 int depth_limit, long long* tr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned lt = (1u << lane) - 1u, le = (2u << lane) - 1u;
   long long t_last = clock64();
-  long long acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long acc[4] = {0, 0, 0, 0};
   int levels_done = 0;
   const int cap32 = (n + 31) & ~31;
   for (int i = tid; i < cap32; i += kSortThreads) S.seg_of[i] = i < n ? uint16_t(0) : kNoSeg;
-  for (int i = tid; i <= cap32 / 32; i += kSortThreads) {
-    S.mL[i] = 0u;
-    S.mR[i] = 0u;
-  }
   if (tid == 0) {
-    S.seg_fl[0][0] = uint32_t(n) << 16;
+    S.seg_fl0[0] = uint32_t(n) << 16;
     sm.sorted_end = n;
     sm.nseg_next[0] = sm.nseg_next[1] = 0;
     sm.hi_next[0] = sm.hi_next[1] = 0;
   }
   __syncthreads();
-  int nseg = 1, hi = n, cur = 0;
+  int nseg = 1, hi = n;
 #pragma unroll 1
   for (int level = 0; nseg > 0; ++level) {
-    uint32_t* seg_fl = S.seg_fl[cur];
-    uint32_t* seg_next = S.seg_fl[cur ^ 1];
+    const int cur = level & 1;
+    const uint32_t* seg_fl = cur ? S.seg_fl1 : S.seg_fl0;
+    uint32_t* seg_next = cur ? S.seg_fl0 : S.seg_fl1;
+    int* seg_cut = cur ? S.seg_cut1 : S.seg_cut0;
+    const int* cut_prev = cur ? S.seg_cut0 : S.seg_cut1;
+    uint32_t* child_cur = cur ? S.seg_child1 : S.seg_child0;
+    const uint32_t* child_prev = cur ? S.seg_child0 : S.seg_child1;
     const int nch = (hi + 31) >> 5;
-    // ---- P1, one thread per range: depth limit reached -> libstdc++'s heapsort and the range is
-    // done; otherwise std::__move_median_to_first(first, first + 1, mid, last - 1)
+    const int B = (nch + kSortWarps - 1) / kSortWarps;          // chunks per warp, contiguous
+    // c / B without a division: exact for c < 2^16 (B = 1 would need 2^32, so it is special-cased)
+    const uint32_t Binv = B > 1 ? 0xFFFFFFFFu / uint32_t(B) + 1u : 0u;   // ceil(2^32 / B)
+    auto chunk_warp = [&](int c) { return B > 1 ? int(__umulhi(uint32_t(c), Binv)) : c; };
+    const int c_begin = min(nch, warp * B), c_end = min(nch, c_begin + B);
+    // ---- P1
 #pragma unroll 1
     for (int s = tid; s < nseg; s += kSortThreads) {
       const int f = int(seg_fl[s] & 0xFFFFu), l = int(seg_fl[s] >> 16);
       if (level >= depth_limit) {
         heap_sort(keys + f, l - f);
         S.seg_piv[s] = kDeadPivot;
+        seg_cut[s] = l;
         continue;
       }
       const int ia = f + 1, ib = f + (l - f) / 2, ic = l - 1;
@@ -209,164 +230,157 @@ __device__ __forceinline__ int introsort_replay(uint32_t* keys, const PartScratc
       keys[f] = keys[pick];
       keys[pick] = t;
       S.seg_piv[s] = uint16_t(key_dist(keys[f]));
+      seg_cut[s] = 0x7fffffff;
     }
-    if (tid == 0) {            // this level's counters: last read at the end of level - 2, used from P5 on
-      sm.nseg_next[level & 1] = 0;
-      sm.hi_next[level & 1] = 0;
+    if (tid == 0) {            // this level's counters: last read at the end of level - 2, used in P5
+      sm.nseg_next[cur] = 0;
+      sm.hi_next[cur] = 0;
     }
     __syncthreads();
     VSF_SORT_TR(0);
-    // ---- P2, one ballot pass over [0, hi): element of [f + 1, l) not < pivot / not > pivot
+    // ---- P2
+    {
+      uint32_t runL = 0, runR = 0;
 #pragma unroll 1
-    for (int c = warp; c < nch; c += kSortWarps) {
-      const int p = (c << 5) + lane;
-      const uint16_t s = S.seg_of[p];
-      const uint32_t d = key_dist(keys[p]);
-      bool fl = false, fr = false;
-      if (s != kNoSeg) {
-        const uint16_t piv = S.seg_piv[s];
-        if (piv != kDeadPivot && p != int(seg_fl[s] & 0xFFFFu)) {
-          fl = d >= piv;
-          fr = d <= piv;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int p = (c << 5) + lane;
+        uint16_t s = S.seg_of[p];
+        const uint32_t d = key_dist(keys[p]);
+        if (level > 0 && s != kNoSeg) {          // the child range the previous level put this element in
+          const uint32_t child = child_prev[s];
+          s = p < cut_prev[s] ? uint16_t(child & 0xFFFFu) : uint16_t(child >> 16);
+          S.seg_of[p] = s;
         }
+        bool fl = false, fr = false;
+        if (s != kNoSeg) {
+          const uint16_t piv = S.seg_piv[s];
+          if (piv != kDeadPivot && p != int(seg_fl[s] & 0xFFFFu)) {
+            fl = d >= piv;
+            fr = d <= piv;
+          }
+        }
+        const unsigned bl = __ballot_sync(0xffffffffu, fl), br = __ballot_sync(0xffffffffu, fr);
+        if (lane == 0) {
+          S.mL[c] = bl;
+          S.mR[c] = br;
+          S.locL[c] = runL;
+          S.locR[c] = runR;
+        }
+        runL += __popc(bl);
+        runR += __popc(br);
       }
-      const unsigned bl = __ballot_sync(0xffffffffu, fl), br = __ballot_sync(0xffffffffu, fr);
       if (lane == 0) {
-        S.mL[c] = bl;
-        S.mR[c] = br;
-        S.cumL[c] = __popc(bl);
-        S.cumR[c] = __popc(br);
+        S.wtotL[warp] = runL;
+        S.wtotR[warp] = runR;
       }
     }
     __syncthreads();
     VSF_SORT_TR(1);
-    // ---- P3, warps 0 and 1: exclusive prefix sums of the ballot counts
-    if (warp < 2) {
-      uint32_t* cnt = warp == 0 ? S.cumL : S.cumR;
-      uint32_t run = 0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < nch; c0 += 32) {
-        const int c = c0 + lane;
-        const uint32_t v = c < nch ? cnt[c] : 0u;
-        uint32_t incl = v;
+    // ---- P4
+    {
+      // exclusive prefix of the per-warp totals: lane j holds the count of all warps before warp j
+      uint32_t baseL = S.wtotL[lane], baseR = S.wtotR[lane];
+      {
+        const uint32_t vL = baseL, vR = baseR;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += u;
+          const uint32_t uL = __shfl_up_sync(0xffffffffu, baseL, o), uR = __shfl_up_sync(0xffffffffu, baseR, o);
+          if (lane >= o) {
+            baseL += uL;
+            baseR += uR;
+          }
         }
-        if (c < nch) cnt[c] = run + incl - v;
-        run += __shfl_sync(0xffffffffu, incl, 31);
+        baseL -= vL;
+        baseR -= vR;
       }
-      if (lane == 0) {
-        cnt[nch] = run;
-        (warp == 0 ? S.mL : S.mR)[nch] = 0u;
+      const uint32_t ownL = __shfl_sync(0xffffffffu, baseL, warp), ownR = __shfl_sync(0xffffffffu, baseR, warp);
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        const int p = (c << 5) + lane;
+        const uint16_t s = S.seg_of[p];
+        const unsigned bl = S.mL[c], br = S.mR[c];
+        const bool live = s != kNoSeg;
+        const uint32_t fl_ = live ? seg_fl[s] : (1u << 16);
+        const int f = int(fl_ & 0xFFFFu), l = int(fl_ >> 16);
+        // L elements in [0, f] (position f itself is never flagged) and R elements in [0, l - 1]
+        const int yf = f, yl = l - 1;
+        const int cf = yf >> 5, cl = yl >> 5;
+        const uint32_t preL_f = __shfl_sync(0xffffffffu, baseL, chunk_warp(cf)) + S.locL[cf] +
+                                __popc(S.mL[cf] & ((2u << (yf & 31)) - 1u));
+        const uint32_t preR_l = __shfl_sync(0xffffffffu, baseR, chunk_warp(cl)) + S.locR[cl] +
+                                __popc(S.mR[cl] & ((2u << (yl & 31)) - 1u));
+        const uint32_t myL_before = ownL + S.locL[c] + __popc(bl & lt);   // L elements in [0, p)
+        const uint32_t myR_upto = ownR + S.locR[c] + __popc(br & le);     // R elements in [0, p]
+        const bool isL = live && ((bl >> lane) & 1u), isR = live && ((br >> lane) & 1u);
+        const uint32_t k = myL_before - preL_f;       // L elements of the range left of p
+        const uint32_t r_after = preR_l - myR_upto;   // R elements of the range right of p
+        const bool swapL = isL && r_after >= k + 1u;
+        const bool swapR = isR && k >= r_after + 1u;
+        if (isL) S.rk[p] = uint16_t(k);
+        if (isR) S.Rl[f + r_after] = uint16_t(p);
+        const unsigned bs = __ballot_sync(0xffffffffu, swapL);
+        if (lane == 0) S.mS[c] = bs;
+        // the cut: lowest candidate position per range; one atomic per (chunk, range).  A range is
+        // a run of consecutive lanes: the run starts where the previous lane's range differs
+        const bool cand = (isL && !swapL) || swapR;
+        const unsigned prev_s = __shfl_up_sync(0xffffffffu, unsigned(s), 1);
+        const unsigned starts = __ballot_sync(0xffffffffu, lane == 0 || prev_s != unsigned(s));
+        const unsigned cands = __ballot_sync(0xffffffffu, cand);
+        const int run0 = 31 - __clz(starts & le);                      // first lane of this lane's run
+        if (cand && (cands & lt & ~((1u << run0) - 1u)) == 0u) atomicMin(&seg_cut[s], p);
       }
     }
     __syncthreads();
     VSF_SORT_TR(2);
-    // ---- P4: scatter the lists.  L[k] = k-th flagged position from the left of its range, R[k]
-    // = k-th from the right; both stored from entry f of the range on
+    // ---- P5: swaps (elements) and child ranges (one thread per range)
 #pragma unroll 1
-    for (int c = warp; c < nch; c += kSortWarps) {
-      const int p = (c << 5) + lane;
-      const uint16_t s = S.seg_of[p];
-      if (s == kNoSeg) continue;
-      const unsigned bl = S.mL[c], br = S.mR[c];
-      const bool isl = (bl >> lane) & 1u, isr = (br >> lane) & 1u;
-      if (!isl && !isr) continue;
-      const int f = int(seg_fl[s] & 0xFFFFu), l = int(seg_fl[s] >> 16);
-      if (isl) {
-        const uint32_t k = S.cumL[c] + __popc(bl & ((1u << lane) - 1u)) - flag_prefix(S.cumL, S.mL, f + 1);
-        S.Ll[f + k] = uint16_t(p);
-      }
-      if (isr) {
-        const uint32_t upto = S.cumR[c] + __popc(br & ((2u << lane) - 1u));      // flagged in [0, p]
-        const uint32_t k = flag_prefix(S.cumR, S.mR, l) - upto;
-        S.Rl[f + k] = uint16_t(p);
+    for (int c = c_begin; c < c_end; ++c) {
+      if ((S.mS[c] >> lane) & 1u) {
+        const int p = (c << 5) + lane;
+        const int f = int(seg_fl[S.seg_of[p]] & 0xFFFFu);
+        const int partner = S.Rl[f + S.rk[p]];
+        const uint32_t t = keys[p];
+        keys[p] = keys[partner];
+        keys[partner] = t;
       }
     }
-    __syncthreads();
-    VSF_SORT_TR(3);
-    // ---- P5, one thread per range: k* by bisection, the cut, the child ranges (long ones go to
-    // the next level, short ones to the serial finish)
 #pragma unroll 1
     for (int s = tid; s < nseg; s += kSortThreads) {
       const int f = int(seg_fl[s] & 0xFFFFu), l = int(seg_fl[s] >> 16);
-      if (S.seg_piv[s] == kDeadPivot) {
-        S.seg_ks[s] = 0;
-        S.seg_cut[s] = uint16_t(l);
-        S.seg_child[s] = uint32_t(kNoSeg) | (uint32_t(kNoSeg) << 16);
-        continue;
-      }
-      const int cntL = int(flag_prefix(S.cumL, S.mL, l) - flag_prefix(S.cumL, S.mL, f + 1));
-      const int cntR = int(flag_prefix(S.cumR, S.mR, l) - flag_prefix(S.cumR, S.mR, f + 1));
-      int lo = 0, up = min(cntL, cntR);     // first k in [0, up] with !(L[k] < R[k]); up = none fails
-#pragma unroll 1
-      while (lo < up) {
-        const int mid = (lo + up) >> 1;
-        if (S.Ll[f + mid] < S.Rl[f + mid]) lo = mid + 1;
-        else up = mid;
-      }
-      const int ks = lo;
-      const int cl = ks < cntL ? int(S.Ll[f + ks]) : 0x7fffffff;
-      const int cr = ks >= 1 ? int(S.Rl[f + ks - 1]) : 0x7fffffff;
-      const int cut = min(cl, cr);
-      S.seg_ks[s] = uint16_t(ks);
-      S.seg_cut[s] = uint16_t(cut);
-      int cf[2], cl2[2], nchild = 0;
-      if (cut - f > kSortThreshold) {
-        cf[nchild] = f;
-        cl2[nchild++] = cut;
-      }
-      if (cut < keep) {
-        if (l - cut > kSortThreshold) {
-          cf[nchild] = cut;
-          cl2[nchild++] = l;
-        }
-      } else {
-        atomicMin(&sm.sorted_end, cut);
-      }
       uint32_t child = uint32_t(kNoSeg) | (uint32_t(kNoSeg) << 16);
-      for (int k = 0; k < nchild; ++k) {
-        const int i = atomicAdd(&sm.nseg_next[level & 1], 1);
-        seg_next[i] = uint32_t(cf[k]) | (uint32_t(cl2[k]) << 16);
-        atomicMax(&sm.hi_next[level & 1], cl2[k]);
-        if (cf[k] == f) child = (child & 0xFFFF0000u) | uint32_t(i);
-        else child = (child & 0x0000FFFFu) | (uint32_t(i) << 16);
-      }
-      S.seg_child[s] = child;
-    }
-    __syncthreads();
-    VSF_SORT_TR(4);
-    // ---- P6: all swaps of the level at once, then every element moves to its child range
-#pragma unroll 1
-    for (int c = warp; c < nch; c += kSortWarps) {
-      const int p = (c << 5) + lane;
-      const uint16_t s = S.seg_of[p];
-      if (s == kNoSeg) continue;
-      const unsigned bl = S.mL[c];
-      const int f = int(seg_fl[s] & 0xFFFFu);
-      if ((bl >> lane) & 1u) {
-        const uint32_t k = S.cumL[c] + __popc(bl & ((1u << lane) - 1u)) - flag_prefix(S.cumL, S.mL, f + 1);
-        if (k < S.seg_ks[s]) {
-          const int partner = S.Rl[f + k];
-          const uint32_t t = keys[p];
-          keys[p] = keys[partner];
-          keys[partner] = t;
+      if (S.seg_piv[s] != kDeadPivot) {
+        const int cut = seg_cut[s];
+        int cf2[2], cl2[2], nchild = 0;
+        if (cut - f > kSortThreshold) {
+          cf2[nchild] = f;
+          cl2[nchild++] = cut;
+        }
+        if (cut < keep) {
+          if (l - cut > kSortThreshold) {
+            cf2[nchild] = cut;
+            cl2[nchild++] = l;
+          }
+        } else {
+          atomicMin(&sm.sorted_end, cut);
+        }
+        for (int k = 0; k < nchild; ++k) {
+          const int i = atomicAdd(&sm.nseg_next[cur], 1);
+          seg_next[i] = uint32_t(cf2[k]) | (uint32_t(cl2[k]) << 16);
+          atomicMax(&sm.hi_next[cur], cl2[k]);
+          if (cf2[k] == f) child = (child & 0xFFFF0000u) | uint32_t(i);
+          else child = (child & 0x0000FFFFu) | (uint32_t(i) << 16);
         }
       }
-      const uint32_t child = S.seg_child[s];
-      S.seg_of[p] = p < int(S.seg_cut[s]) ? uint16_t(child & 0xFFFFu) : uint16_t(child >> 16);
+      child_cur[s] = child;
     }
     __syncthreads();
-    VSF_SORT_TR(5);
+    VSF_SORT_TR(3);
     ++levels_done;
-    nseg = sm.nseg_next[level & 1];
-    hi = sm.hi_next[level & 1];
-    cur ^= 1;
+    nseg = sm.nseg_next[cur];
+    hi = sm.hi_next[cur];
   }
   if (tr && tid == 0) {
-    for (int k = 0; k < 6; ++k) tr[k] = acc[k];
+    for (int k = 0; k < 4; ++k) tr[k] = acc[k];
     tr[9] = levels_done;
   }
   return sm.sorted_end;

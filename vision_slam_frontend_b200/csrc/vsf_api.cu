@@ -243,6 +243,7 @@ struct vsf_ctx {
   unsigned sort_rr = 0;
   int reserve_sms = 0;
   int reserve_override = -1;    // VSF_RESERVE_SMS (tuning)
+  int sort_streams = 2;         // VSF_SORT_STREAMS (tuning): 1 = the sorts of consecutive frames do not overlap
   uint8_t* slot_ptr(int s) const { return d_ring + size_t(s) * rows_pad * row_bytes; }
   vsf_dmatch* region_ptr(int r) const { return match_base + size_t(r) * rows_pad; }
 };
@@ -759,6 +760,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC_HOST(c, c->h_scalar, 16 * sizeof(float));
   VSF_ALLOC_HOST(c, c->h_fm, size_t(window) * N * sizeof(vsf_feature_match));
   if (const char* e = std::getenv("VSF_RESERVE_SMS")) c->reserve_override = std::atoi(e);
+  if (const char* e = std::getenv("VSF_SORT_STREAMS")) c->sort_streams = std::atoi(e) == 1 ? 1 : 2;
   if (const char* e = std::getenv("VSF_ENGINE")) {   // test / bench override of the automatic choice
     const int v = std::atoi(e);
     if (v >= 0 && v <= 3 && (v < 3 || c->words == 8)) c->engine = v;
@@ -1335,10 +1337,14 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   }
   // A device sort (modes 0, 2) runs on its own stream while the main stream goes on with the next
   // frame; that frame's persistent distance kernel then leaves a few SMs to it (one sort CTA per
-  // list, at most sm_count / 14 SMs), which costs the distance kernel a few per cent and takes
-  // the sort off the frame stream's critical path
+  // list), which costs the distance kernel a few per cent and takes the sort off the frame
+  // stream's critical path.  Measured on C4 (10 lists, 148 SMs): the 10 us stable sort is best
+  // served by 8 SMs (57.2 us/pose; 58.7 with 10), the 55 us exact sort - whose CTAs of two
+  // consecutive frames overlap - by 14-16 (62.7; 64.4 with 10, 68.0 with 8)
   const bool side_sort = sort_mode != 1 && nf > 0 && !(c->engine_flags & 64);
-  c->reserve_sms = side_sort ? std::min(nf, std::max(1, c->sm_count / 14)) : 0;
+  c->reserve_sms = !side_sort ? 0
+                   : sort_mode == 2 ? std::min(nf + nf / 2, std::max(1, c->sm_count / 9))
+                                    : std::min(nf, std::max(1, c->sm_count / 18));
   if (side_sort && c->reserve_override >= 0) c->reserve_sms = std::min(c->reserve_override, c->sm_count - 1);
   c->match_base = f.d_matches;
   c->count_base = f.d_counts;
@@ -1347,7 +1353,7 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   c->mir_hcounts = f.h_counts;
   rc = run_knn(c, specs, ratio, sort_mode == 1);
   c->reserve_sms = 0;
-  const unsigned half = (c->sort_rr++) & 1u;
+  const unsigned half = c->sort_streams > 1 ? ((c->sort_rr++) & 1u) : 0u;
   cudaStream_t side = c->sort_stream[half];
   cudaStream_t sort_on = side_sort ? side : c->stream;
   if (rc == VSF_OK && sort_mode != 1 && nf > 0) {
@@ -2012,8 +2018,8 @@ extern "C" int vsf_debug_sort_device(vsf_ctx* c, const vsf_dmatch* matches, int 
     VSF_CUDA(c, cudaStreamSynchronize(c->stream));
     VSF_CUDA(c, cudaMemcpy(t, d_trace, sizeof(t), cudaMemcpyDeviceToHost));
     cudaFree(d_trace);
-    std::fprintf(stderr, "sort trace n=%d exact=%d: P1 %lld P2 %lld P3 %lld P4 %lld P5 %lld P6 %lld load %lld total %lld levels %lld n_eff %lld\n",
-                 n, exact, t[0], t[1], t[2], t[3], t[4], t[5], t[7], t[8], t[9], t[11]);
+    std::fprintf(stderr, "sort trace n=%d exact=%d: P1 %lld P2 %lld P4 %lld P5 %lld load %lld total %lld levels %lld n_eff %lld\n",
+                 n, exact, t[0], t[1], t[2], t[3], t[7], t[8], t[9], t[11]);
   }
   VSF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_fm_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
