@@ -117,6 +117,8 @@ FrontendConfig::FrontendConfig() {
   max_features = 20000;
   descriptor_bytes = 61;   // AKAZE MLDB, the reference's default extractor
   exact_std_sort = true;
+  strict_reference_threshold = true;
+  residual_order = 0;
   UpdateDerived();
 }
 
@@ -180,6 +182,8 @@ void FrontendConfig::Load(const std::string& path) {
     else if (key == "descriptor_bytes") descriptor_bytes = int(v);
     else if (key == "cuda_device") cuda_device = int(v);
     else if (key == "exact_std_sort") exact_std_sort = (v != 0);
+    else if (key == "strict_reference_threshold") strict_reference_threshold = (v != 0);
+    else if (key == "residual_order") residual_order = int(v);
     else throw std::runtime_error("FrontendConfig::Load: unknown key " + key);
   }
 }
@@ -211,6 +215,12 @@ Frontend::Frontend(const std::string& config_path)
   if (!config_path.empty()) config_.Load(config_path);
   Check(vsf_create(config_.cuda_device, config_.max_features, config_.descriptor_bytes,
                    int(config_.frame_life_), &ctx_), "vsf_create");
+  ApplyOptions();
+}
+
+void Frontend::ApplyOptions() {
+  Check(vsf_set_option(ctx_, VSF_OPT_HOLD_THRESHOLD_ON_EMPTY, config_.strict_reference_threshold ? 0 : 1), "vsf_set_option");
+  Check(vsf_set_option(ctx_, VSF_OPT_RESIDUAL_ORDER, config_.residual_order ? 1 : 0), "vsf_set_option");
 }
 
 Frontend::Frontend(const FrontendConfig& config)
@@ -221,6 +231,7 @@ Frontend::Frontend(const FrontendConfig& config)
       odom_timestamp_(0), config_(config), ctx_(nullptr), curr_frame_ID_(0), first_output_ID_(0) {
   Check(vsf_create(config_.cuda_device, config_.max_features, config_.descriptor_bytes,
                    int(config_.frame_life_), &ctx_), "vsf_create");
+  ApplyOptions();
 }
 
 Frontend::~Frontend() {

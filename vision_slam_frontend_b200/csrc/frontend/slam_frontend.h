@@ -73,6 +73,13 @@ struct FrontendConfig {
   int max_features;        // capacity of one frame
   int descriptor_bytes;    // 32 ORB, 61 AKAZE, 64 BRISK/FREAK
   bool exact_std_sort;     // true: std::sort on the host like the reference
+  // The reference's arithmetic sets the adaptive stereo threshold to 0/0 + 2 = NaN after a frame
+  // without stereo matches, which empties the next frame (src/slam_frontend.cc:392-394); false
+  // keeps the previous threshold instead (VSF_OPT_HOLD_THRESHOLD_ON_EMPTY).
+  bool strict_reference_threshold;
+  // float32 summation order of the epipolar residual's dot products: 0 = Eigen 3.2's
+  // (c0 + c1) + c2, 1 = Eigen 3.3's c0 + (c1 + c2) (VSF_OPT_RESIDUAL_ORDER)
+  int residual_order;
 };
 
 class Frame {
@@ -158,6 +165,7 @@ class Frontend {
                                                 Frame* past_frame, Frame* curr_frame,
                                                 std::vector<cv::DMatch>* sorted_out);
   void Check(int rc, const char* what);
+  void ApplyOptions();
 
   bool odom_initialized_;
   Eigen::Vector3f init_odom_translation_;
