@@ -316,7 +316,7 @@ def run_b200(a):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_tuning(a.popc_mode, a.split, a.qpt, a.variant)
-    ctx.set_engine(a.engine, 0)
+    ctx.set_engine(a.engine, int(os.environ.get("VSF_ENGINE_FLAGS", "0")))   # flags: A/B timing knobs of include/vsf.h
     # host threads for the reference's std::sort (e2e leg): the ranks of one box share its cores
     host_threads = max(2, min(16, (os.cpu_count() or 16) // world))
     if os.environ.get("VSF_HOST_THREADS"):
@@ -334,7 +334,7 @@ def run_b200(a):
     base = seq.data_ptr()
 
     def launch_step(s):
-        # poses [s*B, (s+1)*B) of the walk, each against the W poses before it; 4 launches per pose
+        # poses [s*B, (s+1)*B) of the walk, each against the W poses before it
         ctx.window_match_block_device(base, n, n_poses, s * B, B, RATIO)
 
     def barrier():
@@ -348,6 +348,7 @@ def run_b200(a):
         launch_step(s)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count()
     with ClockSampler(local) as clocks:
         e0.record(stream)
         for s in range(K):
@@ -355,6 +356,8 @@ def run_b200(a):
         e1.record(stream)
         barrier()
     ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    two_kernels = launches < 3 * K * B
     counts = ctx.fetch_window(W, with_matches=False)
     engine = ctx.last_engine
     # ---- per-kernel durations (CUDA events on the ctx stream around every kernel of a launch;
@@ -505,9 +508,12 @@ def run_b200(a):
                 "note": "north-star denominator: the integer-pipe roofline of the naive one-POPC-per-word "
                         "comparison; the tensor-core engine is not bound by it (frac > 1)",
             },
-            "gpu_launches": K * B * (4 if tensor else 1),
-            "kernel": ("expand_train + knn2_tc + refine + compact kernels "
-                       "(4 launches per pose, programmatic dependent launch)") if tensor
+            "gpu_launches": int(launches),
+            "kernel": (("knn2_tc (distance) + knn2_tc_finish (refine + ordered compaction + expansion of the next "
+                        "pose's frame) kernels, 2 launches per pose, programmatic dependent launch")
+                       if two_kernels else
+                       ("expand_train + knn2_tc + refine + compact kernels "
+                        "(4 launches per pose, programmatic dependent launch)")) if tensor
                       else "vsf::knn2_kernel<WORDS,R,MODE> (one launch per pose)",
             "kernel_ms": {"expand_train": float(kt[0]), "main": float(kt[1]), "refine": float(kt[2]),
                           "compact": float(kt[3])},

@@ -105,7 +105,11 @@ int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
  * bytes), engine 3 for desc_bytes <= 32 only.  Every engine produces bit-identical
  * results.  flags: pass 0; 128 keeps 33..64-byte rows on the single-CTA tensor kernel instead of
  * CTA pairs (A/B timing); 64 keeps the device sort of the pipelined frame stream (sort_mode 0 / 2)
- * on the main stream instead of a side stream with reserved SMs (A/B timing); 16 / 32 record the per-CTA / per-kernel
+ * on the main stream instead of a side stream with reserved SMs (A/B timing); 512 runs the
+ * tensor engine's refine and compaction as two kernels instead of one (A/B timing); 256 stops
+ * vsf_window_match_block_device from expanding the next pose's frame inside the running pose's
+ * distance kernel, 1024 from starting a pose's distance kernel before the previous pose's
+ * finish kernel has completed (A/B timing); 16 / 32 record the per-CTA / per-kernel
  * timelines read by vsf_debug_tc_trace / vsf_debug_kernel_trace (16, and the
  * timing-only flags 2 / 4, exist only in libraries built with VSF_TC_TRACE /
  * VSF_TC_BRINGUP, see vision_slam_frontend_b200/build.py). */
@@ -395,7 +399,10 @@ int vsf_fetch_window(vsf_ctx* ctx, int n_frames, int* counts, vsf_dmatch* out,
  * k in [0, count) the current frame is c = (first + k) mod (n_poses - window) + window and the
  * query frames are c - window .. c - 1 (the bag loop of src/slam_frontend_main.cc:236-328 with
  * src/slam_frontend.cc:424-434 inside, device-resident).  Asynchronous; the results of the last
- * pose stay in the ctx's device buffers (vsf_fetch_window). */
+ * pose stay in the ctx's device buffers (vsf_fetch_window).  On the tensor engine with rows of
+ * at most 32 bytes a pose is two kernels: the distance kernel, which also expands the next
+ * pose's frame, and one kernel for refine + ordered compaction (csrc/knn2_tc_kernel.cu:
+ * knn2_tc_finish_kernel). */
 int vsf_window_match_block_device(vsf_ctx* ctx, const void* d_seq, int n, int n_poses,
                                   long long first, int count, double nn_match_ratio);
 
@@ -463,14 +470,18 @@ int vsf_debug_sort_device(vsf_ctx* ctx, const vsf_dmatch* matches, int n, float 
 int vsf_debug_tc_plan(int query_blocks, int train_tiles, int sm_count, int force_split,
                       long long rows, long long partial_cap, int* out5);
 
+/* Kernels launched so far by the kNN paths of this ctx (bench.py's gpu_launches). */
+long long vsf_debug_launch_count(const vsf_ctx* ctx);
+
 /* Bring-up aid: per-CTA timeline of the last tensor-engine launch made with engine flag 16
  * (vsf_set_engine(ctx, 2, 16)): 16 values per CTA, layout documented in
  * csrc/knn2_tc_kernel.cu.  Waits for the ctx stream. */
 int vsf_debug_tc_trace(vsf_ctx* ctx, long long* out, int max_ctas, int* n_ctas);
 /* Bring-up aid: kernel-level timeline of the tensor-engine launches made since
- * vsf_set_engine(ctx, engine, 32): per launch 10 values = earliest start / latest end
- * (globaltimer ns) of the expansion, distance, refine and compaction kernels, then of the
- * refine after its wait.  At most 256 launches are kept. */
+ * vsf_set_engine(ctx, engine, 32): per launch 16 values = earliest start / latest end
+ * (globaltimer ns) of the expansion, distance, refine (or refine + compaction: finish) and
+ * compaction kernels, then of the refine after its wait; 6 spare values.  At most 256 launches
+ * are kept. */
 int vsf_debug_kernel_trace(vsf_ctx* ctx, long long* out, int max_records, int* n_records);
 
 #ifdef __cplusplus

@@ -319,6 +319,32 @@ def test_window_match_block_device(width):
     assert sum(len(m) for m in got) > 1000
 
 
+@pytest.mark.parametrize("n,W,count", [(1400, 4, 1), (1400, 4, 2), (1400, 4, 3), (1400, 4, 6), (1237, 3, 5),
+                                        (2900, 2, 4), (700, 10, 9), (130, 38, 3), (3000, 1, 3)])
+def test_block_device_launch_variants(n, W, count):
+    """A pose of a device-resident block is two kernels (distance, which also expands the next
+    pose's frame and starts without waiting for its predecessor, + finish); with the look-ahead
+    off (engine flag 256) three, with refine and compaction as separate kernels (512) four; 1024
+    = no early start.  Same lists every way, equal to the oracle's."""
+    import torch
+    poses, stride, seed = W + 9, 97, 5
+    with new_ctx(max_features=3072, window=W) as ctx:
+        buf = torch.empty((poses, n, 32), dtype=torch.uint8, device="cuda")
+        ctx.synth_sequence_device(buf.data_ptr(), n, 0, poses, stride, seed)
+        got = {}
+        for flags, per_pose, extra in ((0, 2, 1), (256, 3, 0), (512, 4, 0), (1024, 2, 1), (0, 2, 1)):
+            ctx.set_engine(2, flags)
+            before = ctx.launch_count()
+            ctx.window_match_block_device(buf.data_ptr(), n, poses, 2, count, RATIO)
+            got[len(got)] = ctx.fetch_window(W)
+            assert ctx.launch_count() - before == per_pose * count + extra
+    cur = ((2 + count - 1) % (poses - W)) + W
+    for j in range(W):
+        exp = native.get_matches(synth.synth_pose(n, cur - W + j, stride, seed), synth.synth_pose(n, cur, stride, seed), RATIO)
+        for k in got:
+            np.testing.assert_array_equal(got[k][j], exp)
+
+
 @pytest.mark.parametrize("sort_mode", [0, 1, 2])
 def test_window_run_sequence_equals_per_frame_calls(sort_mode):
     import torch

@@ -49,7 +49,7 @@ def main():
         ctx.set_engine(2, 32)
         for t in range(poses):
             step(t)
-        buf = np.zeros((256, 5, 2), np.int64)
+        buf = np.zeros((256, 8, 2), np.int64)
         got = C.c_int(0)
         ctx._check(L.vsf_debug_kernel_trace(ctx._h, buf.ctypes.data, 256, C.byref(got)))
         tr = buf[: got.value].astype(np.float64)

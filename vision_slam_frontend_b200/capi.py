@@ -118,6 +118,7 @@ def load_library():
         "vsf_observe_in_flight": ([vp], i),
         "vsf_probe_pipe": ([vp, i, i, C.POINTER(d)], i),
         "vsf_device_sm_count": ([vp], i),
+        "vsf_debug_launch_count": ([vp], C.c_longlong),
         "vsf_debug_tc_trace": ([vp, vp, i, C.POINTER(i)], i),
         "vsf_debug_kernel_trace": ([vp, vp, i, C.POINTER(i)], i),
         "vsf_debug_tc_plan": ([i, i, i, i, C.c_longlong, C.c_longlong, vp], i),
@@ -144,7 +145,7 @@ EXPORTED_SYMBOLS = [
     "vsf_device_row_bytes", "vsf_window_match_device", "vsf_fetch_window",
     "vsf_window_match_block_device", "vsf_window_run_sequence",
     "vsf_synth_sequence_device", "vsf_device_match_lists", "vsf_stream", "vsf_observe_submit",
-    "vsf_observe_collect", "vsf_observe_in_flight", "vsf_probe_pipe", "vsf_device_sm_count",
+    "vsf_observe_collect", "vsf_observe_in_flight", "vsf_probe_pipe", "vsf_device_sm_count", "vsf_debug_launch_count",
     "vsf_debug_tc_trace", "vsf_debug_kernel_trace", "vsf_debug_tc_plan", "vsf_debug_sort_prefix",
     "vsf_debug_sort_prefix_depth", "vsf_debug_sort_device",
 ]
@@ -215,6 +216,10 @@ class Context:
     def set_tuning(self, popc_mode=-1, train_split=0, queries_per_thread=0, variant=-1):
         self._check(self._L.vsf_set_tuning(self._h, popc_mode, train_split, queries_per_thread,
                                            variant))
+
+    def launch_count(self) -> int:
+        """Kernels launched so far by the kNN paths of this ctx."""
+        return int(self._L.vsf_debug_launch_count(self._h))
 
     def set_engine(self, engine: int = 0, flags: int = 0):
         """0 auto, 1 POPC pipe, 2 tensor cores (int8), 3 tensor cores (e4m3)."""

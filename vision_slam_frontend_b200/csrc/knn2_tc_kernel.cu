@@ -34,6 +34,7 @@
 //   knn2_compact_kernel   ratio survivors in ascending queryIdx order.
 // launch_knn2_tc chains the four on one stream with programmatic dependent launch.
 #include <atomic>
+#include <cstdlib>
 #include <utility>
 
 #include "knn2_tail.cuh"
@@ -224,6 +225,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     tr[1] = clock64();
   }
   if (tid == 0) ktrace_start(batch.ktrace, 1);
+  if (tc.early) pdl_launch_dependents();
 
   if (tid == 0) {
 #pragma unroll
@@ -263,8 +265,10 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     // ------------------------------ TMA producer ------------------------------
     TcUnit U;
     if (lane == 0 && walk_more(wk)) U = walk_unit(batch, tc, wk);
-    pdl_wait();                 // the expanded train image is complete
-    pdl_launch_dependents();
+    if (!tc.early) {
+      pdl_wait();               // the expanded train image is complete
+      pdl_launch_dependents();
+    }
     if (lane == 0) {
       uint32_t it = 0;
       while (walk_more(wk)) {
@@ -285,8 +289,10 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     __syncwarp();
   } else if (warp == kTcEpiWarps + 1) {
     // ------------------------------ MMA issuer ------------------------------
-    pdl_wait();
-    pdl_launch_dependents();
+    if (!tc.early) {
+      pdl_wait();
+      pdl_launch_dependents();
+    }
     if (lane == 0) {
       uint32_t it = 0, unit_it = 0, acc_use[2] = {0u, 0u};
       long long wait_a = 0, wait_b = 0, nseg = 0;
@@ -390,9 +396,33 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
         expanded = true;
       }
     }
-    pdl_wait();                 // partial keys of the previous launch have been consumed
-    pdl_launch_dependents();
+    if (!tc.early) {
+      pdl_wait();               // partial keys of the previous launch have been consumed
+      pdl_launch_dependents();
+    }
     if (tid == 0) TC_TRACE(3);
+    if (tc.exp_src) {
+      // this CTA's share of the next launch's train image (layout of expand_train_kernel), while
+      // the tensor core works on the first tile.  The image it replaces was last read two
+      // launches ago.
+      const int rows_pad = (tc.exp_nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
+      for (int idx = blockIdx.x * (kTcEpiWarps * 32) + tid; idx < rows_pad * 4; idx += gridDim.x * (kTcEpiWarps * 32)) {
+        const int row = idx % rows_pad;
+        const int cg = idx / rows_pad;  // 0..3: K-chunks 4*cg .. 4*cg+3  (words 2*cg, 2*cg+1)
+        uint2 wd = make_uint2(0u, 0u);
+        const bool live = row < tc.exp_nt;
+        if (live) wd = __ldg(reinterpret_cast<const uint2*>(tc.exp_src + size_t(row) * 8) + cg);
+        const int tile = row / kTcTileRows, rr = row % kTcTileRows;
+        uint8_t* dst = tc.exp_out + size_t(tile) * kTcBBytes + size_t(rr) * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t word = (c < 2) ? wd.x : wd.y;
+          const uint32_t b16 = (word >> (16 * (c & 1))) & 0xFFFFu;
+          const uint4 v = live ? expand16<I8>(b16) : make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst + size_t(4 * cg + c) * (kTcTileRows * 16)) = v;
+        }
+      }
+    }
     while (walk_more(wk)) {
       walk_next(wk, U);                       // wk now stands on the unit after U
       const bool more = walk_more(wk);
@@ -520,6 +550,8 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     tc::fence_after_sync();
     tc::tmem_dealloc<kTcTmemCols>(tmem_base);
   }
+  // early start: completion of this kernel must still imply completion of its stream predecessor
+  if (tc.early) pdl_wait();
   if (tid == 0) {
     ktrace_end(batch.ktrace, 1);
     if (tr) {
@@ -541,30 +573,38 @@ constexpr int kRefineQB = 64;                                // queries per refi
 constexpr int kCompactQB = 128;                              // queries per compaction CTA
 constexpr int kRefineThreads = 2 * kRefineQB;
 constexpr int kRefineRows = 8;                               // rows per pair per pass
-constexpr int kRefinePitch = kRefineRows * 32 + 16;          // bytes per pair in the stage (+16: bank skew)
-constexpr int kRefinePP = kRefineRows * 2;                   // 16-byte pieces of one pair's run of rows
-static_assert(kTcBucket % kRefineRows == 0 && 32 % kRefinePP == 0, "bucket must be a multiple of the refine pass");
 
 // EXACT2 = true: two lanes per query as described (vsf_knn2 reports the second neighbour's index).
 // EXACT2 = false (every other entry point: only the second neighbour's DISTANCE matters, for the
 // ratio test): one lane per query rescans the best bucket and takes the second-best bucket's
 // best distance from its exact maximum dot, dot = 256 - 2 * hamming - half the rows to fetch,
 // half the lanes, 128 queries per CTA.
-template <bool EXACT2>
-__global__ void __launch_bounds__(kRefineThreads)
-knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
+// ROWS = rows per pair per staging pass (8 for the stand-alone kernel; 4 for the chained post
+// kernel, whose shared memory has to fit beside a resident CTA of knn2_tc_kernel).
+// PDL: the stand-alone kernel waits for its stream predecessor between the query fetch and the
+// partial keys.  All kRefineThreads threads of the CTA call this with the same (problem, qb).
+template <int ROWS>
+struct RefineGeom {
+  static constexpr int kPitch = ROWS * 32 + 16;   // bytes per pair in the stage (+16: bank skew)
+  static constexpr int kPP = ROWS * 2;            // 16-byte pieces of one pair's run of rows
+  static constexpr int kStageBytes = (kRefineThreads / 32) * 32 * kPitch;
+  static_assert(kTcBucket % ROWS == 0 && 32 % kPP == 0, "bucket must be a multiple of the refine pass");
+};
+
+template <bool EXACT2, int ROWS, bool PDL>
+__device__ __forceinline__ void refine_block(const KnnBatch& batch, const TcBatch& tc, int problem, int qb,
+                                             uint8_t* s_stage_all) {
   constexpr int kQB = EXACT2 ? kRefineQB : 2 * kRefineQB;      // queries per CTA
-  __shared__ __align__(16) uint8_t s_stage[kRefineThreads / 32][32 * kRefinePitch];
-  const KnnProblem& P = batch.p[blockIdx.y];
+  constexpr int kPitch = RefineGeom<ROWS>::kPitch;
+  constexpr int kPP = RefineGeom<ROWS>::kPP;
+  const KnnProblem& P = batch.p[problem];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) ktrace_start(batch.ktrace, 2);
   // The descriptors and row counts were written before the launch sequence began (see
   // knn2_tc_kernel): the query words are fetched while the distance kernel is still finishing.
   int nq = P.nq, nt = P.nt;
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
   if (P.nt_dev) nt = min(nt, *P.nt_dev);
-  const int qb = blockIdx.x;
   const int q0 = qb * kQB;
   const int q = q0 + (EXACT2 ? (tid >> 1) : tid);
   const int c = EXACT2 ? (tid & 1) : 0;                       // 0: best bucket, 1: second-best bucket
@@ -575,11 +615,13 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     qw[0] = w0.x; qw[1] = w0.y; qw[2] = w0.z; qw[3] = w0.w;
     qw[4] = w1.x; qw[5] = w1.y; qw[6] = w1.z; qw[7] = w1.w;
   }
-  pdl_wait();                                  // the partial bucket keys are complete
-  if (tid == 0) ktrace_start(batch.ktrace, 4);
-  pdl_launch_dependents();
+  if (PDL) {
+    pdl_wait();                                  // the partial bucket keys are complete
+    if (tid == 0) ktrace_start(batch.ktrace, 4);
+    pdl_launch_dependents();
+  }
   if (nq <= 0) {
-    if (blockIdx.x == 0 && tid == 0) {
+    if (qb == 0 && tid == 0) {
       *P.match_count = 0;
       if (batch.host_counts) batch.host_counts[P.region] = 0;
     }
@@ -591,8 +633,7 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   if (q < nq) {
     int b1 = kTcKeySentinel, b2 = kTcKeySentinel;
     // the query block's tile slots were shared out to consecutive CTAs, one partial segment each
-    const int nseg = tc_block_segments(tc, tc.qb_begin[blockIdx.y] + q / kTcQ);
-    const int np = nseg * kTcColSplit;
+    const int nseg = tc_block_segments(tc, tc.qb_begin[problem] + q / kTcQ);
     // a segment's two column-half partials are one aligned 16-byte record; four records are
     // fetched together so that a block cut into many segments costs one L2 round trip per four
     // segments, not one per partial
@@ -617,7 +658,6 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
         merge(int(p[j].z), int(p[j].w));
       }
     }
-    (void)np;
     key = c ? b2 : b1;
     key2 = b2;
   }
@@ -630,25 +670,25 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     const int dot = key2 >> kBucketIdBits;
     k1 = (uint32_t((kTcRowBytes - dot) >> 1) << kIdxBits) + uint32_t((kBucketIdMask - (key2 & kBucketIdMask)) * kTcBucket);
   }
-  uint8_t* stage = s_stage[warp];
+  uint8_t* stage = s_stage_all + size_t(warp) * (32 * kPitch);
 #pragma unroll 1
-  for (int r0 = 0; r0 < kTcBucket; r0 += kRefineRows) {
-    // stage: 32 pairs x 8 rows x 32 B in pieces of 16 B, 16 per lane
+  for (int r0 = 0; r0 < kTcBucket; r0 += ROWS) {
+    // stage: 32 pairs x ROWS rows x 32 B in pieces of 16 B, kPP per lane
 #pragma unroll
-    for (int i = 0; i < kRefinePP; ++i) {
-      const int g = i * (32 / kRefinePP) + lane / kRefinePP;          // pair (lane) whose rows this piece belongs to
-      const int piece = lane % kRefinePP;                       // 16-byte piece of the pair's run of rows
+    for (int i = 0; i < kPP; ++i) {
+      const int g = i * (32 / kPP) + lane / kPP;          // pair (lane) whose rows this piece belongs to
+      const int piece = lane % kPP;                       // 16-byte piece of the pair's run of rows
       const int base = __shfl_sync(0xffffffffu, my_row0, g);
       const int row = base + r0 + (piece >> 1);
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (base >= 0 && row < nt) v = __ldg(reinterpret_cast<const uint4*>(P.t + size_t(row) * 8) + (piece & 1));
-      *reinterpret_cast<uint4*>(stage + g * kRefinePitch + piece * 16) = v;
+      *reinterpret_cast<uint4*>(stage + g * kPitch + piece * 16) = v;
     }
     __syncwarp();
     if (my_row0 >= 0) {
-      const uint4* mine = reinterpret_cast<const uint4*>(stage + lane * kRefinePitch);
+      const uint4* mine = reinterpret_cast<const uint4*>(stage + lane * kPitch);
 #pragma unroll
-      for (int k = 0; k < kRefineRows; ++k) {
+      for (int k = 0; k < ROWS; ++k) {
         const int row = my_row0 + r0 + k;
         const uint4 t0 = mine[2 * k], t1 = mine[2 * k + 1];
         const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
@@ -685,31 +725,36 @@ knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       batch.qblock_pass[P.qb0 + 2 * qb + 1] = unsigned(n1);
     }
   }
-  if (tid == 0) ktrace_end(batch.ktrace, 2);
+}
+
+template <bool EXACT2>
+__global__ void __launch_bounds__(kRefineThreads)
+knn2_tc_refine_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
+  __shared__ __align__(16) uint8_t s_stage[RefineGeom<kRefineRows>::kStageBytes];
+  if (threadIdx.x == 0) ktrace_start(batch.ktrace, 2);
+  refine_block<EXACT2, kRefineRows, true>(batch, tc, blockIdx.y, blockIdx.x, s_stage);
+  if (threadIdx.x == 0) ktrace_end(batch.ktrace, 2);
 }
 
 // Ordered compaction of the ratio survivors, one CTA per block of 128 queries: the CTA's
 // output offset is the sum of the survivor counts of the query blocks before it, so the list
 // comes out in ascending queryIdx order (what Frontend::GetMatches returns) with no serial pass.
-__global__ void __launch_bounds__(kCompactQB)
-knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
-  __shared__ unsigned s_red[kCompactQB / 32];
-  __shared__ unsigned s_woff[kCompactQB / 32];
-  const KnnProblem& P = batch.p[blockIdx.y];
+// All QB threads of the CTA call this with the same (problem, qb); the survivor counts (one per
+// CNT queries) and knn_out of the whole problem must be complete.
+template <int QB, int CNT>
+__device__ __forceinline__ void compact_block(const KnnBatch& batch, int problem, int qb, unsigned* s_red,
+                                              unsigned* s_woff) {
+  const KnnProblem& P = batch.p[problem];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) ktrace_start(batch.ktrace, 3);
-  pdl_wait();
-  pdl_launch_dependents();
   int nq = P.nq;
   if (P.nq_dev) nq = min(nq, *P.nq_dev);
-  if (nq <= 0) return;                       // the refine kernel wrote match_count = 0
-  const int qb = blockIdx.x;
-  const int q0 = qb * kCompactQB;
+  if (nq <= 0) return;                       // the refine wrote match_count = 0
+  const int q0 = qb * QB;
   if (q0 >= nq) return;
-  const int nqb = (nq + kCompactQB - 1) / kCompactQB;
+  const int nqb = (nq + QB - 1) / QB;
   unsigned sum = 0;
-  for (int i = tid; i < qb * (kCompactQB / kRefineQB); i += kCompactQB) sum += __ldcg(&batch.qblock_pass[P.qb0 + i]);
+  for (int i = tid; i < qb * (QB / CNT); i += QB) sum += __ldcg(&batch.qblock_pass[P.qb0 + i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if (lane == 0) s_red[warp] = sum;
@@ -725,7 +770,7 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
   __syncthreads();
   unsigned off = 0, total = 0;
 #pragma unroll
-  for (int w = 0; w < kCompactQB / 32; ++w) {
+  for (int w = 0; w < QB / 32; ++w) {
     off += s_red[w];
     if (w < warp) off += s_woff[w];
     total += s_woff[w];
@@ -744,11 +789,231 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
   if (qb == nqb - 1 && tid == 0) {
     unsigned base = 0;
 #pragma unroll
-    for (int w = 0; w < kCompactQB / 32; ++w) base += s_red[w];
+    for (int w = 0; w < QB / 32; ++w) base += s_red[w];
     *P.match_count = int(base + total);
     if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
   }
-  if (tid == 0) ktrace_end(batch.ktrace, 3);
+}
+
+__global__ void __launch_bounds__(kCompactQB)
+knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
+  __shared__ unsigned s_red[kCompactQB / 32];
+  __shared__ unsigned s_woff[kCompactQB / 32];
+  if (threadIdx.x == 0) ktrace_start(batch.ktrace, 3);
+  pdl_wait();
+  pdl_launch_dependents();
+  compact_block<kCompactQB, kRefineQB>(batch, blockIdx.y, blockIdx.x, s_red, s_woff);
+  if (threadIdx.x == 0) ktrace_end(batch.ktrace, 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Refine + ordered compaction in one kernel (every entry point that does not need the second
+// neighbour's index).  Four lanes per query, 32 queries per 128-thread CTA, no shared-memory
+// staging: step by step the four lanes of a query read 64 contiguous bytes (two rows) of its
+// best bucket, neighbouring lanes add up the two halves of a row's exact Hamming distance, and
+// one shuffle step merges the packed (distance, trainIdx) top-2 keys of the even and the odd
+// rows (lowest train index winning ties, as everywhere).  Short dependency chains, 12 CTAs per SM:
+// the whole launch is resident at once, and a CTA is small enough to sit beside a CTA of
+// knn2_tc_kernel.
+// The compaction needs the survivor counts of the query blocks before this one: each CTA
+// publishes its count as (epoch << 8 | count) with a release store and reads its predecessors'
+// with acquire loads ("decoupled look-back": the blocks of a problem are refined side by side,
+// so the wait is short).  A CTA only ever waits for CTAs with a smaller logical index, and the
+// logical index is handed out by an atomic ticket in the order the CTAs start, so every CTA
+// that is waited for is already running: no deadlock whatever order the hardware dispatches
+// the grid in.  Ticket counter, per-SM counters and look-back words carry the launch's epoch in
+// their upper bits (64-bit words, the epoch only grows), so nothing is ever reset; consecutive
+// launches, whose CTAs may be starting while the previous launch is still running, alternate
+// between two ticket counters.
+constexpr int kFinLanes = 4;                          // lanes per query
+constexpr int kFinThreads = 128;
+constexpr int kFinQ = kFinThreads / kFinLanes;        // queries per CTA (= one survivor counter)
+static_assert(kFinLanes == 4 && kTcBucket % 8 == 0, "knn2_tc_finish_kernel: 4 lanes x 4 steps of 2 rows");
+static_assert(kFinQ == 32, "FinishArgs::flags is indexed in 32-query units (KnnProblem::qb0)");
+
+// The look-back words carry their payload themselves (epoch | count): relaxed accesses at GPU
+// scope are enough, and an acquire load in the polling loop would invalidate the SM's L1 on
+// every iteration (CCTL.IVALL).
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kFinThreads, 12)
+knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc,
+                      const __grid_constant__ FinishArgs fa) {
+  __shared__ unsigned s_woff[kFinThreads / 32];
+  __shared__ unsigned s_base;
+  __shared__ int s_where[3];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int part = tid % kFinLanes;
+  if (tid == 0) ktrace_start(batch.ktrace, 2);
+  // one block per CTA, taken by ticket (the do-while only gives the early exits a common end)
+  do {
+    if (tid == 0) {
+      // the integer divisions of the block's coordinates are done once per CTA
+      atomicMax(fa.ticket, fa.epoch << 24);
+      const int id = int(atomicAdd(fa.ticket, 1ull) - (fa.epoch << 24));
+      const int pr = id / fa.nqb, b = id - pr * fa.nqb;
+      s_where[0] = pr;
+      s_where[1] = b;
+      // (the 32 queries of a block are in one 256-query block of the distance kernel)
+      s_where[2] = tc_block_segments(tc, tc.qb_begin[pr] + (b * kFinQ) / kTcQ);
+    }
+    __syncthreads();
+    const int problem = s_where[0], qb = s_where[1];
+    const KnnProblem& P = batch.p[problem];
+    // The descriptors and row counts were written before the launch sequence began (see
+    // knn2_tc_kernel): the query words are fetched while the distance kernel is still finishing.
+    int nq = P.nq, nt = P.nt;
+    if (P.nq_dev) nq = min(nq, *P.nq_dev);
+    if (P.nt_dev) nt = min(nt, *P.nt_dev);
+    const int q0 = qb * kFinQ;
+    const int q = q0 + tid / kFinLanes;
+    // lane `part` of a query works on 16-byte half `part & 1` of every second row of the bucket
+    uint4 qh = make_uint4(0u, 0u, 0u, 0u);
+    if (q < nq) qh = __ldg(reinterpret_cast<const uint4*>(P.q + size_t(q) * 8) + (part & 1));
+    pdl_wait();                                // the partial bucket keys are complete
+    if (tid == 0) ktrace_start(batch.ktrace, 4);
+    pdl_launch_dependents();
+    if (nq <= 0) {                             // CTA-uniform, like the next test
+      if (qb == 0 && tid == 0) {
+        *P.match_count = 0;
+        if (batch.host_counts) batch.host_counts[P.region] = 0;
+      }
+      break;
+    }
+    if (q0 >= nq) break;
+    const int nqb = (nq + kFinQ - 1) / kFinQ;
+
+    // ---- merge the query's partial bucket keys (the four lanes of a query read the same words)
+    int key = kTcKeySentinel, key2 = kTcKeySentinel;
+    if (q < nq) {
+      int b1 = kTcKeySentinel, b2 = kTcKeySentinel;
+      // the query block's tile slots were shared out to consecutive CTAs, one partial segment each
+      const int nseg = s_where[2];
+      static_assert(kTcColSplit == 2 && kTcQ % kFinQ == 0, "one uint4 = the two column-half partials of a segment");
+      const uint4* part_keys = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(batch.partial) +
+                                                               size_t(P.row0 + q) * (tc.slots * kTcColSplit));
+      auto merge = [&](int a1, int a2) {   // merge two descending pairs
+        const int hi = max(b1, a1), lo = min(b1, a1);
+        b2 = max(lo, max(b2, a2));
+        b1 = hi;
+      };
+      for (int z0 = 0; z0 < nseg; z0 += 2) {
+        uint4 p[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          p[j] = (z0 + j < nseg) ? __ldcg(part_keys + z0 + j)
+                                 : make_uint4(uint32_t(kTcKeySentinel), uint32_t(kTcKeySentinel),
+                                              uint32_t(kTcKeySentinel), uint32_t(kTcKeySentinel));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          merge(int(p[j].x), int(p[j].y));
+          merge(int(p[j].z), int(p[j].w));
+        }
+      }
+      key = b1;
+      key2 = b2;
+    }
+    // ---- exact distances to the rows of the best bucket.  The bucket is 2 * kTcBucket 16-byte
+    // pieces; in step j the query's four lanes read pieces 4j .. 4j+3 (64 contiguous bytes = rows
+    // 2j, 2j+1), a lane and its neighbour add up the two halves of a row.
+    uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
+    {
+      const bool have = key != kTcKeySentinel;
+      const int row_base = have ? (kBucketIdMask - (key & kBucketIdMask)) * kTcBucket : 0;
+      const uint4* pieces = reinterpret_cast<const uint4*>(P.t + size_t(row_base) * 8) + part;
+      const int rsub = part >> 1;
+#pragma unroll
+      for (int j0 = 0; j0 < kTcBucket / 2; j0 += 4) {
+        uint4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          t[u] = (have && row_base + 2 * (j0 + u) + rsub < nt) ? __ldg(pieces + 4 * (j0 + u)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t d = __popc(t[u].x ^ qh.x) + __popc(t[u].y ^ qh.y) + __popc(t[u].z ^ qh.z) + __popc(t[u].w ^ qh.w);
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          const int row = row_base + 2 * (j0 + u) + rsub;
+          if (have && row < nt) top2_insert(k1, k2, (d << kIdxBits) + uint32_t(row));
+        }
+      }
+    }
+    // the two lane pairs of a query saw the even / the odd rows
+    {
+      const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, 2), o2 = __shfl_xor_sync(0xffffffffu, k2, 2);
+      top2_merge(k1, k2, o1, o2);
+    }
+    if (key2 != kTcKeySentinel) {
+      // the second-best bucket's best distance is exact (its maximum dot is); its first row stands
+      // in as the index, which nobody reads on this path
+      const int dot = key2 >> kBucketIdBits;
+      top2_insert(k1, k2, (uint32_t((kTcRowBytes - dot) >> 1) << kIdxBits) +
+                              uint32_t((kBucketIdMask - (key2 & kBucketIdMask)) * kTcBucket));
+    }
+    // ---- ratio test (src/slam_frontend.cc:529-536), one lane per query
+    bool pass = false;
+    int i0 = -1, d0 = -1;
+    if (q < nq && part == 0) {
+      i0 = (k1 == kKeySentinel) ? -1 : int(k1 & kIdxMask);
+      d0 = (k1 == kKeySentinel) ? -1 : int(k1 >> kIdxBits);
+      const int i1 = (k2 == kKeySentinel) ? -1 : int(k2 & kIdxMask);
+      const int d1 = (k2 == kKeySentinel) ? -1 : int(k2 >> kIdxBits);
+      pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
+    }
+    // ---- publish this block's survivor count, fetch the ones before it
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) s_woff[warp] = __popc(bal);
+    __syncthreads();
+    unsigned total = 0, woff = 0;
+#pragma unroll
+    for (int w = 0; w < kFinThreads / 32; ++w) {
+      if (w < warp) woff += s_woff[w];
+      total += s_woff[w];
+    }
+    unsigned long long* flags = fa.flags + P.qb0;              // qb0 counts 32-query units
+    if (tid == 0) st_relaxed_u64(flags + qb, (fa.epoch << 8) | total);
+    if (warp == 0) {
+      // one warp polls (with a back-off: the other CTAs of the SM are still refining)
+      unsigned sum = 0;
+      for (int i = lane; i < qb; i += 32) {
+        unsigned long long v = ld_relaxed_u64(flags + i);
+        while ((v >> 8) != fa.epoch) {
+          __nanosleep(40);
+          v = ld_relaxed_u64(flags + i);
+        }
+        sum += unsigned(v & 0xFFull);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) s_base = sum;
+    }
+    __syncthreads();
+    const unsigned base = s_base;
+    // ---- ordered store (ascending queryIdx, what Frontend::GetMatches returns)
+    if (pass) {
+      int4 m;
+      m.x = q;                                  // queryIdx
+      m.y = i0;                                 // trainIdx
+      m.z = 0;                                  // imgIdx
+      m.w = __float_as_int(float(d0));          // distance
+      const unsigned dst = base + woff + __popc(bal & ((1u << lane) - 1u));
+      reinterpret_cast<int4*>(P.matches)[dst] = m;
+      if (batch.host_matches)
+        reinterpret_cast<int4*>(batch.host_matches + size_t(P.region) * batch.host_region_stride)[dst] = m;
+    }
+    if (qb == nqb - 1 && tid == 0) {
+      *P.match_count = int(base + total);
+      if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
+    }
+  } while (false);
+  if (tid == 0) ktrace_end(batch.ktrace, 2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -812,8 +1077,11 @@ cudaError_t launch_knn2_compact(const KnnBatch& batch, int max_nq, bool pdl, cud
 // ev (optional, 4 events): recorded before the main kernel, after it, after the refine and
 // after the compaction kernel (per-kernel timing for bench.py's roofline; an event between two
 // kernels removes their programmatic overlap, so it is only used in dedicated timing passes).
+// fa (optional): refine + compaction as ONE kernel (knn2_tc_finish_kernel; fa->nqb and the
+// grid are filled in here); ignored when the second neighbour's index is wanted.
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
-                           cudaEvent_t* ev, cudaStream_t stream) {
+                           cudaEvent_t* ev, cudaStream_t stream, FinishArgs* fa, int* launched) {
+  if (launched) *launched = 0;
   if (batch.num_problems <= 0 || tc.total <= 0) return cudaSuccess;
   cudaError_t e;
   // per-device attribute; setting it is a cheap host-side call
@@ -826,6 +1094,17 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
            : launch_pdl(knn2_tc_kernel<false>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
   if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[1], stream);
+  if (fa && !batch.exact_second) {
+    fa->nqb = (max_nq + kFinQ - 1) / kFinQ;
+    const int grid = fa->nqb * batch.num_problems;
+    e = launch_pdl(knn2_tc_finish_kernel, dim3(grid), dim3(kFinThreads), 0, stream, p, batch, tc, *fa);
+    if (ev) {
+      cudaEventRecord(ev[2], stream);
+      cudaEventRecord(ev[3], stream);
+    }
+    if (launched) *launched = 2;
+    return e;
+  }
   dim3 cgrid((max_nq + kCompactQB - 1) / kCompactQB, batch.num_problems);
   if (batch.exact_second) {
     dim3 rgrid((max_nq + kRefineQB - 1) / kRefineQB, batch.num_problems);
@@ -838,6 +1117,7 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
   if (ev) cudaEventRecord(ev[2], stream);
   e = launch_pdl(knn2_compact_kernel, cgrid, dim3(kCompactQB), 0, stream, p, batch);
   if (ev) cudaEventRecord(ev[3], stream);
+  if (launched) *launched = 3;
   return e;
 }
 

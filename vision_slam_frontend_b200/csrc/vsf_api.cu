@@ -27,7 +27,7 @@ cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int v
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
                                 int pdl, cudaStream_t stream, long long* ktrace);
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
-                           cudaEvent_t* ev, cudaStream_t stream);
+                           cudaEvent_t* ev, cudaStream_t stream, FinishArgs* fa, int* launched);
 cudaError_t launch_expand_train64(const void* t, int nt_bound, const int* nt_dev, void* out, int pdl,
                                   cudaStream_t stream);
 cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_nq, int pdl, cudaEvent_t* ev,
@@ -74,6 +74,17 @@ struct ProblemSpec {
   int t_exp_int8 = 1;
 };
 
+// A stream of poses (vsf_window_match_block_device): the train frame of the NEXT launch, expanded
+// by this launch's distance kernel; early = this launch's own image was made that way and its
+// partial keys go to the second buffer (TcBatch::early).
+struct NextExpand {
+  const void* src;
+  int nt;
+  uint8_t* out;
+  int early;
+  int odd;     // partial-key buffer of this launch (alternates from pose to pose)
+};
+
 struct vsf_ctx {
   int device = 0, max_features = 0, desc_bytes = 0, row_bytes = 0, words = 0, window = 0;
   int sm_count = 0;
@@ -88,7 +99,7 @@ struct vsf_ctx {
   int engine = 0;         // 0 auto, 1 POPC pipe, 2 tensor cores int8, 3 tensor cores e4m3
   int engine_flags = 0;   // timing experiments only (TcBatch::flags)
   long long* d_tc_trace = nullptr;   // engine flag 16: per-CTA timeline of knn2_tc_kernel
-  long long* d_ktrace = nullptr;     // engine flag 32: kernel-level timeline, kKtracePoses records of [5][2]
+  long long* d_ktrace = nullptr;     // engine flag 32: kernel-level timeline, kKtracePoses records of [8][2]
   long long ktrace_n = 0;
   int last_engine = 0;    // engine the last kNN launch used
   int want_second_index = 0;   // set around vsf_knn2's launch: the tensor engine's refine must produce the exact idx[1]
@@ -110,6 +121,12 @@ struct vsf_ctx {
   float2 *d_xy_left = nullptr, *d_xy_right = nullptr, *d_xy_left_c = nullptr, *d_xy_right_c = nullptr;
   uint4* d_knn_out = nullptr;
   uint2* d_partial = nullptr;
+  uint2* d_partial2 = nullptr;              // streams of poses: every other pose (allocated on first use)
+  long long launches = 0;                   // kernels launched by run_knn (vsf_debug_launch_count)
+  // knn2_tc_finish_kernel: ticket counter, per-block (epoch | survivor count) words, and the
+  // host's copies of the running values
+  unsigned long long *d_finish_ticket = nullptr, *d_finish_flags = nullptr;   // ticket: [2], alternating
+  unsigned long long finish_epoch = 0;
   size_t partial_cap = 0;
   unsigned *d_qblock_arrivals = nullptr, *d_qblock_pass = nullptr, *d_problem_arrivals = nullptr;
   vsf_dmatch* d_matches = nullptr;
@@ -368,7 +385,7 @@ static void plan_tc_partition(TcBatch* tbp, int qblocks, int sm, int force_split
 // latency: the call is a blocking / one-frame-at-a-time one (its own automatic-engine threshold,
 // see tc_auto_min_cmp_latency).
 static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio, bool mirror = false,
-                   bool latency = false) {
+                   bool latency = false, const NextExpand* next = nullptr) {
   if (specs.empty()) return VSF_OK;
   c->main_dirty = true;
   if (int(specs.size()) > kMaxProblems) return fail(c, VSF_ERR_CAPACITY, "too many problems in one batch");
@@ -463,7 +480,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     if (c->profile) VSF_CUDA(c, cudaEventRecord(c->pev[0], c->stream));
     long long* kt = nullptr;
     if ((c->engine_flags & 32) && c->d_ktrace) {   // kernel-level timeline, one record per launch (ring)
-      kt = c->d_ktrace + size_t(c->ktrace_n % kKtracePoses) * 10;
+      kt = c->d_ktrace + size_t(c->ktrace_n % kKtracePoses) * 16;
       ++c->ktrace_n;
     }
     b.ktrace = kt;
@@ -480,6 +497,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       else
         VSF_CUDA(c, launch_expand_train(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
                                         c->d_train_exp[k], int8, pdl, c->stream, kt));
+      ++c->launches;
     }
     TcBatch tb;
     std::memset(&tb, 0, sizeof(tb));
@@ -506,8 +524,29 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     b.split = tb.slots;
     if (wide)
       VSF_CUDA(c, launch_knn2_tc64(b, tb, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
-    else
-      VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
+    else {
+      // refine + compaction as one kernel (engine flag 512: the two separate kernels, A/B timing)
+      FinishArgs fa;
+      std::memset(&fa, 0, sizeof(fa));
+      fa.epoch = c->finish_epoch + 1;
+      fa.ticket = c->d_finish_ticket + (fa.epoch & 1ull);
+      fa.flags = c->d_finish_flags;
+      if (next) {
+        if (next->src && next->nt > 0) {
+          tb.exp_src = static_cast<const uint32_t*>(next->src);
+          tb.exp_nt = next->nt;
+          tb.exp_out = next->out;
+        }
+        tb.early = next->early;
+        if (next->odd) b.partial = c->d_partial2;
+      }
+      int launched = 0;
+      VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream,
+                                 (c->engine_flags & 512) ? nullptr : &fa, &launched));
+      if (launched == 2) ++c->finish_epoch;
+      c->launches += launched;
+    }
+    if (wide) c->launches += 3;
     c->pev_valid = c->profile != 0;
     return VSF_OK;
   }
@@ -540,6 +579,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     VSF_CUDA(c, cudaEventRecord(c->pev[1], c->stream));
   }
   VSF_CUDA(c, launch_knn2(b, c->words, R, mode, variant, max_qblocks, c->stream));
+  ++c->launches;
   if (c->profile) {
     for (int k = 2; k < 5; ++k) VSF_CUDA(c, cudaEventRecord(c->pev[k], c->stream));
     c->pev_valid = true;
@@ -582,7 +622,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
   }
   std::free(c->h_keys);
   void* dev[] = {c->d_ring, c->d_raw_left, c->d_raw_right, c->d_right_c, c->d_xy_left, c->d_xy_right,
-                 c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_qblock_arrivals,
+                 c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_partial2, c->d_finish_ticket, c->d_finish_flags, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
                  c->d_chunk_keep, c->d_chunk_off, c->d_ticket, c->d_kept_left, c->d_kept_right, c->d_slot_rows, c->d_thresh, c->d_X4,
                  c->d_tri_io, c->d_sink, c->d_fm, c->d_fm_count, c->d_train_exp[0], c->d_train_exp[1], c->d_tc_trace,
@@ -706,6 +746,10 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   cudaMemset(c->d_qblock_arrivals, 0, qb_cap * sizeof(unsigned));
   cudaMemset(c->d_qblock_pass, 0, qb_cap * sizeof(unsigned));
   cudaMemset(c->d_problem_arrivals, 0, kMaxProblems * sizeof(unsigned));
+  VSF_ALLOC(c, c->d_finish_ticket, 2 * sizeof(unsigned long long));
+  VSF_ALLOC(c, c->d_finish_flags, (qb_cap + 8) * sizeof(unsigned long long));
+  cudaMemset(c->d_finish_ticket, 0, 2 * sizeof(unsigned long long));
+  cudaMemset(c->d_finish_flags, 0, (qb_cap + 8) * sizeof(unsigned long long));   // epoch 0 is never used
   VSF_ALLOC(c, c->d_matches, rows_cap * sizeof(vsf_dmatch));
   c->match_base = c->d_matches;
   VSF_ALLOC(c, c->d_match_count, kMaxProblems * sizeof(int));
@@ -761,6 +805,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC_HOST(c, c->h_fm, size_t(window) * N * sizeof(vsf_feature_match));
   if (const char* e = std::getenv("VSF_RESERVE_SMS")) c->reserve_override = std::atoi(e);
   if (const char* e = std::getenv("VSF_SORT_STREAMS")) c->sort_streams = std::atoi(e) == 1 ? 1 : 2;
+  if (const char* e = std::getenv("VSF_ENGINE_FLAGS")) c->engine_flags = std::atoi(e) & (8 | 64 | 128 | 256 | 512 | 1024);   // A/B timing
   if (const char* e = std::getenv("VSF_ENGINE")) {   // test / bench override of the automatic choice
     const int v = std::atoi(e);
     if (v >= 0 && v <= 3 && (v < 3 || c->words == 8)) c->engine = v;
@@ -838,7 +883,7 @@ extern "C" int vsf_set_engine(vsf_ctx* c, int engine, int flags) {
   if (flags & 32) {
     // kernel-level timeline: starts = +inf, ends = 0
     cudaSetDevice(c->device);
-    std::vector<long long> init(size_t(kKtracePoses) * 10);
+    std::vector<long long> init(size_t(kKtracePoses) * 16);
     for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0 : 0x7fffffffffffffffLL;
     if (!c->d_ktrace) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_ktrace), init.size() * sizeof(long long)));
     VSF_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1889,12 +1934,39 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
   cudaSetDevice(c->device);
   const size_t fb = size_t(n) * c->row_bytes;
   const uint8_t* base = static_cast<const uint8_t*>(d_seq);
+  auto pose_frame = [&](int k) { return (first + k) % (n_poses - W) + W; };
+  // Tensor engine, 32-byte rows: every pose's distance kernel also expands the NEXT pose's current
+  // frame (into the other of the two image buffers), so a pose is two kernels - distance +
+  // finish - and the distance kernel, which then depends on nothing its stream predecessor
+  // writes, starts as soon as that one's CTAs leave the SMs (engine flag 256: pose-by-pose
+  // launches, 1024: no early start; A/B timing).
+  const bool tensor = c->engine >= 2 || (c->engine == 0 && double(W) * double(n) * double(n) >= c->tc_auto_min_cmp);
+  const bool ahead = tensor && c->words == 8 && n > 0 && count > 0 && !(c->engine_flags & (256 | 512));
+  const int int8 = c->engine == 3 ? 0 : 1;
+  if (ahead) {
+    if (!c->d_partial2) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_partial2), c->partial_cap * sizeof(uint2)));
+    VSF_CUDA(c, launch_expand_train(base + size_t(pose_frame(0)) * fb, n, nullptr, c->d_train_exp[0], int8,
+                                    (c->engine_flags & 8) ? 0 : 1, c->stream, nullptr));
+    ++c->launches;
+  }
   std::vector<ProblemSpec> specs(W);
   for (int k = 0; k < count; ++k) {
-    const long long cur = (first + k) % (n_poses - W) + W;
-    for (int j = 0; j < W; ++j)
+    const long long cur = pose_frame(k);
+    for (int j = 0; j < W; ++j) {
       specs[j] = ProblemSpec{base + size_t(cur - W + j) * fb, n, nullptr, base + size_t(cur) * fb, n, nullptr, j};
-    const int rc = run_knn(c, specs, ratio);
+      if (ahead) {
+        specs[j].t_exp = c->d_train_exp[k & 1];
+        specs[j].t_exp_int8 = int8;
+      }
+    }
+    int rc;
+    if (ahead) {
+      const NextExpand nx{k + 1 < count ? base + size_t(pose_frame(k + 1)) * fb : nullptr, n, c->d_train_exp[(k + 1) & 1],
+                          (k > 0 && !(c->engine_flags & (8 | 1024))) ? 1 : 0, k & 1};
+      rc = run_knn(c, specs, ratio, false, false, &nx);
+    } else {
+      rc = run_knn(c, specs, ratio);
+    }
     if (rc) return rc;
   }
   c->last_n_frames = W;
@@ -1963,6 +2035,8 @@ extern "C" int vsf_device_match_lists(vsf_ctx* c, const vsf_dmatch** d_lists, co
   *regions = c->window;
   return VSF_OK;
 }
+
+extern "C" long long vsf_debug_launch_count(const vsf_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" void* vsf_stream(vsf_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 
@@ -2067,7 +2141,7 @@ extern "C" int vsf_debug_kernel_trace(vsf_ctx* c, long long* out, int max_record
   cudaSetDevice(c->device);
   VSF_CUDA(c, cudaStreamSynchronize(c->stream));
   const int n = int(std::min<long long>(std::min<long long>(max_records, kKtracePoses), c->ktrace_n));
-  VSF_CUDA(c, cudaMemcpy(out, c->d_ktrace, size_t(n) * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+  VSF_CUDA(c, cudaMemcpy(out, c->d_ktrace, size_t(n) * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   *n_records = n;
   return VSF_OK;
 }

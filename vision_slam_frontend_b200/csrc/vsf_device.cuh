@@ -61,7 +61,7 @@ struct KnnBatch {
   vsf_dmatch* host_matches;
   int* host_counts;
   int host_region_stride;
-  long long* ktrace;   // engine flag 32: [5][2] earliest start / latest end (globaltimer ns) of expand, distance, refine, compaction, refine-after-wait
+  long long* ktrace;   // engine flag 32: [8][2] earliest start / latest end (globaltimer ns) of expand, distance, refine, compaction, refine-after-wait; 5..7 spare
   KnnProblem p[kMaxProblems];
 };
 
@@ -102,8 +102,28 @@ struct TcBatch {
   int unit_q;                          // 64-byte engine: queries per block (128: one CTA per unit, 256: a CTA pair per unit)
   int flags;                           // bring-up knobs (timing experiments; results invalid): 2 = skip the bucket reduction, 4 = skip the TMEM loads
   long long* trace;                    // flag 16 (builds with -DVSF_TC_TRACE): per-CTA timeline, kTcTraceSlots values per CTA
+  // A stream of poses (vsf_window_match_block_device).  exp_src != nullptr: the distance kernel
+  // also expands the NEXT launch's train frame (packed rows exp_src, exp_nt of them) into
+  // exp_out, each CTA its share, while its epilogue warps wait for the first accumulators.
+  // early != 0: everything this launch reads was complete before its stream predecessor (the
+  // previous pose's finish kernel) let it launch, and its partial keys go to another buffer than
+  // the one that kernel reads: it starts without waiting for the predecessor and only waits for
+  // it just before it exits (so that "complete" still implies "everything before it complete").
+  const uint32_t* exp_src;
+  uint8_t* exp_out;
+  int exp_nt;
+  int early;
 };
 constexpr int kTcTraceSlots = 16;
+
+// Arguments of knn2_tc_finish_kernel (refine + ordered compaction in one kernel, see there).
+struct FinishArgs {
+  unsigned long long* ticket;        // (epoch << 24 | next block): raised to this launch's epoch by its first CTAs
+  unsigned long long* flags;         // [32-query blocks of the batch, KnnProblem::qb0 + block] (epoch << 8 | survivors)
+  unsigned long long epoch;
+  int nqb;                           // 32-query blocks per problem (grid = nqb * num_problems)
+};
+
 
 // CTA that owns slot x = the largest i with floor(i*T/G) <= x
 __host__ __device__ __forceinline__ int tc_owner(long long x, long long T, int G) {
@@ -180,6 +200,12 @@ __device__ __forceinline__ long long globaltimer_ns() {
 }
 __device__ __forceinline__ void ktrace_start(long long* kt, int k) {
   if (kt) atomicMin(reinterpret_cast<long long*>(kt + 2 * k), globaltimer_ns());
+}
+__device__ __forceinline__ void ktrace_minmax(long long* kt, int k, long long v) {
+  if (kt) {
+    atomicMin(reinterpret_cast<long long*>(kt + 2 * k), v);
+    atomicMax(reinterpret_cast<long long*>(kt + 2 * k + 1), v);
+  }
 }
 __device__ __forceinline__ void ktrace_end(long long* kt, int k) {
   if (kt) atomicMax(reinterpret_cast<long long*>(kt + 2 * k + 1), globaltimer_ns());
