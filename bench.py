@@ -509,14 +509,19 @@ def run_b200(a):
                         "comparison; the tensor-core engine is not bound by it (frac > 1)",
             },
             "gpu_launches": int(launches),
-            "kernel": (("knn2_tc (distance) + knn2_tc_finish (refine + ordered compaction + expansion of the next "
-                        "pose's frame) kernels, 2 launches per pose, programmatic dependent launch")
+            "kernel": (("knn2_tc (distance) + knn2_tc_finish (refine + ordered compaction) kernels, 2 launches per "
+                        "pose, launched in groups of poses (the distance kernels of a group back to back, then "
+                        "its finish kernels side by side), programmatic dependent launch")
                        if two_kernels else
                        ("expand_train + knn2_tc + refine + compact kernels "
                         "(4 launches per pose, programmatic dependent launch)")) if tensor
                       else "vsf::knn2_kernel<WORDS,R,MODE> (one launch per pose)",
-            "kernel_ms": {"expand_train": float(kt[0]), "main": float(kt[1]), "refine": float(kt[2]),
-                          "compact": float(kt[3])},
+            "kernel_ms": ({"expand_train": float(kt[0]), "main": float(kt[1]), "finish": float(kt[2]),
+                           "note": "CUDA events around every kernel of a pose launched alone (the events serialise "
+                                   "kernels that overlap in the timed region)"}
+                          if two_kernels else
+                          {"expand_train": float(kt[0]), "main": float(kt[1]), "refine": float(kt[2]),
+                           "compact": float(kt[3])}),
             "last_step_survivors": [int(c) for c in counts],
             "clocks": clocks.summary(),
         }

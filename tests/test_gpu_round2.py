@@ -322,21 +322,27 @@ def test_window_match_block_device(width):
 @pytest.mark.parametrize("n,W,count", [(1400, 4, 1), (1400, 4, 2), (1400, 4, 3), (1400, 4, 6), (1237, 3, 5),
                                         (2900, 2, 4), (700, 10, 9), (130, 38, 3), (3000, 1, 3)])
 def test_block_device_launch_variants(n, W, count):
-    """A pose of a device-resident block is two kernels (distance, which also expands the next
-    pose's frame and starts without waiting for its predecessor, + finish); with the look-ahead
-    off (engine flag 256) three, with refine and compaction as separate kernels (512) four; 1024
-    = no early start.  Same lists every way, equal to the oracle's."""
+    """A pose of a device-resident block is two kernels (distance + finish), launched in groups
+    (all distance kernels of a group, then all its finish kernels, the first of which expands
+    the next group's frames); group 1: the distance kernel expands the next pose's frame.  Engine flag
+    256 = pose by pose (three kernels), 512 = refine and compaction as separate kernels (four),
+    1024 = no early starts.  Same lists every way, equal to the oracle's."""
     import torch
+    from vision_slam_frontend_b200 import capi
     poses, stride, seed = W + 9, 97, 5
     with new_ctx(max_features=3072, window=W) as ctx:
         buf = torch.empty((poses, n, 32), dtype=torch.uint8, device="cuda")
         ctx.synth_sequence_device(buf.data_ptr(), n, 0, poses, stride, seed)
         got = {}
-        for flags, per_pose, extra in ((0, 2, 1), (256, 3, 0), (512, 4, 0), (1024, 2, 1), (0, 2, 1)):
+        for group, flags, per_pose in ((4, 0, 2), (1, 0, 2), (3, 0, 2), (8, 0, 2), (2, 1024, 2), (1, 1024, 2), (4, 256, 3),
+                                       (4, 512, 4), (4, 0, 2)):
+            ctx.set_option(capi.OPT_POSE_GROUP, group)
             ctx.set_engine(2, flags)
             before = ctx.launch_count()
             ctx.window_match_block_device(buf.data_ptr(), n, poses, 2, count, RATIO)
             got[len(got)] = ctx.fetch_window(W)
+            # + the expansion of the first pose's / group's frames (flags 256 / 512: one per pose, in per_pose)
+            extra = 0 if flags & (256 | 512) else 1
             assert ctx.launch_count() - before == per_pose * count + extra
     cur = ((2 + count - 1) % (poses - W)) + W
     for j in range(W):

@@ -50,6 +50,10 @@ def main():
         return best
 
     res = {"features": n, "window": W, "desc_bytes": width}
+    from vision_slam_frontend_b200 import capi
+    for g in (4, 1, 4, 1, 4):
+        ctx.set_option(capi.OPT_POSE_GROUP, g)
+        res.setdefault("us_per_pose_group", {})[f"{g}" if f"{g}" not in res.get("us_per_pose_group", {}) else f"{g}_again"] = timed(0)
     res["us_per_pose_two_kernels"] = timed(0)
     res["us_per_pose_three_kernels"] = timed(256)
     res["us_per_pose_four_kernels"] = timed(512)
@@ -58,27 +62,28 @@ def main():
     counts = ctx.fetch_window(W, with_matches=False)
     res["survivors_last_pose"] = [int(c) for c in counts]
 
-    # timeline of one chained block
-    names = ["expand", "distance", "refine", "compact", "refine_after_wait"]
-    for label, flags in (("two_kernels", 32), ("two_kernels_no_early_start", 32 | 1024), ("four_kernels", 32 | 512)):
+    # kernel-level timeline of a block of poses (one record per kernel sequence launched: with pose
+    # groups a pose has one record for its distance kernel and one for its finish kernel)
+    for label, flags, group in (("group_4", 32, 4), ("group_1", 32, 1), ("four_kernels", 32 | 512, 4)):
+        ctx.set_option(capi.OPT_POSE_GROUP, group)
         ctx.set_engine(2, flags)
         ctx.window_match_block_device(base, n, n_poses, 3, 40, RATIO)
         buf = np.zeros((256, 8, 2), np.int64)
         got = C.c_int(0)
         ctx._check(ctx._L.vsf_debug_kernel_trace(ctx._h, buf.ctypes.data, 256, C.byref(got)))
         tr = buf[: got.value].astype(np.float64)
-        t0 = tr[20, 1, 0]
-        rows = []
-        for p in range(20, 24):
-            rows.append({names[k]: [round((tr[p, k, 0] - t0) / 1e3, 2), round((tr[p, k, 1] - t0) / 1e3, 2)] for k in range(5)})
-        extra = {}
-        res["timeline_" + label] = {
-            **extra,
-            "us_between_distance_kernel_starts_median": float(np.median(np.diff(tr[4:, 1, 0])) / 1e3),
-            "distance_us_median": float(np.median(tr[4:, 1, 1] - tr[4:, 1, 0]) / 1e3),
-            "gap_distance_end_to_next_start_median": float(np.median(tr[5:, 1, 0] - tr[4:-1, 1, 1]) / 1e3),
-            "poses_20_23_us_[start,end]": rows,
-        }
+        recs = []
+        lo = 32 if group > 1 and not (flags & 512) else 16
+        t0 = None
+        for p in range(lo, min(lo + 16, got.value)):
+            r = {}
+            for k, name in ((1, "distance"), (2, "finish")):
+                if tr[p, k, 1] > 0:   # the kernel ran in this record
+                    if t0 is None:
+                        t0 = tr[p, k, 0]
+                    r[name] = [round((tr[p, k, 0] - t0) / 1e3, 2), round((tr[p, k, 1] - t0) / 1e3, 2)]
+            recs.append(r)
+        res["timeline_" + label] = recs
     ctx.set_engine(0, 0)
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     with open(out_path, "w") as f:

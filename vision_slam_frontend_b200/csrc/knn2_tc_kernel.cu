@@ -98,6 +98,35 @@ expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __r
   if (threadIdx.x == 0) ktrace_end(kt, 0);
 }
 
+// One (row, group of 4 K-chunks) item of a frame's image (the unit of work of every expansion).
+template <bool I8>
+__device__ __forceinline__ void expand_item(const uint32_t* __restrict__ t, int nt, uint8_t* __restrict__ out, int row, int cg) {
+  uint2 w = make_uint2(0u, 0u);
+  const bool live = row < nt;
+  if (live) w = __ldg(reinterpret_cast<const uint2*>(t + size_t(row) * 8) + cg);
+  const int tile = row / kTcTileRows, r = row % kTcTileRows;
+  uint8_t* base = out + size_t(tile) * kTcBBytes + size_t(r) * 16;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t word = (c < 2) ? w.x : w.y;
+    const uint32_t b16 = (word >> (16 * (c & 1))) & 0xFFFFu;
+    uint4 v = live ? expand16<I8>(b16) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(base + size_t(4 * cg + c) * (kTcTileRows * 16)) = v;
+  }
+}
+
+// The same for the frames of a group of poses, blockIdx.y = frame.
+template <bool I8>
+__global__ void __launch_bounds__(256)
+expand_train_multi_kernel(const __grid_constant__ ExpandMulti em) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int rows_pad = (em.nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_pad * 4) return;
+  expand_item<I8>(em.src[blockIdx.y], em.nt, em.out[blockIdx.y], idx % rows_pad, idx / rows_pad);
+}
+
 // ---------------------------------------------------------------------------------------------
 // TcBatch::flags 2 / 4 (skip the bucket reduction / the TMEM loads: timing experiments whose
 // results are invalid) only exist in builds with -DVSF_TC_BRINGUP
@@ -826,10 +855,13 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
 // launches, whose CTAs may be starting while the previous launch is still running, alternate
 // between two ticket counters.
 constexpr int kFinLanes = 4;                          // lanes per query
-constexpr int kFinThreads = 128;
+#ifndef VSF_FIN_THREADS
+#define VSF_FIN_THREADS 256
+#endif
+constexpr int kFinThreads = VSF_FIN_THREADS;
 constexpr int kFinQ = kFinThreads / kFinLanes;        // queries per CTA (= one survivor counter)
 static_assert(kFinLanes == 4 && kTcBucket % 8 == 0, "knn2_tc_finish_kernel: 4 lanes x 4 steps of 2 rows");
-static_assert(kFinQ == 32, "FinishArgs::flags is indexed in 32-query units (KnnProblem::qb0)");
+static_assert(kFinQ % 32 == 0 && kFinQ <= 128, "FinishArgs::flags is indexed in 32-query units (KnnProblem::qb0); the count has 8 bits");
 
 // The look-back words carry their payload themselves (epoch | count): relaxed accesses at GPU
 // scope are enough, and an acquire load in the polling loop would invalidate the SM's L1 on
@@ -843,7 +875,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(kFinThreads, 12)
+__global__ void __launch_bounds__(kFinThreads, 1536 / kFinThreads)
 knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc,
                       const __grid_constant__ FinishArgs fa) {
   __shared__ unsigned s_woff[kFinThreads / 32];
@@ -853,6 +885,16 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   const int warp = tid >> 5, lane = tid & 31;
   const int part = tid % kFinLanes;
   if (tid == 0) ktrace_start(batch.ktrace, 2);
+  if (fa.nowait) pdl_launch_dependents();
+  if (fa.em.frames > 0) {
+    // the next group's train images; nothing here depends on the running distance kernels
+    const int rows_pad = (fa.em.nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
+    for (int f = 0; f < fa.em.frames; ++f)
+      for (int idx = blockIdx.x * kFinThreads + tid; idx < rows_pad * 4; idx += gridDim.x * kFinThreads) {
+        if (fa.em_int8) expand_item<true>(fa.em.src[f], fa.em.nt, fa.em.out[f], idx % rows_pad, idx / rows_pad);
+        else expand_item<false>(fa.em.src[f], fa.em.nt, fa.em.out[f], idx % rows_pad, idx / rows_pad);
+      }
+  }
   // one block per CTA, taken by ticket (the do-while only gives the early exits a common end)
   do {
     if (tid == 0) {
@@ -878,9 +920,11 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     // lane `part` of a query works on 16-byte half `part & 1` of every second row of the bucket
     uint4 qh = make_uint4(0u, 0u, 0u, 0u);
     if (q < nq) qh = __ldg(reinterpret_cast<const uint4*>(P.q + size_t(q) * 8) + (part & 1));
-    pdl_wait();                                // the partial bucket keys are complete
-    if (tid == 0) ktrace_start(batch.ktrace, 4);
-    pdl_launch_dependents();
+    if (!fa.nowait) {
+      pdl_wait();                              // the partial bucket keys are complete
+      if (tid == 0) ktrace_start(batch.ktrace, 4);
+      pdl_launch_dependents();
+    }
     if (nq <= 0) {                             // CTA-uniform, like the next test
       if (qb == 0 && tid == 0) {
         *P.match_count = 0;
@@ -977,16 +1021,16 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       if (w < warp) woff += s_woff[w];
       total += s_woff[w];
     }
-    unsigned long long* flags = fa.flags + P.qb0;              // qb0 counts 32-query units
-    if (tid == 0) st_relaxed_u64(flags + qb, (fa.epoch << 8) | total);
+    unsigned long long* flags = fa.flags + P.qb0;              // qb0 counts 32-query units: every (kFinQ / 32)-th word is used
+    if (tid == 0) st_relaxed_u64(flags + qb * (kFinQ / 32), (fa.epoch << 8) | total);
     if (warp == 0) {
       // one warp polls (with a back-off: the other CTAs of the SM are still refining)
       unsigned sum = 0;
       for (int i = lane; i < qb; i += 32) {
-        unsigned long long v = ld_relaxed_u64(flags + i);
+        unsigned long long v = ld_relaxed_u64(flags + i * (kFinQ / 32));
         while ((v >> 8) != fa.epoch) {
           __nanosleep(40);
-          v = ld_relaxed_u64(flags + i);
+          v = ld_relaxed_u64(flags + i * (kFinQ / 32));
         }
         sum += unsigned(v & 0xFFull);
       }
@@ -1013,6 +1057,7 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
     }
   } while (false);
+  if (fa.nowait) pdl_wait();
   if (tid == 0) ktrace_end(batch.ktrace, 2);
 }
 
@@ -1031,6 +1076,15 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+cudaError_t launch_expand_train_multi(const ExpandMulti& em, int int8, int pdl, cudaStream_t stream) {
+  if (em.frames <= 0 || em.nt <= 0) return cudaSuccess;
+  const int rows_pad = (em.nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
+  constexpr int kExpandThreads = 128;
+  const dim3 grid((rows_pad * 4 + kExpandThreads - 1) / kExpandThreads, em.frames);
+  return int8 ? launch_pdl(expand_train_multi_kernel<true>, grid, dim3(kExpandThreads), 0, stream, pdl != 0, em)
+              : launch_pdl(expand_train_multi_kernel<false>, grid, dim3(kExpandThreads), 0, stream, pdl != 0, em);
 }
 
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
@@ -1079,8 +1133,10 @@ cudaError_t launch_knn2_compact(const KnnBatch& batch, int max_nq, bool pdl, cud
 // kernels removes their programmatic overlap, so it is only used in dedicated timing passes).
 // fa (optional): refine + compaction as ONE kernel (knn2_tc_finish_kernel; fa->nqb and the
 // grid are filled in here); ignored when the second neighbour's index is wanted.
+// phase: 0 = the whole sequence, 1 = the distance kernel only, 2 = the finish kernel only (a
+// group of poses: first every pose's distance kernel, then every pose's finish kernel).
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
-                           cudaEvent_t* ev, cudaStream_t stream, FinishArgs* fa, int* launched) {
+                           cudaEvent_t* ev, cudaStream_t stream, FinishArgs* fa, int* launched, int phase) {
   if (launched) *launched = 0;
   if (batch.num_problems <= 0 || tc.total <= 0) return cudaSuccess;
   cudaError_t e;
@@ -1090,10 +1146,14 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
   if (e != cudaSuccess) return e;
   const bool p = pdl != 0;
   if (ev) cudaEventRecord(ev[0], stream);
-  e = int8 ? launch_pdl(knn2_tc_kernel<true>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc)
-           : launch_pdl(knn2_tc_kernel<false>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
-  if (e != cudaSuccess) return e;
+  if (phase != 2) {
+    e = int8 ? launch_pdl(knn2_tc_kernel<true>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc)
+             : launch_pdl(knn2_tc_kernel<false>, dim3(tc.grid), dim3(kTcThreads), kTcSmemBytes, stream, p, batch, tc);
+    if (e != cudaSuccess) return e;
+    if (launched) *launched = 1;
+  }
   if (ev) cudaEventRecord(ev[1], stream);
+  if (phase == 1) return cudaSuccess;
   if (fa && !batch.exact_second) {
     fa->nqb = (max_nq + kFinQ - 1) / kFinQ;
     const int grid = fa->nqb * batch.num_problems;
@@ -1102,9 +1162,10 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
       cudaEventRecord(ev[2], stream);
       cudaEventRecord(ev[3], stream);
     }
-    if (launched) *launched = 2;
+    if (launched) *launched = phase == 2 ? 1 : 2;
     return e;
   }
+  if (phase == 2) return cudaErrorInvalidValue;
   dim3 cgrid((max_nq + kCompactQB - 1) / kCompactQB, batch.num_problems);
   if (batch.exact_second) {
     dim3 rgrid((max_nq + kRefineQB - 1) / kRefineQB, batch.num_problems);

@@ -27,7 +27,8 @@ cudaError_t launch_knn2(const KnnBatch& batch, int words, int R, int mode, int v
 cudaError_t launch_expand_train(const void* t, int nt_bound, const int* nt_dev, void* out, int int8,
                                 int pdl, cudaStream_t stream, long long* ktrace);
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
-                           cudaEvent_t* ev, cudaStream_t stream, FinishArgs* fa, int* launched);
+                           cudaEvent_t* ev, cudaStream_t stream, FinishArgs* fa, int* launched, int phase);
+cudaError_t launch_expand_train_multi(const ExpandMulti& em, int int8, int pdl, cudaStream_t stream);
 cudaError_t launch_expand_train64(const void* t, int nt_bound, const int* nt_dev, void* out, int pdl,
                                   cudaStream_t stream);
 cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_nq, int pdl, cudaEvent_t* ev,
@@ -74,15 +75,19 @@ struct ProblemSpec {
   int t_exp_int8 = 1;
 };
 
-// A stream of poses (vsf_window_match_block_device): the train frame of the NEXT launch, expanded
-// by this launch's distance kernel; early = this launch's own image was made that way and its
-// partial keys go to the second buffer (TcBatch::early).
-struct NextExpand {
-  const void* src;
-  int nt;
-  uint8_t* out;
-  int early;
-  int odd;     // partial-key buffer of this launch (alternates from pose to pose)
+// A stream of poses (vsf_window_match_block_device): how one pose's kernels are launched.
+struct PoseLaunch {
+  int phase = 0;                  // 0 distance + finish, 1 distance kernel only, 2 finish kernel only
+  // the distance kernel expands the NEXT pose's train frame (one pose at a time: group size 1)
+  const void* exp_src = nullptr;
+  int exp_nt = 0;
+  uint8_t* exp_out = nullptr;
+  int early = 0;                  // TcBatch::early
+  uint2* partial = nullptr;       // partial-key buffer of this pose (nullptr: the ctx's)
+  unsigned long long* flags = nullptr;    // look-back words / ticket counter of this pose's finish kernel
+  unsigned long long* ticket = nullptr;   //   (nullptr: the ctx's)
+  int nowait = 0;                 // FinishArgs::nowait
+  const ExpandMulti* em = nullptr;   // FinishArgs::em (the first finish kernel of a group)
 };
 
 struct vsf_ctx {
@@ -122,6 +127,14 @@ struct vsf_ctx {
   uint4* d_knn_out = nullptr;
   uint2* d_partial = nullptr;
   uint2* d_partial2 = nullptr;              // streams of poses: every other pose (allocated on first use)
+  // groups of poses (vsf_window_match_block_device): per-slot buffers, allocated on first use
+  int pose_group = 4;                       // VSF_POSE_GROUP (1 .. kMaxPoseGroup)
+  uint2* grp_partial[2 * kMaxPoseGroup] = {};
+  uint8_t* grp_exp[2 * kMaxPoseGroup] = {};
+  unsigned long long* grp_flags = nullptr;  // [kMaxPoseGroup][qb_cap + 8] + [kMaxPoseGroup] ticket counters
+  vsf_dmatch* grp_matches = nullptr;        // [kMaxPoseGroup - 1][regions][rows_pad]
+  int* grp_counts = nullptr;                // [kMaxPoseGroup - 1][kMaxProblems]
+  size_t qb_cap = 0;
   long long launches = 0;                   // kernels launched by run_knn (vsf_debug_launch_count)
   // knn2_tc_finish_kernel: ticket counter, per-block (epoch | survivor count) words, and the
   // host's copies of the running values
@@ -385,7 +398,7 @@ static void plan_tc_partition(TcBatch* tbp, int qblocks, int sm, int force_split
 // latency: the call is a blocking / one-frame-at-a-time one (its own automatic-engine threshold,
 // see tc_auto_min_cmp_latency).
 static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio, bool mirror = false,
-                   bool latency = false, const NextExpand* next = nullptr) {
+                   bool latency = false, const PoseLaunch* pose = nullptr) {
   if (specs.empty()) return VSF_OK;
   c->main_dirty = true;
   if (int(specs.size()) > kMaxProblems) return fail(c, VSF_ERR_CAPACITY, "too many problems in one batch");
@@ -531,19 +544,28 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       fa.epoch = c->finish_epoch + 1;
       fa.ticket = c->d_finish_ticket + (fa.epoch & 1ull);
       fa.flags = c->d_finish_flags;
-      if (next) {
-        if (next->src && next->nt > 0) {
-          tb.exp_src = static_cast<const uint32_t*>(next->src);
-          tb.exp_nt = next->nt;
-          tb.exp_out = next->out;
+      int phase = 0;
+      if (pose) {
+        if (pose->exp_src && pose->exp_nt > 0) {
+          tb.exp_src = static_cast<const uint32_t*>(pose->exp_src);
+          tb.exp_nt = pose->exp_nt;
+          tb.exp_out = pose->exp_out;
         }
-        tb.early = next->early;
-        if (next->odd) b.partial = c->d_partial2;
+        tb.early = pose->early;
+        if (pose->partial) b.partial = pose->partial;
+        if (pose->flags) fa.flags = pose->flags;
+        if (pose->ticket) fa.ticket = pose->ticket;
+        fa.nowait = pose->nowait;
+        if (pose->em) {
+          fa.em = *pose->em;
+          fa.em_int8 = int8;
+        }
+        phase = pose->phase;
       }
       int launched = 0;
       VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream,
-                                 (c->engine_flags & 512) ? nullptr : &fa, &launched));
-      if (launched == 2) ++c->finish_epoch;
+                                 (c->engine_flags & 512) ? nullptr : &fa, &launched, phase));
+      if (phase != 1 && !(c->engine_flags & 512)) ++c->finish_epoch;
       c->launches += launched;
     }
     if (wide) c->launches += 3;
@@ -621,6 +643,13 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
     for (std::thread& t : c->workers) t.join();
   }
   std::free(c->h_keys);
+  for (uint2* p : c->grp_partial)
+    if (p && p != c->d_partial && p != c->d_partial2) cudaFree(p);
+  for (uint8_t* p : c->grp_exp)
+    if (p && p != c->d_train_exp[0] && p != c->d_train_exp[1]) cudaFree(p);
+  if (c->grp_flags) cudaFree(c->grp_flags);
+  if (c->grp_matches) cudaFree(c->grp_matches);
+  if (c->grp_counts) cudaFree(c->grp_counts);
   void* dev[] = {c->d_ring, c->d_raw_left, c->d_raw_right, c->d_right_c, c->d_xy_left, c->d_xy_right,
                  c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_partial2, c->d_finish_ticket, c->d_finish_flags, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
@@ -740,6 +769,8 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   c->partial_cap = rows_cap * 16 + 262144;
   VSF_ALLOC(c, c->d_partial, c->partial_cap * sizeof(uint2));
   const size_t qb_cap = rows_cap / 32 + kMaxProblems * 4;
+  c->qb_cap = qb_cap;
+  if (const char* e = std::getenv("VSF_POSE_GROUP")) c->pose_group = std::max(1, std::min(kMaxPoseGroup, std::atoi(e)));
   VSF_ALLOC(c, c->d_qblock_arrivals, qb_cap * sizeof(unsigned));
   VSF_ALLOC(c, c->d_qblock_pass, qb_cap * sizeof(unsigned));
   VSF_ALLOC(c, c->d_problem_arrivals, kMaxProblems * sizeof(unsigned));
@@ -1630,6 +1661,11 @@ extern "C" int vsf_set_option(vsf_ctx* c, int option, int value) {
     c->sort_depth_override = value;
     return VSF_OK;
   }
+  if (option == VSF_OPT_POSE_GROUP) {
+    if (value < 1 || value > kMaxPoseGroup) return fail(c, VSF_ERR_BAD_ARG, "pose group must be 1 .. 8");
+    c->pose_group = value;
+    return VSF_OK;
+  }
   if (value != 0 && value != 1) return fail(c, VSF_ERR_BAD_ARG, "option value must be 0 or 1");
   switch (option) {
     case VSF_OPT_RESIDUAL_ORDER: c->opt_residual_order = value; return VSF_OK;
@@ -1644,6 +1680,7 @@ extern "C" int vsf_get_option(const vsf_ctx* c, int option, int* value) {
     case VSF_OPT_RESIDUAL_ORDER: *value = c->opt_residual_order; return VSF_OK;
     case VSF_OPT_HOLD_THRESHOLD_ON_EMPTY: *value = c->opt_hold_on_empty; return VSF_OK;
     case VSF_OPT_DEBUG_SORT_DEPTH: *value = c->sort_depth_override; return VSF_OK;
+    case VSF_OPT_POSE_GROUP: *value = c->pose_group; return VSF_OK;
     default: return VSF_ERR_BAD_ARG;
   }
 }
@@ -1935,35 +1972,129 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
   const size_t fb = size_t(n) * c->row_bytes;
   const uint8_t* base = static_cast<const uint8_t*>(d_seq);
   auto pose_frame = [&](int k) { return (first + k) % (n_poses - W) + W; };
-  // Tensor engine, 32-byte rows: every pose's distance kernel also expands the NEXT pose's current
-  // frame (into the other of the two image buffers), so a pose is two kernels - distance +
-  // finish - and the distance kernel, which then depends on nothing its stream predecessor
-  // writes, starts as soon as that one's CTAs leave the SMs (engine flag 256: pose-by-pose
-  // launches, 1024: no early start; A/B timing).
+  // Tensor engine, 32-byte rows (engine flag 256: pose-by-pose launches, 1024: no early start;
+  // A/B timing).  A pose is two kernels, distance + finish, and the poses are launched in groups
+  // of G (ctx pose_group, VSF_POSE_GROUP): first the G distance kernels - each starts as soon as
+  // its predecessor's CTAs leave the SMs, it depends on nothing that one writes - then the G
+  // finish kernels, which run side by side; the first of them also expands the NEXT group's
+  // current frames.  The per-launch latencies between a distance kernel and the finish kernel that
+  // needs all of its CTAs' partial keys are paid once per group instead of once per pose.
+  // Per-slot buffers: partial keys and +-1 images 2 G deep (a group writes while the previous
+  // one is read), look-back words / ticket counters and survivor lists G deep; the last pose of
+  // the call writes the ctx's own lists (vsf_fetch_window).  With G = 1 the distance kernel
+  // expands the next pose's frame itself.
   const bool tensor = c->engine >= 2 || (c->engine == 0 && double(W) * double(n) * double(n) >= c->tc_auto_min_cmp);
   const bool ahead = tensor && c->words == 8 && n > 0 && count > 0 && !(c->engine_flags & (256 | 512));
   const int int8 = c->engine == 3 ? 0 : 1;
-  if (ahead) {
-    if (!c->d_partial2) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_partial2), c->partial_cap * sizeof(uint2)));
-    VSF_CUDA(c, launch_expand_train(base + size_t(pose_frame(0)) * fb, n, nullptr, c->d_train_exp[0], int8,
-                                    (c->engine_flags & 8) ? 0 : 1, c->stream, nullptr));
-    ++c->launches;
-  }
+  const int pdl = (c->engine_flags & 8) ? 0 : 1;
+  const bool early_ok = !(c->engine_flags & (8 | 1024));
+  const int G = (ahead && !c->profile) ? c->pose_group : 1;   // (per-kernel event timing: one pose at a time)
   std::vector<ProblemSpec> specs(W);
-  for (int k = 0; k < count; ++k) {
+  auto fill_specs = [&](int k, const uint8_t* image) {
     const long long cur = pose_frame(k);
     for (int j = 0; j < W; ++j) {
       specs[j] = ProblemSpec{base + size_t(cur - W + j) * fb, n, nullptr, base + size_t(cur) * fb, n, nullptr, j};
-      if (ahead) {
-        specs[j].t_exp = c->d_train_exp[k & 1];
+      if (image) {
+        specs[j].t_exp = image;
         specs[j].t_exp_int8 = int8;
       }
     }
+  };
+  if (ahead && G > 1) {
+    // ---- per-slot buffers
+    const size_t image_bytes = size_t(round_up(c->max_features, kTcTileRows)) * size_t(c->row_bytes) * 8;
+    const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
+    const size_t flag_words = c->qb_cap + 8;
+    for (int i = 0; i < 2 * G; ++i) {
+      if (!c->grp_partial[i]) {
+        if (i == 0) c->grp_partial[i] = c->d_partial;
+        else VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_partial[i]), c->partial_cap * sizeof(uint2)));
+      }
+      if (!c->grp_exp[i]) {
+        if (i < kTcMaxTrains) c->grp_exp[i] = c->d_train_exp[i];
+        else VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_exp[i]), image_bytes));
+      }
+    }
+    if (!c->grp_flags) {
+      const size_t bytes = (size_t(kMaxPoseGroup) * flag_words + kMaxPoseGroup) * sizeof(unsigned long long);
+      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), bytes));
+      VSF_CUDA(c, cudaMemsetAsync(c->grp_flags, 0, bytes, c->stream));
+      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
+      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
+    }
+    unsigned long long* tickets = c->grp_flags + size_t(kMaxPoseGroup) * flag_words;
+    auto group_images = [&](int k0, int parity) {   // frames of poses k0 .. k0 + G - 1
+      ExpandMulti em;
+      std::memset(&em, 0, sizeof(em));
+      em.nt = n;
+      for (int g = 0; g < G && k0 + g < count; ++g) {
+        em.src[g] = reinterpret_cast<const uint32_t*>(base + size_t(pose_frame(k0 + g)) * fb);
+        em.out[g] = c->grp_exp[parity * G + g];
+        em.frames = g + 1;
+      }
+      return em;
+    };
+    {
+      const ExpandMulti em = group_images(0, 0);
+      VSF_CUDA(c, launch_expand_train_multi(em, int8, pdl, c->stream));
+      ++c->launches;
+    }
+    int rc = VSF_OK;
+    vsf_dmatch* const own_matches = c->match_base;
+    int* const own_counts = c->count_base;
+    for (int k0 = 0, grp = 0; k0 < count; k0 += G, ++grp) {
+      const int parity = grp & 1;
+      const int m = std::min(G, count - k0);
+      // the next group's images are made by this group's first finish kernel
+      const ExpandMulti next_em = group_images(k0 + G, parity ^ 1);
+      for (int phase = 1; phase <= 2 && !rc; ++phase) {
+        for (int g = 0; g < m && !rc; ++g) {
+          const int k = k0 + g;
+          fill_specs(k, c->grp_exp[parity * G + g]);
+          PoseLaunch pl;
+          pl.phase = phase;
+          // the first distance kernel of a group waits for its predecessor (the expansion, or the
+          // previous group's last finish kernel, whose completion implies that of the first,
+          // which made this group's images); the others start at once
+          pl.early = (phase == 1 && early_ok && g > 0) ? 1 : 0;
+          pl.partial = c->grp_partial[parity * G + g];
+          pl.flags = c->grp_flags + size_t(g) * flag_words;
+          pl.ticket = tickets + g;
+          pl.nowait = (phase == 2 && g > 0 && early_ok) ? 1 : 0;
+          if (phase == 2 && g == 0 && next_em.frames > 0) pl.em = &next_em;
+          // survivor lists: slot 0 = the ctx's own (the last pose of the call ends up there)
+          const int slot = (count - 1 - k) % G;
+          c->match_base = slot == 0 ? own_matches : c->grp_matches + size_t(slot - 1) * rows_cap;
+          c->count_base = slot == 0 ? own_counts : c->grp_counts + size_t(slot - 1) * kMaxProblems;
+          rc = run_knn(c, specs, ratio, false, false, &pl);
+        }
+      }
+      c->match_base = own_matches;
+      c->count_base = own_counts;
+      if (rc) return rc;
+    }
+    c->last_n_frames = W;
+    return VSF_OK;
+  }
+  if (ahead) {
+    if (!c->d_partial2) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_partial2), c->partial_cap * sizeof(uint2)));
+    VSF_CUDA(c, launch_expand_train(base + size_t(pose_frame(0)) * fb, n, nullptr, c->d_train_exp[0], int8, pdl,
+                                    c->stream, nullptr));
+    ++c->launches;
+  }
+  for (int k = 0; k < count; ++k) {
+    fill_specs(k, ahead ? c->d_train_exp[k & 1] : nullptr);
     int rc;
     if (ahead) {
-      const NextExpand nx{k + 1 < count ? base + size_t(pose_frame(k + 1)) * fb : nullptr, n, c->d_train_exp[(k + 1) & 1],
-                          (k > 0 && !(c->engine_flags & (8 | 1024))) ? 1 : 0, k & 1};
-      rc = run_knn(c, specs, ratio, false, false, &nx);
+      PoseLaunch pl;
+      if (k + 1 < count) {
+        pl.exp_src = base + size_t(pose_frame(k + 1)) * fb;
+        pl.exp_nt = n;
+        pl.exp_out = c->d_train_exp[(k + 1) & 1];
+      }
+      pl.early = (k > 0 && early_ok) ? 1 : 0;
+      pl.partial = (k & 1) ? c->d_partial2 : c->d_partial;
+      rc = run_knn(c, specs, ratio, false, false, &pl);
     } else {
       rc = run_knn(c, specs, ratio);
     }

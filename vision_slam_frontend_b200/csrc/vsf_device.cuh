@@ -116,13 +116,32 @@ struct TcBatch {
 };
 constexpr int kTcTraceSlots = 16;
 
+// Several frames expanded to +-1 images by one launch (a group of poses).
+constexpr int kMaxPoseGroup = 8;
+struct ExpandMulti {
+  const uint32_t* src[kMaxPoseGroup];
+  uint8_t* out[kMaxPoseGroup];
+  int frames;
+  int nt;                            // rows of every frame
+};
+
 // Arguments of knn2_tc_finish_kernel (refine + ordered compaction in one kernel, see there).
 struct FinishArgs {
   unsigned long long* ticket;        // (epoch << 24 | next block): raised to this launch's epoch by its first CTAs
   unsigned long long* flags;         // [32-query blocks of the batch, KnnProblem::qb0 + block] (epoch << 8 | survivors)
   unsigned long long epoch;
   int nqb;                           // 32-query blocks per problem (grid = nqb * num_problems)
+  // nowait != 0 (the later finish kernels of a group of poses): the distance kernel this launch
+  // reads from had completed before the stream predecessor - the previous pose's finish kernel -
+  // passed its own wait, so the kernel starts at once and only waits for the predecessor just
+  // before it exits ("complete" still implies "everything before it complete").
+  int nowait;
+  // A group of poses: the first finish kernel of the group also expands the NEXT group's train
+  // frames (em.frames > 0), each CTA its share, before it waits for the distance kernels.
+  ExpandMulti em;
+  int em_int8;
 };
+
 
 
 // CTA that owns slot x = the largest i with floor(i*T/G) <= x
