@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads legs (C2, C3, C5, other width)")
-    ap.add_argument("--e2e-lag", type=int, default=6,
+    ap.add_argument("--e2e-lag", type=int, default=12,
                     help="frames submitted ahead of the one being collected in the pipelined e2e leg "
                          "(1 .. VSF_PIPELINE_DEPTH - 1)")
     ap.add_argument("--popc-mode", type=int, default=-1)

@@ -223,7 +223,7 @@ int vsf_window_feature_matches(vsf_ctx* ctx, const uint8_t* desc, int n,
  * meaning; *frame_id = the id given at submit; sort_mode / best_percent are the
  * ones given at submit).  VSF_ERR_STATE: submit with VSF_PIPELINE_DEPTH frames
  * in flight, or collect with none. */
-#define VSF_PIPELINE_DEPTH 8
+#define VSF_PIPELINE_DEPTH 16
 #define VSF_SUBMIT_PINNED_DESC 1
 /* together with VSF_SUBMIT_PINNED_DESC for descriptors narrower than the device row (61 -> 64):
  * the rows are already padded to vsf_device_row_bytes(ctx) with zero bytes */
@@ -418,7 +418,9 @@ int vsf_window_match_block_device(vsf_ctx* ctx, const void* d_seq, int n, int n_
  * lengths to counts + (k mod ring) * window, so a ring of >= 1 frames of output is enough when
  * the caller only wants the lists to have reached host memory.  The window must hold the frames
  * the caller wants frame `first` matched against (vsf_window_push).  Returns after every frame
- * has been collected; *h2d_bytes / *d2h_bytes (optional) accumulate vsf_window_last_transfer. */
+ * has been collected; *h2d_bytes / *d2h_bytes (optional) accumulate vsf_window_last_transfer.
+ * Knowing the frames ahead, the call uploads min(VSF_OPT_POSE_GROUP, lag) of them before it
+ * launches their kernels together (like vsf_window_match_block_device); the lists are the same. */
 int vsf_window_run_sequence(vsf_ctx* ctx, const uint8_t* h_seq, int n, int n_poses,
                             long long first, int count, double nn_match_ratio,
                             float best_percent, int sort_mode, int lag,

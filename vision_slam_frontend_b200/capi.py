@@ -21,7 +21,7 @@ OPT_RESIDUAL_ORDER = 1            # VSF_OPT_RESIDUAL_ORDER
 OPT_HOLD_THRESHOLD_ON_EMPTY = 2
 OPT_POSE_GROUP = 3   # VSF_OPT_HOLD_THRESHOLD_ON_EMPTY
 OPT_DEBUG_SORT_DEPTH = 100        # VSF_OPT_DEBUG_SORT_DEPTH
-PIPELINE_DEPTH = 8   # VSF_PIPELINE_DEPTH (include/vsf.h): frames vsf_window_submit keeps in flight
+PIPELINE_DEPTH = 16   # VSF_PIPELINE_DEPTH (include/vsf.h): frames vsf_window_submit keeps in flight
 
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"),
                          ("imgIdx", "<i4"), ("distance", "<f4")])

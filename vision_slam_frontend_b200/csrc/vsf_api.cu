@@ -217,6 +217,13 @@ struct vsf_ctx {
     int keep[kMaxProblems];
     std::atomic<int> pending{0};
     int cuda_error = 0;
+    // staged by vsf_window_submit, launched by flush_flights (a group of frames at a time)
+    bool launched = false;
+    std::vector<ProblemSpec> specs;
+    double ratio = 0.0;
+    int n = 0, slot = 0, max_cnt = 0;
+    uint2* d_partial = nullptr;         // partial bucket keys of this frame's distance kernel (tensor engine)
+    cudaEvent_t chain = nullptr;        // the ev_chain recorded behind this frame's kernels (its group's last frame's)
   };
   struct SortTask {
     Flight* f;
@@ -242,6 +249,8 @@ struct vsf_ctx {
   size_t last_h2d = 0, last_d2h = 0;   // PCIe bytes of the most recent window call (vsf_window_last_transfer)
   bool flights_ready = false;
   int flight_head = 0, flight_count = 0;   // FIFO: oldest = flights[flight_head]
+  int flights_staged = 0;   // the newest flights_staged flights are uploaded but their kernels not launched yet
+  int defer_group = 1;      // vsf_window_run_sequence: launch the kernels of this many frames together
 
   // pipelined full-frame path (vsf_observe_submit / vsf_observe_collect): per frame in flight one
   // upload block and one block of mapped host memory the kernels store their results into
@@ -673,6 +682,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
       if (p) cudaFreeHost(p);
     if (f.d_matches) cudaFree(f.d_matches);
     if (f.d_train_exp) cudaFree(f.d_train_exp);
+    if (f.d_partial) cudaFree(f.d_partial);
     if (f.d_fm) cudaFree(f.d_fm);
     if (f.d_counts) cudaFree(f.d_counts);
     for (cudaEvent_t e : {f.ev_up, f.ev_chain, f.done, f.ev_sort})
@@ -756,7 +766,9 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
 
   const size_t N = size_t(c->rows_pad);
   const size_t rows_cap = size_t(c->regions) * N;
-  c->ring_slots = window + 2;
+  // (+ kMaxPoseGroup - 1: vsf_window_run_sequence uploads a group of frames before it launches
+  // their kernels; a slot must not be reused while a staged frame still has to read it)
+  c->ring_slots = window + 2 + (kMaxPoseGroup - 1);
   VSF_ALLOC(c, c->d_ring, size_t(c->ring_slots) * N * c->row_bytes);
   VSF_ALLOC(c, c->d_raw_left, N * c->row_bytes);
   VSF_ALLOC(c, c->d_raw_right, N * c->row_bytes);
@@ -793,8 +805,8 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   cudaMemset(c->d_ticket, 0, sizeof(unsigned));
   VSF_ALLOC(c, c->d_kept_left, N * sizeof(int));
   VSF_ALLOC(c, c->d_kept_right, N * sizeof(int));
-  VSF_ALLOC(c, c->d_slot_rows, (window + 2) * sizeof(int));
-  cudaMemset(c->d_slot_rows, 0, (window + 2) * sizeof(int));
+  VSF_ALLOC(c, c->d_slot_rows, c->ring_slots * sizeof(int));
+  cudaMemset(c->d_slot_rows, 0, c->ring_slots * sizeof(int));
   VSF_ALLOC(c, c->d_thresh, 2 * sizeof(float));
   VSF_ALLOC(c, c->d_X4, N * sizeof(float4));
   VSF_ALLOC(c, c->d_tri_io, N * 8 * sizeof(float));
@@ -1336,6 +1348,191 @@ static int flights_init(vsf_ctx* c) {
 
 extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_count : 0; }
 
+// Launch the kernels of the staged frames (vsf_window_submit stages one frame; ordinarily it is
+// flushed at once, vsf_window_run_sequence lets c->defer_group frames accumulate).  On the tensor
+// engine with 32-byte rows a group is launched like a group of poses of
+// vsf_window_match_block_device: the distance kernels back to back (each but the first starts
+// without waiting for its predecessor: their inputs were all uploaded and expanded before the
+// group started, their partial keys go to per-frame buffers), then the finish kernels side by
+// side, then the device sorts, one event for the whole group.
+static int flush_flights(vsf_ctx* c) {
+  const int m = c->flights_staged;
+  if (m == 0) return VSF_OK;
+  cudaSetDevice(c->device);
+  vsf_ctx::Flight* fl[VSF_PIPELINE_DEPTH];
+  for (int g = 0; g < m; ++g)
+    fl[g] = &c->flights[(c->flight_head + c->flight_count - m + g) % VSF_PIPELINE_DEPTH];
+  c->flights_staged = 0;
+  // the uploads (and expansions) of the whole group precede the last frame's event on the upload stream
+  VSF_CUDA(c, cudaStreamWaitEvent(c->stream, fl[m - 1]->ev_up, 0));
+  int rc = VSF_OK;
+  // grouped launch: every frame has work for the tensor engine's 32-byte kernels
+  bool grouped = m > 1 && c->words == 8 && c->engine != 1 && !(c->engine_flags & (8 | 512 | 1024)) && !c->profile;
+  bool any_side_sort = false;
+  for (int g = 0; g < m; ++g) {
+    const vsf_ctx::Flight& f = *fl[g];
+    if (f.nf == 0 || f.n == 0 || f.max_cnt == 0) grouped = false;
+    else if (c->engine == 0 && double(f.nf) * double(f.max_cnt) * double(f.n) < c->tc_auto_min_cmp) grouped = false;   // (an upper bound of the batch's comparisons: frames with device-side row counts)
+    if (f.sort_mode != 1 && f.nf > 0 && !(c->engine_flags & 64)) any_side_sort = true;
+  }
+  if (grouped && c->engine == 0) {
+    // the automatic choice must come out as the tensor engine for every frame (run_knn decides on
+    // sum(nq) * nt); otherwise launch frame by frame
+    for (int g = 0; g < m && grouped; ++g) {
+      long long tq = 0;
+      for (const ProblemSpec& sp : fl[g]->specs) tq += sp.nq;
+      if (double(tq) * double(fl[g]->n) < c->tc_auto_min_cmp) grouped = false;
+    }
+  }
+  unsigned long long* tickets = nullptr;
+  size_t flag_words = 0;
+  if (grouped) {
+    flag_words = c->qb_cap + 8;
+    if (!c->grp_flags) {
+      const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
+      const size_t bytes = (size_t(kMaxPoseGroup) * flag_words + kMaxPoseGroup) * sizeof(unsigned long long);
+      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), bytes));
+      VSF_CUDA(c, cudaMemsetAsync(c->grp_flags, 0, bytes, c->stream));
+      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
+      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
+    }
+    tickets = c->grp_flags + size_t(kMaxPoseGroup) * flag_words;
+    for (int g = 0; g < m; ++g)
+      if (!fl[g]->d_partial)
+        VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&fl[g]->d_partial), c->partial_cap * sizeof(uint2)));
+  }
+  // ---- main stream: every resident past frame (query side) against the frame (train side); the
+  // survivors go to the flight's own device buffer, the counts straight to mapped host memory.
+  // A device sort (modes 0, 2) runs on its own stream while the main stream goes on with the next
+  // frames; their persistent distance kernels then leave a few SMs to it (one sort CTA per
+  // list), which costs the distance kernel a few per cent and takes the sort off the frame
+  // stream's critical path.  Measured on C4 (10 lists, 148 SMs): the 10 us stable sort is best
+  // served by 8 SMs (57.2 us/pose; 58.7 with 10), the 55 us exact sort - whose CTAs of two
+  // consecutive frames overlap - by 14-16 (62.7; 64.4 with 10, 68.0 with 8)
+  auto frame_state = [&](vsf_ctx::Flight& f) {
+    const bool side_sort = f.sort_mode != 1 && f.nf > 0 && !(c->engine_flags & 64);
+    c->reserve_sms = !side_sort ? 0
+                     : f.sort_mode == 2 ? std::min(f.nf + f.nf / 2, std::max(1, c->sm_count / 9))
+                                        : std::min(f.nf, std::max(1, c->sm_count / 18));
+    if (side_sort && c->reserve_override >= 0) c->reserve_sms = std::min(c->reserve_override, c->sm_count - 1);
+    c->match_base = f.d_matches;
+    c->count_base = f.d_counts;
+    c->mir_dm = nullptr;
+    c->mir_dcounts = f.dm_counts;
+    c->mir_hcounts = f.h_counts;
+  };
+  auto restore_state = [&]() {
+    c->reserve_sms = 0;
+    c->match_base = c->d_matches;
+    c->count_base = c->d_match_count;
+    c->mir_dm = c->dm_matches;
+    c->mir_dcounts = c->dm_region_counts;
+    c->mir_hcounts = c->h_region_counts;
+  };
+  for (int phase = grouped ? 1 : 0; phase <= (grouped ? 2 : 0) && !rc; ++phase) {
+    for (int g = 0; g < m && !rc; ++g) {
+      vsf_ctx::Flight& f = *fl[g];
+      frame_state(f);
+      if (grouped) {
+        PoseLaunch pl;
+        pl.phase = phase;
+        pl.early = (phase == 1 && g > 0) ? 1 : 0;
+        pl.partial = f.d_partial;
+        pl.flags = c->grp_flags + size_t(g) * flag_words;
+        pl.ticket = tickets + g;
+        pl.nowait = (phase == 2 && g > 0) ? 1 : 0;
+        rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1, false, &pl);
+      } else {
+        rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1);
+      }
+    }
+  }
+  // ---- device sort (stable, or the replay of the reference's std::sort) + cut; the kept counts
+  // go to the flights' mapped counters
+  if (!rc && any_side_sort) {
+    cudaError_t e = cudaEventRecord(c->ev_main, c->stream);
+    if (e != cudaSuccess) {
+      c->err = std::string("cudaEventRecord: ") + cudaGetErrorString(e);
+      rc = VSF_ERR_CUDA;
+    }
+  }
+  for (int g = 0; g < m && !rc; ++g) {
+    vsf_ctx::Flight& f = *fl[g];
+    if (f.sort_mode == 1 || f.nf == 0) continue;
+    frame_state(f);
+    const bool side_sort = !(c->engine_flags & 64);
+    const unsigned half = c->sort_streams > 1 ? ((c->sort_rr++) & 1u) : 0u;
+    cudaStream_t side = c->sort_stream[half];
+    const vsf_dmatch* mp[kMaxProblems];
+    const int* cp[kMaxProblems];
+    for (int j = 0; j < f.nf; ++j) {
+      mp[j] = c->region_ptr(j);
+      cp[j] = c->count_base + j;
+    }
+    void* gs = nullptr;
+    if ((rc = sort_scratch(c, f.sort_mode == 2, &gs, half)) == VSF_OK) {
+      cudaError_t e = cudaSuccess;
+      if (side_sort) e = cudaStreamWaitEvent(side, c->ev_main, 0);
+      if (e == cudaSuccess)
+        e = launch_sort_cut(mp, cp, f.nf, f.best_percent, f.d_fm, c->rows_pad, f.dm_counts, 8 * c->row_bytes + 1,
+                            gs ? c->rows_pad : f.max_cnt, f.sort_mode == 2, c->sort_depth_override, gs,
+                            side_sort ? side : c->stream);
+      if (e == cudaSuccess && side_sort) e = cudaEventRecord(f.ev_sort, side);
+      if (e != cudaSuccess) {
+        c->err = std::string("launch_sort_cut: ") + cudaGetErrorString(e);
+        rc = VSF_ERR_CUDA;
+      }
+    }
+  }
+  restore_state();
+  if (rc) return rc;
+  c->main_dirty = false;
+  // one event behind the kernels of the whole group
+  cudaEvent_t chain = fl[m - 1]->ev_chain;
+  VSF_CUDA(c, cudaEventRecord(chain, c->stream));
+  for (int g = 0; g < m; ++g) {
+    vsf_ctx::Flight& f = *fl[g];
+    f.chain = chain;
+    f.launched = true;
+    for (const ProblemSpec& sp : f.specs) {
+      const int slot = int((static_cast<const uint8_t*>(sp.q) - c->d_ring) / (size_t(c->rows_pad) * c->row_bytes));
+      c->slot_last_chain[slot] = chain;
+    }
+    c->slot_last_chain[f.slot] = chain;
+  }
+  // ---- download stream: the lists leave through the copy engine while the main stream goes on
+  // with the next frames.  Their lengths are only known on the device, so each list is copied up
+  // to its bound (a past frame's row count, cut by best_percent for the sorted lists).
+  for (int g = 0; g < m; ++g) {
+    vsf_ctx::Flight& f = *fl[g];
+    const bool side_sort = f.sort_mode != 1 && f.nf > 0 && !(c->engine_flags & 64);
+    VSF_CUDA(c, cudaStreamWaitEvent(c->down_stream, side_sort ? f.ev_sort : chain, 0));
+    f.d2h_bytes = size_t(f.nf) * sizeof(int);
+    if (f.nf > 0 && f.max_cnt > 0) {
+      const size_t pitch = size_t(c->rows_pad) * 16;
+      const int rows = f.sort_mode == 1 ? f.max_cnt
+                                        : std::min(f.max_cnt, int(float(size_t(f.max_cnt)) * f.best_percent) + 1);   // modes 0, 2: the kept part
+      if (rows > 0) {
+        VSF_CUDA(c, cudaMemcpy2DAsync(f.sort_mode == 1 ? static_cast<void*>(f.h_matches) : static_cast<void*>(f.h_fm), pitch,
+                                      f.sort_mode == 1 ? static_cast<const void*>(f.d_matches) : static_cast<const void*>(f.d_fm), pitch,
+                                      size_t(rows) * 16, size_t(f.nf), cudaMemcpyDeviceToHost, c->down_stream));
+        f.d2h_bytes += size_t(rows) * 16 * size_t(f.nf);
+      }
+    }
+    VSF_CUDA(c, cudaEventRecord(f.done, c->down_stream));
+    f.cuda_error = 0;
+    if (f.sort_mode == 1) {
+      f.pending.store(1, std::memory_order_release);   // the device-wait token
+      {
+        std::lock_guard<std::mutex> lk(c->disp_mu);
+        c->disp_q.push_back(&f);
+      }
+      c->disp_cv.notify_one();
+    }
+  }
+  return VSF_OK;
+}
+
 extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* desc, int n, size_t stride,
                                  double ratio, float best_percent, int sort_mode, int flags) {
   if (!c) return VSF_ERR_BAD_ARG;
@@ -1358,15 +1555,20 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
   f.best_percent = best_percent;
   f.frame_id = frame_id;
   f.h2d_bytes = size_t(n) * c->row_bytes;
+  f.launched = false;
+  f.ratio = ratio;
+  f.n = n;
   int max_cnt = 0;
   for (int j = 0; j < nf; ++j) {
     f.fids[j] = c->slot_frame[c->live[j]];
     max_cnt = std::max(max_cnt, c->slot_count[c->live[j]]);
   }
+  f.max_cnt = max_cnt;
   // ---- upload stream: the frame's rows go into the free ring slot while the main stream is
-  // still matching the previous frame.  The slot was last read by the frame before that one.
+  // still matching the previous frames.  The slot was last read several frames ago.
   const int S = c->staging_slot;
-  if (c->main_dirty) {   // kernels launched outside the pipeline may still be reading the ring
+  f.slot = S;
+  if (c->main_dirty && c->flights_staged == 0) {   // kernels launched outside the pipeline may still be reading the ring
     VSF_CUDA(c, cudaEventRecord(c->ev_main, c->stream));
     VSF_CUDA(c, cudaStreamWaitEvent(c->up_stream, c->ev_main, 0));
   }
@@ -1398,103 +1600,20 @@ extern "C" int vsf_window_submit(vsf_ctx* c, uint64_t frame_id, const uint8_t* d
       VSF_CUDA(c, launch_expand_train(c->slot_ptr(S), n, nullptr, f.d_train_exp, exp_int8, 0, c->up_stream, nullptr));
   }
   VSF_CUDA(c, cudaEventRecord(f.ev_up, c->up_stream));
-  VSF_CUDA(c, cudaStreamWaitEvent(c->stream, f.ev_up, 0));
-  // ---- main stream: every resident past frame (query side) against this frame (train side);
-  // the survivors go to the flight's own device buffer, the counts straight to mapped host memory
-  std::vector<ProblemSpec> specs;
+  f.specs.clear();
   for (int j = 0; j < nf; ++j) {
     const int s = c->live[j];
-    specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], c->slot_dev[s] ? c->d_slot_rows + s : nullptr,
-                                c->slot_ptr(S), n, nullptr, j});
+    f.specs.push_back(ProblemSpec{c->slot_ptr(s), c->slot_count[s], c->slot_dev[s] ? c->d_slot_rows + s : nullptr,
+                                  c->slot_ptr(S), n, nullptr, j});
     if (pre_expand) {
-      specs.back().t_exp = f.d_train_exp;
-      specs.back().t_exp_int8 = exp_int8;
+      f.specs.back().t_exp = f.d_train_exp;
+      f.specs.back().t_exp_int8 = exp_int8;
     }
   }
-  // A device sort (modes 0, 2) runs on its own stream while the main stream goes on with the next
-  // frame; that frame's persistent distance kernel then leaves a few SMs to it (one sort CTA per
-  // list), which costs the distance kernel a few per cent and takes the sort off the frame
-  // stream's critical path.  Measured on C4 (10 lists, 148 SMs): the 10 us stable sort is best
-  // served by 8 SMs (57.2 us/pose; 58.7 with 10), the 55 us exact sort - whose CTAs of two
-  // consecutive frames overlap - by 14-16 (62.7; 64.4 with 10, 68.0 with 8)
-  const bool side_sort = sort_mode != 1 && nf > 0 && !(c->engine_flags & 64);
-  c->reserve_sms = !side_sort ? 0
-                   : sort_mode == 2 ? std::min(nf + nf / 2, std::max(1, c->sm_count / 9))
-                                    : std::min(nf, std::max(1, c->sm_count / 18));
-  if (side_sort && c->reserve_override >= 0) c->reserve_sms = std::min(c->reserve_override, c->sm_count - 1);
-  c->match_base = f.d_matches;
-  c->count_base = f.d_counts;
-  c->mir_dm = nullptr;
-  c->mir_dcounts = f.dm_counts;
-  c->mir_hcounts = f.h_counts;
-  rc = run_knn(c, specs, ratio, sort_mode == 1);
-  c->reserve_sms = 0;
-  const unsigned half = c->sort_streams > 1 ? ((c->sort_rr++) & 1u) : 0u;
-  cudaStream_t side = c->sort_stream[half];
-  cudaStream_t sort_on = side_sort ? side : c->stream;
-  if (rc == VSF_OK && sort_mode != 1 && nf > 0) {
-    // device sort (stable, or the replay of the reference's std::sort) + cut; the kept counts go
-    // to the flight's mapped counters
-    const vsf_dmatch* mp[kMaxProblems];
-    const int* cp[kMaxProblems];
-    for (int j = 0; j < nf; ++j) {
-      mp[j] = c->region_ptr(j);
-      cp[j] = c->count_base + j;
-    }
-    void* gs = nullptr;
-    if ((rc = sort_scratch(c, sort_mode == 2, &gs, half)) == VSF_OK) {
-      cudaError_t e = cudaSuccess;
-      if (side_sort) {
-        e = cudaEventRecord(c->ev_main, c->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, c->ev_main, 0);
-      }
-      if (e == cudaSuccess)
-        e = launch_sort_cut(mp, cp, nf, best_percent, f.d_fm, c->rows_pad, f.dm_counts, 8 * c->row_bytes + 1,
-                            gs ? c->rows_pad : max_cnt, sort_mode == 2, c->sort_depth_override, gs, sort_on);
-      if (e == cudaSuccess && side_sort) e = cudaEventRecord(f.ev_sort, side);
-      if (e != cudaSuccess) {
-        c->err = std::string("launch_sort_cut: ") + cudaGetErrorString(e);
-        rc = VSF_ERR_CUDA;
-      }
-    }
-  }
-  c->match_base = c->d_matches;
-  c->count_base = c->d_match_count;
-  c->mir_dm = c->dm_matches;
-  c->mir_dcounts = c->dm_region_counts;
-  c->mir_hcounts = c->h_region_counts;
-  if (rc) return rc;
-  c->main_dirty = false;
-  VSF_CUDA(c, cudaEventRecord(f.ev_chain, c->stream));
-  for (int j = 0; j < nf; ++j) c->slot_last_chain[c->live[j]] = f.ev_chain;
-  c->slot_last_chain[S] = f.ev_chain;
-  // ---- download stream: the lists leave through the copy engine while the main stream goes on
-  // with the next frame.  Their lengths are only known on the device, so each list is copied up
-  // to its bound (a past frame's row count, cut by best_percent for the sorted lists).
-  VSF_CUDA(c, cudaStreamWaitEvent(c->down_stream, (side_sort && nf > 0) ? f.ev_sort : f.ev_chain, 0));
-  f.d2h_bytes = size_t(nf) * sizeof(int);
-  if (nf > 0 && max_cnt > 0) {
-    const size_t pitch = size_t(c->rows_pad) * 16;
-    const int rows = sort_mode == 1 ? max_cnt : std::min(max_cnt, int(float(size_t(max_cnt)) * best_percent) + 1);   // modes 0, 2: the kept part
-    if (rows > 0) {
-      VSF_CUDA(c, cudaMemcpy2DAsync(sort_mode == 1 ? static_cast<void*>(f.h_matches) : static_cast<void*>(f.h_fm), pitch,
-                                    sort_mode == 1 ? static_cast<const void*>(f.d_matches) : static_cast<const void*>(f.d_fm), pitch,
-                                    size_t(rows) * 16, size_t(nf), cudaMemcpyDeviceToHost, c->down_stream));
-      f.d2h_bytes += size_t(rows) * 16 * size_t(nf);
-    }
-  }
-  VSF_CUDA(c, cudaEventRecord(f.done, c->down_stream));
   commit_staging(c, frame_id, n);   // eviction + push (src/slam_frontend.cc:467-470)
   ++c->flight_count;
-  f.cuda_error = 0;
-  if (sort_mode == 1) {
-    f.pending.store(1, std::memory_order_release);   // the device-wait token
-    {
-      std::lock_guard<std::mutex> lk(c->disp_mu);
-      c->disp_q.push_back(&f);
-    }
-    c->disp_cv.notify_one();
-  }
+  ++c->flights_staged;
+  if (c->flights_staged >= std::max(1, std::min(c->defer_group, kMaxPoseGroup))) return flush_flights(c);
   return VSF_OK;
 }
 
@@ -1505,6 +1624,10 @@ extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* fram
   if (c->flight_count == 0) return fail(c, VSF_ERR_STATE, "no submitted frame to collect");
   cudaSetDevice(c->device);
   vsf_ctx::Flight& f = c->flights[c->flight_head];
+  if (!f.launched) {   // (only inside vsf_window_run_sequence: a group still filling up)
+    const int rc = flush_flights(c);
+    if (rc) return rc;
+  }
   cudaError_t werr = cudaSuccess;
   if (f.sort_mode == 1) {
     std::unique_lock<std::mutex> lk(c->done_mu);
@@ -2115,6 +2238,12 @@ extern "C" int vsf_window_run_sequence(vsf_ctx* c, const uint8_t* h_seq, int n, 
   const int W = c->window;
   const size_t fb = size_t(n) * c->row_bytes;
   const int flags = VSF_SUBMIT_PINNED_DESC | VSF_SUBMIT_PADDED_ROWS;   // the buffer is in the device layout
+  // the kernels of up to pose_group frames are launched together (flush_flights)
+  struct DeferGuard {
+    vsf_ctx* c;
+    ~DeferGuard() { c->defer_group = 1; }
+  } guard{c};
+  c->defer_group = std::max(1, std::min(c->pose_group, lag));
   uint64_t fid = 0, fids[kMaxProblems];
   int nf = 0;
   long long collected = 0;
