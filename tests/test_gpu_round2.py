@@ -319,9 +319,10 @@ def test_window_match_block_device(width):
     assert sum(len(m) for m in got) > 1000
 
 
-@pytest.mark.parametrize("n,W,count", [(1400, 4, 1), (1400, 4, 2), (1400, 4, 3), (1400, 4, 6), (1237, 3, 5),
-                                        (2900, 2, 4), (700, 10, 9), (130, 38, 3), (3000, 1, 3)])
-def test_block_device_launch_variants(n, W, count):
+@pytest.mark.parametrize("n,W,count,width", [(1400, 4, 1, 32), (1400, 4, 2, 32), (1400, 4, 3, 32), (1400, 4, 6, 32),
+                                              (1237, 3, 5, 32), (2900, 2, 4, 32), (700, 10, 9, 32), (130, 38, 3, 32),
+                                              (3000, 1, 3, 32), (1400, 4, 6, 61), (1237, 3, 9, 64), (700, 10, 5, 61)])
+def test_block_device_launch_variants(n, W, count, width):
     """A pose of a device-resident block is two kernels (distance + finish), launched in groups
     (all distance kernels of a group, then all its finish kernels, the first of which expands
     the next group's frames); group 1: the distance kernel expands the next pose's frame.  Engine flag
@@ -330,8 +331,8 @@ def test_block_device_launch_variants(n, W, count):
     import torch
     from vision_slam_frontend_b200 import capi
     poses, stride, seed = W + 9, 97, 5
-    with new_ctx(max_features=3072, window=W) as ctx:
-        buf = torch.empty((poses, n, 32), dtype=torch.uint8, device="cuda")
+    with new_ctx(desc_bytes=width, max_features=3072, window=W) as ctx:
+        buf = torch.empty((poses, n, ctx.row_bytes), dtype=torch.uint8, device="cuda")
         ctx.synth_sequence_device(buf.data_ptr(), n, 0, poses, stride, seed)
         got = {}
         for group, flags, per_pose in ((4, 0, 2), (1, 0, 2), (3, 0, 2), (8, 0, 2), (2, 1024, 2), (1, 1024, 2), (4, 256, 3),
@@ -341,33 +342,43 @@ def test_block_device_launch_variants(n, W, count):
             before = ctx.launch_count()
             ctx.window_match_block_device(buf.data_ptr(), n, poses, 2, count, RATIO)
             got[len(got)] = ctx.fetch_window(W)
-            # + the expansion of the first pose's / group's frames (flags 256 / 512: one per pose, in per_pose)
-            extra = 0 if flags & (256 | 512) else 1
-            assert ctx.launch_count() - before == per_pose * count + extra
+            if width <= 32:
+                # + the expansion of the first pose's / group's frames (flags 256 / 512: one per pose, in per_pose)
+                extra = 0 if flags & (256 | 512) else 1
+                assert ctx.launch_count() - before == per_pose * count + extra
     cur = ((2 + count - 1) % (poses - W)) + W
     for j in range(W):
-        exp = native.get_matches(synth.synth_pose(n, cur - W + j, stride, seed), synth.synth_pose(n, cur, stride, seed), RATIO)
+        exp = native.get_matches(synth.synth_pose(n, cur - W + j, stride, seed, width),
+                                 synth.synth_pose(n, cur, stride, seed, width), RATIO)
         for k in got:
             np.testing.assert_array_equal(got[k][j], exp)
 
 
-@pytest.mark.parametrize("sort_mode", [0, 1, 2])
-def test_window_run_sequence_equals_per_frame_calls(sort_mode):
+@pytest.mark.parametrize("sort_mode,width", [(0, 32), (1, 32), (2, 32), (1, 61), (2, 61)])
+def test_window_run_sequence_equals_per_frame_calls(sort_mode, width):
+    """vsf_window_run_sequence (groups of frames uploaded, then launched together) returns per
+    frame what the oracle's GetMatches + sort + cut gives for the window of that moment."""
     import torch
     from vision_slam_frontend_b200 import capi
     n, W, n_pool, count = 1100, 3, 9, 14
-    pool = torch.from_numpy(np.stack([synth.synth_pose(n, p, 110, 3) for p in range(n_pool)])).pin_memory()
+    rb = 32 if width <= 32 else 64
+    frames = [synth.synth_pose(n, p, 110, 3, width) for p in range(n_pool)]
+    padded = np.zeros((n_pool, n, rb), np.uint8)
+    for p in range(n_pool):
+        padded[p, :, :width] = frames[p]
+    pool = torch.from_numpy(padded).pin_memory()
     hp = pool.numpy()
-    with new_ctx(max_features=2048, window=W) as ctx:
+    with new_ctx(desc_bytes=width, max_features=2048, window=W) as ctx:
+        ctx.set_engine(2, 0)
         for p in range(W):
-            ctx.window_push(1000 + p, hp[p])
+            ctx.window_push(1000 + p, frames[p])
         out = np.zeros((count, W, n), capi.FEATURE_MATCH_DTYPE)
         counts = np.zeros((count, W), np.int32)
         h2d, d2h = ctx.window_run_sequence(hp, W, count, RATIO, float(BP), sort_mode, 5, out, counts)
-        assert h2d == count * n * 32 and d2h > 0 and ctx.window_in_flight() == 0
-    live = [hp[p] for p in range(W)]
+        assert h2d == count * n * rb and d2h > 0 and ctx.window_in_flight() == 0
+    live = [frames[p] for p in range(W)]
     for k in range(count):
-        D = hp[(W + k) % n_pool]
+        D = frames[(W + k) % n_pool]
         for j, past in enumerate(live):
             m = native.get_matches(past, D, RATIO)
             keep = restate.num_good_matches(len(m), BP)

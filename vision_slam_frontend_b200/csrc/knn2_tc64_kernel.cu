@@ -19,6 +19,8 @@
 namespace vsf {
 
 cudaError_t launch_knn2_compact(const KnnBatch& batch, int max_nq, bool pdl, cudaStream_t stream);
+cudaError_t launch_knn2_tc64_finish(const KnnBatch& batch, const TcBatch& tc, int max_nq, bool pdl,
+                                    cudaStream_t stream, FinishArgs* fa);
 
 namespace w64 {
 
@@ -51,11 +53,31 @@ __device__ __forceinline__ uint4 expand16(uint32_t b16) {
 }
 
 // Train expansion: one thread = one (row, group of 4 K-chunks); tile image [32 chunks][128 rows][16 B].
+__device__ __forceinline__ void expand_rows64(const uint32_t* __restrict__ t, int nt, uint8_t* __restrict__ out, int idx) {
+  const int rows_pad = (nt + kT - 1) / kT * kT;
+  const int row = idx % rows_pad;
+  const int cg = idx / rows_pad;     // 0..7: K-chunks 4*cg .. 4*cg+3 (words 2*cg, 2*cg+1)
+  if (cg >= 8) return;
+  uint2 w = make_uint2(0u, 0u);
+  const bool live = row < nt;
+  if (live) w = __ldg(reinterpret_cast<const uint2*>(t + size_t(row) * 16) + cg);
+  const int tile = row / kT, r = row % kT;
+  uint8_t* base = out + size_t(tile) * kBBytes + size_t(r) * 16;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t word = (c < 2) ? w.x : w.y;
+    const uint32_t b16 = (word >> (16 * (c & 1))) & 0xFFFFu;
+    const uint4 v = live ? expand16(b16) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(base + size_t(4 * cg + c) * (kT * 16)) = v;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 expand_train64_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __restrict__ nt_dev,
                       uint8_t* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
+  // (rows_pad comes from the bound: rows between the device-side count and the bound are zeroed)
   const int rows_pad = (nt_bound + kT - 1) / kT * kT;
   int nt = nt_bound;
   if (nt_dev) nt = min(nt, *nt_dev);
@@ -136,6 +158,16 @@ __device__ __forceinline__ void epi_barrier() {   // the 16 epilogue warps only
   asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 }
 
+// Start of a role's dependent work: wait for the stream predecessor, then let the successor
+// launch - unless the launch is an early one (TcBatch::early: a stream of poses, everything the
+// kernel reads was complete before its predecessor let it launch; it waits just before it exits).
+__device__ __forceinline__ void role_wait(const TcBatch& tc) {
+  if (!tc.early) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc) {
   extern __shared__ uint8_t smem_raw[];
@@ -153,6 +185,7 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  if (tc.early) pdl_launch_dependents();
 
   if (tid == 0) {
 #pragma unroll
@@ -182,8 +215,7 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
     // ------------------------------ TMA producer ------------------------------
     Unit U;
     if (lane == 0 && walk_more(wk)) U = walk_unit(batch, tc, wk);
-    pdl_wait();
-    pdl_launch_dependents();
+    role_wait(tc);
     if (lane == 0) {
       uint32_t it = 0;
       while (walk_more(wk)) {
@@ -203,8 +235,7 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
     __syncwarp();
   } else if (warp == kEpiWarps + 1) {
     // ------------------------------ MMA issuer ------------------------------
-    pdl_wait();
-    pdl_launch_dependents();
+    role_wait(tc);
     if (lane == 0) {
       uint32_t it = 0, unit_it = 0, acc_use[2] = {0u, 0u};
       const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
@@ -278,8 +309,7 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
         expanded = true;
       }
     }
-    pdl_wait();
-    pdl_launch_dependents();
+    role_wait(tc);
     while (walk_more(wk)) {
       walk_next(wk, U);
       const bool more = walk_more(wk);
@@ -356,6 +386,7 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
     tc::fence_after_sync();
     tc::tmem_dealloc<kTmemCols>(tmem_base);
   }
+  if (tc.early) pdl_wait();   // "complete" must still imply "the stream predecessor is complete"
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -431,6 +462,7 @@ knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  if (tc.early) pdl_launch_dependents();
   const uint32_t rank = tc::cluster_ctarank();
 
   if (tid == 0) {
@@ -462,8 +494,7 @@ knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     // ------------------------------ TMA producer (each CTA: its half of B) ------------------------------
     Unit U;
     if (lane == 0 && walk_more(wk)) U = walk_unit_pair(batch, tc, wk);
-    pdl_wait();
-    pdl_launch_dependents();
+    role_wait(tc);
     if (lane == 0) {
       uint32_t it = 0;
       while (walk_more(wk)) {
@@ -482,8 +513,7 @@ knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     }
     __syncwarp();
   } else if (warp == kEpiWarps + 1) {
-    pdl_wait();
-    pdl_launch_dependents();
+    role_wait(tc);
     if (lane == 0 && rank == 0) {
       // ------------------------------ MMA issuer (rank 0, for the pair) ------------------------------
       uint32_t it = 0, unit_it = 0, acc_use[2] = {0u, 0u};
@@ -572,8 +602,7 @@ knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
         expanded = true;
       }
     }
-    pdl_wait();
-    pdl_launch_dependents();
+    role_wait(tc);
     while (walk_more(wk)) {
       walk_next(wk, U);
       const bool more = walk_more(wk);
@@ -653,6 +682,7 @@ knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     tc::fence_after_sync();
     tc::tmem_dealloc_2cta<kTmemCols>(tmem_base);
   }
+  if (tc.early) pdl_wait();   // "complete" must still imply "the stream predecessor is complete"
 }
 
 }  // namespace pair
@@ -824,25 +854,57 @@ cudaError_t launch_expand_train64(const void* t, int nt_bound, const int* nt_dev
                          static_cast<const uint32_t*>(t), nt_bound, nt_dev, static_cast<uint8_t*>(out));
 }
 
-// ev: as launch_knn2_tc
+// The same for the frames of a group of poses, blockIdx.y = frame (ExpandMulti).
+namespace w64 {
+__global__ void __launch_bounds__(128)
+expand_train64_multi_kernel(const __grid_constant__ ExpandMulti em) {
+  pdl_wait();
+  pdl_launch_dependents();
+  expand_rows64(em.src[blockIdx.y], em.nt, em.out[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x);
+}
+}  // namespace w64
+
+cudaError_t launch_expand_train64_multi(const ExpandMulti& em, int pdl, cudaStream_t stream) {
+  if (em.frames <= 0 || em.nt <= 0) return cudaSuccess;
+  const int rows_pad = (em.nt + w64::kT - 1) / w64::kT * w64::kT;
+  const dim3 grid((rows_pad * 8 + 127) / 128, em.frames);
+  return w64::launch_pdl(w64::expand_train64_multi_kernel, grid, dim3(128), 0, stream, pdl != 0, em);
+}
+
+// ev, fa, launched, phase: as launch_knn2_tc
 cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_nq, int pdl, cudaEvent_t* ev,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, FinishArgs* fa, int* launched, int phase) {
+  if (launched) *launched = 0;
   if (batch.num_problems <= 0 || tc.total <= 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(w64::knn2_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::kSmemBytes);
   if (e != cudaSuccess) return e;
   const bool p = pdl != 0;
   if (ev) cudaEventRecord(ev[0], stream);
-  if (tc.unit_q == 2 * w64::kQ) {
-    // CTA pairs: tc.grid counts pairs; cluster dimensions are a compile-time attribute of the kernel
-    e = cudaFuncSetAttribute(w64::pair::knn2_tc64_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::pair::kSmemBytesP);
+  if (phase != 2) {
+    if (tc.unit_q == 2 * w64::kQ) {
+      // CTA pairs: tc.grid counts pairs; cluster dimensions are a compile-time attribute of the kernel
+      e = cudaFuncSetAttribute(w64::pair::knn2_tc64_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::pair::kSmemBytesP);
+      if (e != cudaSuccess) return e;
+      e = w64::launch_pdl(w64::pair::knn2_tc64_pair_kernel, dim3(2 * tc.grid), dim3(w64::kThreads), w64::pair::kSmemBytesP, stream, p,
+                          batch, tc);
+    } else {
+      e = w64::launch_pdl(w64::knn2_tc64_kernel, dim3(tc.grid), dim3(w64::kThreads), w64::kSmemBytes, stream, p, batch, tc);
+    }
     if (e != cudaSuccess) return e;
-    e = w64::launch_pdl(w64::pair::knn2_tc64_pair_kernel, dim3(2 * tc.grid), dim3(w64::kThreads), w64::pair::kSmemBytesP, stream, p,
-                        batch, tc);
-  } else {
-    e = w64::launch_pdl(w64::knn2_tc64_kernel, dim3(tc.grid), dim3(w64::kThreads), w64::kSmemBytes, stream, p, batch, tc);
+    if (launched) *launched = 1;
   }
-  if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[1], stream);
+  if (phase == 1) return cudaSuccess;
+  if (fa && !batch.exact_second) {
+    e = launch_knn2_tc64_finish(batch, tc, max_nq, p, stream, fa);
+    if (ev) {
+      cudaEventRecord(ev[2], stream);
+      cudaEventRecord(ev[3], stream);
+    }
+    if (launched) *launched = phase == 2 ? 1 : 2;
+    return e;
+  }
+  if (phase == 2) return cudaErrorInvalidValue;
   if (batch.exact_second) {
     dim3 rgrid((max_nq + w64::kRefineQB - 1) / w64::kRefineQB, batch.num_problems);
     e = w64::launch_pdl(w64::knn2_tc64_refine_kernel<true>, rgrid, dim3(w64::kRefineThreads), 0, stream, p, batch, tc);
@@ -854,6 +916,7 @@ cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_n
   if (ev) cudaEventRecord(ev[2], stream);
   e = launch_knn2_compact(batch, max_nq, p, stream);
   if (ev) cudaEventRecord(ev[3], stream);
+  if (launched) *launched = 3;
   return e;
 }
 

@@ -875,9 +875,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
   return v;
 }
 
+// WORDS = 8: 32-byte rows (knn2_tc_kernel's partial keys: one 16-byte record per segment), 16:
+// 64-byte rows (knn2_tc64_kernel.cu: two records per segment; a step reads one row, 16 bytes
+// per lane, and the four lanes add up their quarters).
+template <int WORDS>
 __global__ void __launch_bounds__(kFinThreads, 1536 / kFinThreads)
 knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc,
                       const __grid_constant__ FinishArgs fa) {
+  static_assert(WORDS == 8 || WORDS == 16, "32- or 64-byte rows");
+  constexpr int kRecs = WORDS / 8;             // 16-byte partial records per segment
   __shared__ unsigned s_woff[kFinThreads / 32];
   __shared__ unsigned s_base;
   __shared__ int s_where[3];
@@ -904,8 +910,8 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       const int pr = id / fa.nqb, b = id - pr * fa.nqb;
       s_where[0] = pr;
       s_where[1] = b;
-      // (the 32 queries of a block are in one 256-query block of the distance kernel)
-      s_where[2] = tc_block_segments(tc, tc.qb_begin[pr] + (b * kFinQ) / kTcQ);
+      // (the queries of a block are in one query block of the distance kernel)
+      s_where[2] = tc_block_segments(tc, tc.qb_begin[pr] + (b * kFinQ) / (WORDS == 8 ? kTcQ : tc.unit_q));
     }
     __syncthreads();
     const int problem = s_where[0], qb = s_where[1];
@@ -918,8 +924,9 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     const int q0 = qb * kFinQ;
     const int q = q0 + tid / kFinLanes;
     // lane `part` of a query works on 16-byte half `part & 1` of every second row of the bucket
+    // (64-byte rows: on quarter `part` of every row)
     uint4 qh = make_uint4(0u, 0u, 0u, 0u);
-    if (q < nq) qh = __ldg(reinterpret_cast<const uint4*>(P.q + size_t(q) * 8) + (part & 1));
+    if (q < nq) qh = __ldg(reinterpret_cast<const uint4*>(P.q + size_t(q) * WORDS) + (WORDS == 8 ? (part & 1) : part));
     if (!fa.nowait) {
       pdl_wait();                              // the partial bucket keys are complete
       if (tid == 0) ktrace_start(batch.ktrace, 4);
@@ -940,10 +947,10 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     if (q < nq) {
       int b1 = kTcKeySentinel, b2 = kTcKeySentinel;
       // the query block's tile slots were shared out to consecutive CTAs, one partial segment each
-      const int nseg = s_where[2];
-      static_assert(kTcColSplit == 2 && kTcQ % kFinQ == 0, "one uint4 = the two column-half partials of a segment");
+      const int nseg = s_where[2] * kRecs;
+      static_assert(kTcColSplit == 2 && kTcQ % kFinQ == 0 && 128 % kFinQ == 0, "one uint4 = two partial pairs of a segment");
       const uint4* part_keys = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(batch.partial) +
-                                                               size_t(P.row0 + q) * (tc.slots * kTcColSplit));
+                                                               size_t(P.row0 + q) * (tc.slots * kTcColSplit * kRecs));
       auto merge = [&](int a1, int a2) {   // merge two descending pairs
         const int hi = max(b1, a1), lo = min(b1, a1);
         b2 = max(lo, max(b2, a2));
@@ -967,30 +974,34 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     }
     // ---- exact distances to the rows of the best bucket.  The bucket is 2 * kTcBucket 16-byte
     // pieces; in step j the query's four lanes read pieces 4j .. 4j+3 (64 contiguous bytes = rows
-    // 2j, 2j+1), a lane and its neighbour add up the two halves of a row.
+    // 2j, 2j+1), a lane and its neighbour add up the two halves of a row.  (64-byte rows: 4 *
+    // kTcBucket pieces, a step is one row, the four lanes add up its quarters.)
     uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
     {
       const bool have = key != kTcKeySentinel;
       const int row_base = have ? (kBucketIdMask - (key & kBucketIdMask)) * kTcBucket : 0;
-      const uint4* pieces = reinterpret_cast<const uint4*>(P.t + size_t(row_base) * 8) + part;
-      const int rsub = part >> 1;
+      const uint4* pieces = reinterpret_cast<const uint4*>(P.t + size_t(row_base) * WORDS) + part;
+      const int rsub = WORDS == 8 ? (part >> 1) : 0;
+      constexpr int kSteps = WORDS == 8 ? kTcBucket / 2 : kTcBucket;
+      constexpr int kRowsPerStep = WORDS == 8 ? 2 : 1;
 #pragma unroll
-      for (int j0 = 0; j0 < kTcBucket / 2; j0 += 4) {
+      for (int j0 = 0; j0 < kSteps; j0 += 4) {
         uint4 t[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          t[u] = (have && row_base + 2 * (j0 + u) + rsub < nt) ? __ldg(pieces + 4 * (j0 + u)) : make_uint4(0u, 0u, 0u, 0u);
+          t[u] = (have && row_base + kRowsPerStep * (j0 + u) + rsub < nt) ? __ldg(pieces + 4 * (j0 + u)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint32_t d = __popc(t[u].x ^ qh.x) + __popc(t[u].y ^ qh.y) + __popc(t[u].z ^ qh.z) + __popc(t[u].w ^ qh.w);
           d += __shfl_xor_sync(0xffffffffu, d, 1);
-          const int row = row_base + 2 * (j0 + u) + rsub;
+          if (WORDS == 16) d += __shfl_xor_sync(0xffffffffu, d, 2);
+          const int row = row_base + kRowsPerStep * (j0 + u) + rsub;
           if (have && row < nt) top2_insert(k1, k2, (d << kIdxBits) + uint32_t(row));
         }
       }
     }
-    // the two lane pairs of a query saw the even / the odd rows
-    {
+    if (WORDS == 8) {
+      // the two lane pairs of a query saw the even / the odd rows
       const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, 2), o2 = __shfl_xor_sync(0xffffffffu, k2, 2);
       top2_merge(k1, k2, o1, o2);
     }
@@ -998,7 +1009,7 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       // the second-best bucket's best distance is exact (its maximum dot is); its first row stands
       // in as the index, which nobody reads on this path
       const int dot = key2 >> kBucketIdBits;
-      top2_insert(k1, k2, (uint32_t((kTcRowBytes - dot) >> 1) << kIdxBits) +
+      top2_insert(k1, k2, (uint32_t((32 * WORDS - dot) >> 1) << kIdxBits) +
                               uint32_t((kBucketIdMask - (key2 & kBucketIdMask)) * kTcBucket));
     }
     // ---- ratio test (src/slam_frontend.cc:529-536), one lane per query
@@ -1133,6 +1144,14 @@ cudaError_t launch_knn2_compact(const KnnBatch& batch, int max_nq, bool pdl, cud
 // kernels removes their programmatic overlap, so it is only used in dedicated timing passes).
 // fa (optional): refine + compaction as ONE kernel (knn2_tc_finish_kernel; fa->nqb and the
 // grid are filled in here); ignored when the second neighbour's index is wanted.
+// The finish kernel alone, for the 64-byte engine (knn2_tc64_kernel.cu).
+cudaError_t launch_knn2_tc64_finish(const KnnBatch& batch, const TcBatch& tc, int max_nq, bool pdl,
+                                    cudaStream_t stream, FinishArgs* fa) {
+  fa->nqb = (max_nq + kFinQ - 1) / kFinQ;
+  const int grid = fa->nqb * batch.num_problems;
+  return launch_pdl(knn2_tc_finish_kernel<16>, dim3(grid), dim3(kFinThreads), 0, stream, pdl, batch, tc, *fa);
+}
+
 // phase: 0 = the whole sequence, 1 = the distance kernel only, 2 = the finish kernel only (a
 // group of poses: first every pose's distance kernel, then every pose's finish kernel).
 cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, int max_nq, int pdl,
@@ -1157,7 +1176,7 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
   if (fa && !batch.exact_second) {
     fa->nqb = (max_nq + kFinQ - 1) / kFinQ;
     const int grid = fa->nqb * batch.num_problems;
-    e = launch_pdl(knn2_tc_finish_kernel, dim3(grid), dim3(kFinThreads), 0, stream, p, batch, tc, *fa);
+    e = launch_pdl(knn2_tc_finish_kernel<8>, dim3(grid), dim3(kFinThreads), 0, stream, p, batch, tc, *fa);
     if (ev) {
       cudaEventRecord(ev[2], stream);
       cudaEventRecord(ev[3], stream);

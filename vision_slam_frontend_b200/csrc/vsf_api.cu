@@ -32,7 +32,8 @@ cudaError_t launch_expand_train_multi(const ExpandMulti& em, int int8, int pdl, 
 cudaError_t launch_expand_train64(const void* t, int nt_bound, const int* nt_dev, void* out, int pdl,
                                   cudaStream_t stream);
 cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_nq, int pdl, cudaEvent_t* ev,
-                             cudaStream_t stream);
+                             cudaStream_t stream, FinishArgs* fa, int* launched, int phase);
+cudaError_t launch_expand_train64_multi(const ExpandMulti& em, int pdl, cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* out, int n, int first_pose, int n_poses, int stride,
                          uint64_t seed, int words, int desc_bytes, cudaStream_t stream);
 int probe_ops_per_step(int kind);
@@ -544,9 +545,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     plan_tc_partition(&tb, qblocks, pair ? sm_avail / 2 : sm_avail, c->force_split,
                       size_t(row0) * (wide ? 2 : 1), c->partial_cap);
     b.split = tb.slots;
-    if (wide)
-      VSF_CUDA(c, launch_knn2_tc64(b, tb, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream));
-    else {
+    {
       // refine + compaction as one kernel (engine flag 512: the two separate kernels, A/B timing)
       FinishArgs fa;
       std::memset(&fa, 0, sizeof(fa));
@@ -555,7 +554,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       fa.flags = c->d_finish_flags;
       int phase = 0;
       if (pose) {
-        if (pose->exp_src && pose->exp_nt > 0) {
+        if (!wide && pose->exp_src && pose->exp_nt > 0) {
           tb.exp_src = static_cast<const uint32_t*>(pose->exp_src);
           tb.exp_nt = pose->exp_nt;
           tb.exp_out = pose->exp_out;
@@ -565,19 +564,21 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
         if (pose->flags) fa.flags = pose->flags;
         if (pose->ticket) fa.ticket = pose->ticket;
         fa.nowait = pose->nowait;
-        if (pose->em) {
+        if (pose->em && !wide) {
           fa.em = *pose->em;
           fa.em_int8 = int8;
         }
         phase = pose->phase;
       }
       int launched = 0;
-      VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream,
-                                 (c->engine_flags & 512) ? nullptr : &fa, &launched, phase));
-      if (phase != 1 && !(c->engine_flags & 512)) ++c->finish_epoch;
+      FinishArgs* fap = (c->engine_flags & 512) ? nullptr : &fa;
+      if (wide)
+        VSF_CUDA(c, launch_knn2_tc64(b, tb, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream, fap, &launched, phase));
+      else
+        VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream, fap, &launched, phase));
+      if (phase != 1 && fap && !b.exact_second) ++c->finish_epoch;
       c->launches += launched;
     }
-    if (wide) c->launches += 3;
     c->pev_valid = c->profile != 0;
     return VSF_OK;
   }
@@ -1367,7 +1368,8 @@ static int flush_flights(vsf_ctx* c) {
   VSF_CUDA(c, cudaStreamWaitEvent(c->stream, fl[m - 1]->ev_up, 0));
   int rc = VSF_OK;
   // grouped launch: every frame has work for the tensor engine's 32-byte kernels
-  bool grouped = m > 1 && c->words == 8 && c->engine != 1 && !(c->engine_flags & (8 | 512 | 1024)) && !c->profile;
+  bool grouped = m > 1 && (c->words == 8 || (c->words == 16 && c->engine != 3)) && c->engine != 1 &&
+                 !(c->engine_flags & (8 | 512 | 1024)) && !c->profile;
   bool any_side_sort = false;
   for (int g = 0; g < m; ++g) {
     const vsf_ctx::Flight& f = *fl[g];
@@ -2107,7 +2109,9 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
   // the call writes the ctx's own lists (vsf_fetch_window).  With G = 1 the distance kernel
   // expands the next pose's frame itself.
   const bool tensor = c->engine >= 2 || (c->engine == 0 && double(W) * double(n) * double(n) >= c->tc_auto_min_cmp);
-  const bool ahead = tensor && c->words == 8 && n > 0 && count > 0 && !(c->engine_flags & (256 | 512));
+  const bool wide = c->words == 16;
+  bool ahead = tensor && (c->words == 8 || (wide && c->engine != 3)) && n > 0 && count > 0 && !(c->engine_flags & (256 | 512));
+  if (wide && (c->profile || c->pose_group < 2)) ahead = false;   // 64-byte rows: groups only (no expansion inside the distance kernel)
   const int int8 = c->engine == 3 ? 0 : 1;
   const int pdl = (c->engine_flags & 8) ? 0 : 1;
   const bool early_ok = !(c->engine_flags & (8 | 1024));
@@ -2157,10 +2161,16 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
       }
       return em;
     };
-    {
-      const ExpandMulti em = group_images(0, 0);
-      VSF_CUDA(c, launch_expand_train_multi(em, int8, pdl, c->stream));
+    auto expand_images = [&](const ExpandMulti& em) -> int {
+      if (em.frames == 0) return VSF_OK;
+      if (wide) VSF_CUDA(c, launch_expand_train64_multi(em, pdl, c->stream));
+      else VSF_CUDA(c, launch_expand_train_multi(em, int8, pdl, c->stream));
       ++c->launches;
+      return VSF_OK;
+    };
+    {
+      const int rc0 = expand_images(group_images(0, 0));
+      if (rc0) return rc0;
     }
     int rc = VSF_OK;
     vsf_dmatch* const own_matches = c->match_base;
@@ -2168,7 +2178,8 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
     for (int k0 = 0, grp = 0; k0 < count; k0 += G, ++grp) {
       const int parity = grp & 1;
       const int m = std::min(G, count - k0);
-      // the next group's images are made by this group's first finish kernel
+      // the next group's images are made by this group's first finish kernel (64-byte rows: by
+      // a kernel of their own between the group's distance and finish kernels)
       const ExpandMulti next_em = group_images(k0 + G, parity ^ 1);
       for (int phase = 1; phase <= 2 && !rc; ++phase) {
         for (int g = 0; g < m && !rc; ++g) {
@@ -2184,13 +2195,14 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
           pl.flags = c->grp_flags + size_t(g) * flag_words;
           pl.ticket = tickets + g;
           pl.nowait = (phase == 2 && g > 0 && early_ok) ? 1 : 0;
-          if (phase == 2 && g == 0 && next_em.frames > 0) pl.em = &next_em;
+          if (phase == 2 && g == 0 && next_em.frames > 0 && !wide) pl.em = &next_em;
           // survivor lists: slot 0 = the ctx's own (the last pose of the call ends up there)
           const int slot = (count - 1 - k) % G;
           c->match_base = slot == 0 ? own_matches : c->grp_matches + size_t(slot - 1) * rows_cap;
           c->count_base = slot == 0 ? own_counts : c->grp_counts + size_t(slot - 1) * kMaxProblems;
           rc = run_knn(c, specs, ratio, false, false, &pl);
         }
+        if (phase == 1 && wide && !rc) rc = expand_images(next_em);
       }
       c->match_base = own_matches;
       c->count_base = own_counts;
