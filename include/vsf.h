@@ -419,8 +419,9 @@ int vsf_window_match_block_device(vsf_ctx* ctx, const void* d_seq, int n, int n_
  * the caller only wants the lists to have reached host memory.  The window must hold the frames
  * the caller wants frame `first` matched against (vsf_window_push).  Returns after every frame
  * has been collected; *h2d_bytes / *d2h_bytes (optional) accumulate vsf_window_last_transfer.
- * Knowing the frames ahead, the call uploads min(VSF_OPT_POSE_GROUP, lag) of them before it
- * launches their kernels together (like vsf_window_match_block_device); the lists are the same. */
+ * Knowing the frames ahead, the call uploads min(VSF_OPT_POSE_GROUP, lag / 3) of them before
+ * it launches their kernels together (like vsf_window_match_block_device); the lists are the
+ * same.  lag = 12 keeps groups of four frames flowing. */
 int vsf_window_run_sequence(vsf_ctx* ctx, const uint8_t* h_seq, int n, int n_poses,
                             long long first, int count, double nn_match_ratio,
                             float best_percent, int sort_mode, int lag,

@@ -354,8 +354,63 @@ def test_block_device_launch_variants(n, W, count, width):
             np.testing.assert_array_equal(got[k][j], exp)
 
 
-@pytest.mark.parametrize("sort_mode,width", [(0, 32), (1, 32), (2, 32), (1, 61), (2, 61)])
-def test_window_run_sequence_equals_per_frame_calls(sort_mode, width):
+@pytest.mark.parametrize("width", [32, 61])
+def test_tensor_launch_replayed_from_a_cuda_graph(width):
+    """The finish kernel's ticket counter and look-back epoch live on the device and are advanced by
+    the launch itself, so a captured launch sequence can be replayed (bench.py's C2 leg does) - also
+    on new data in the same buffers."""
+    import ctypes as C
+    import torch
+    n, W = 1500, 2
+    with new_ctx(desc_bytes=width, max_features=2048, window=W) as ctx:
+        stream = torch.cuda.Stream()
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_engine(2, 0)
+        rb = ctx.row_bytes
+
+        def padded(a):
+            out = np.zeros((a.shape[0], rb), np.uint8)
+            out[:, :width] = a
+            return out
+        q = [torch.zeros((n, rb), dtype=torch.uint8, device="cuda") for _ in range(W)]
+        t = torch.zeros((n, rb), dtype=torch.uint8, device="cuda")
+        qp = (C.c_void_p * W)(*[x.data_ptr() for x in q])
+        nn = (C.c_int * W)(*([n] * W))
+
+        def launch():
+            assert ctx._L.vsf_window_match_device(ctx._h, qp, nn, W, C.c_void_p(t.data_ptr()), n, RATIO) == 0
+
+        def load(seed):
+            frames = [synth.synth_pose(n, p, 150, seed, width) for p in range(W + 1)]
+            for j in range(W):
+                q[j].copy_(torch.from_numpy(padded(frames[j])))
+            t.copy_(torch.from_numpy(padded(frames[W])))
+            torch.cuda.synchronize()
+            return frames
+        load(1)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                launch()
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                launch()
+        for seed in (2, 3, 4, 5):
+            frames = load(seed)
+            g.replay()
+            torch.cuda.synchronize()
+            got = ctx.fetch_window(W)
+            for j in range(W):
+                np.testing.assert_array_equal(got[j], native.get_matches(frames[j], frames[W], RATIO))
+        launch()     # and an ordinary launch after the replays
+        got = ctx.fetch_window(W)
+        for j in range(W):
+            np.testing.assert_array_equal(got[j], native.get_matches(frames[j], frames[W], RATIO))
+
+
+@pytest.mark.parametrize("sort_mode,width,lag", [(0, 32, 12), (1, 32, 12), (2, 32, 12), (1, 61, 12), (2, 61, 9), (1, 32, 5),
+                                                  (2, 32, 1)])
+def test_window_run_sequence_equals_per_frame_calls(sort_mode, width, lag):
     """vsf_window_run_sequence (groups of frames uploaded, then launched together) returns per
     frame what the oracle's GetMatches + sort + cut gives for the window of that moment."""
     import torch
@@ -374,7 +429,7 @@ def test_window_run_sequence_equals_per_frame_calls(sort_mode, width):
             ctx.window_push(1000 + p, frames[p])
         out = np.zeros((count, W, n), capi.FEATURE_MATCH_DTYPE)
         counts = np.zeros((count, W), np.int32)
-        h2d, d2h = ctx.window_run_sequence(hp, W, count, RATIO, float(BP), sort_mode, 5, out, counts)
+        h2d, d2h = ctx.window_run_sequence(hp, W, count, RATIO, float(BP), sort_mode, lag, out, counts)
         assert h2d == count * n * rb and d2h > 0 and ctx.window_in_flight() == 0
     live = [frames[p] for p in range(W)]
     for k in range(count):

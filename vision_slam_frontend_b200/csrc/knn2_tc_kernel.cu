@@ -850,10 +850,9 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
 // so the wait is short).  A CTA only ever waits for CTAs with a smaller logical index, and the
 // logical index is handed out by an atomic ticket in the order the CTAs start, so every CTA
 // that is waited for is already running: no deadlock whatever order the hardware dispatches
-// the grid in.  Ticket counter, per-SM counters and look-back words carry the launch's epoch in
-// their upper bits (64-bit words, the epoch only grows), so nothing is ever reset; consecutive
-// launches, whose CTAs may be starting while the previous launch is still running, alternate
-// between two ticket counters.
+// the grid in.  The look-back words carry the launch's epoch in their upper bits (64-bit words,
+// the epoch only grows) and are never reset; the epoch and the ticket counter live in device
+// memory (FinishArgs::state) and are advanced / reset by the last CTA of a launch to finish.
 constexpr int kFinLanes = 4;                          // lanes per query
 #ifndef VSF_FIN_THREADS
 #define VSF_FIN_THREADS 256
@@ -887,6 +886,7 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   __shared__ unsigned s_woff[kFinThreads / 32];
   __shared__ unsigned s_base;
   __shared__ int s_where[3];
+  __shared__ unsigned long long s_epoch;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int part = tid % kFinLanes;
@@ -905,8 +905,8 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   do {
     if (tid == 0) {
       // the integer divisions of the block's coordinates are done once per CTA
-      atomicMax(fa.ticket, fa.epoch << 24);
-      const int id = int(atomicAdd(fa.ticket, 1ull) - (fa.epoch << 24));
+      s_epoch = ld_relaxed_u64(fa.state + 2);   // stable while any CTA of this launch runs
+      const int id = int(atomicAdd(fa.state, 1ull));
       const int pr = id / fa.nqb, b = id - pr * fa.nqb;
       s_where[0] = pr;
       s_where[1] = b;
@@ -915,6 +915,7 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     }
     __syncthreads();
     const int problem = s_where[0], qb = s_where[1];
+    const unsigned long long epoch = s_epoch;
     const KnnProblem& P = batch.p[problem];
     // The descriptors and row counts were written before the launch sequence began (see
     // knn2_tc_kernel): the query words are fetched while the distance kernel is still finishing.
@@ -1033,13 +1034,13 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       total += s_woff[w];
     }
     unsigned long long* flags = fa.flags + P.qb0;              // qb0 counts 32-query units: every (kFinQ / 32)-th word is used
-    if (tid == 0) st_relaxed_u64(flags + qb * (kFinQ / 32), (fa.epoch << 8) | total);
+    if (tid == 0) st_relaxed_u64(flags + qb * (kFinQ / 32), (epoch << 8) | total);
     if (warp == 0) {
       // one warp polls (with a back-off: the other CTAs of the SM are still refining)
       unsigned sum = 0;
       for (int i = lane; i < qb; i += 32) {
         unsigned long long v = ld_relaxed_u64(flags + i * (kFinQ / 32));
-        while ((v >> 8) != fa.epoch) {
+        while ((v >> 8) != epoch) {
           __nanosleep(40);
           v = ld_relaxed_u64(flags + i * (kFinQ / 32));
         }
@@ -1069,7 +1070,19 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     }
   } while (false);
   if (fa.nowait) pdl_wait();
-  if (tid == 0) ktrace_end(batch.ktrace, 2);
+  // the last CTA to get here leaves the state ready for the next launch on it
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(fa.state + 1, 1ull) == (unsigned long long)(gridDim.x - 1)) {
+      const unsigned long long e = ld_relaxed_u64(fa.state + 2);
+      st_relaxed_u64(fa.state, 0ull);
+      st_relaxed_u64(fa.state + 1, 0ull);
+      __threadfence();
+      st_relaxed_u64(fa.state + 2, e + 1ull);
+    }
+    ktrace_end(batch.ktrace, 2);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

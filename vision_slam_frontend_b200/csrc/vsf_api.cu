@@ -139,8 +139,8 @@ struct vsf_ctx {
   long long launches = 0;                   // kernels launched by run_knn (vsf_debug_launch_count)
   // knn2_tc_finish_kernel: ticket counter, per-block (epoch | survivor count) words, and the
   // host's copies of the running values
-  unsigned long long *d_finish_ticket = nullptr, *d_finish_flags = nullptr;   // ticket: [2], alternating
-  unsigned long long finish_epoch = 0;
+  unsigned long long *d_finish_ticket = nullptr, *d_finish_flags = nullptr;   // ticket: two FinishArgs::state (4 words each)
+  int finish_parity = 0;
   size_t partial_cap = 0;
   unsigned *d_qblock_arrivals = nullptr, *d_qblock_pass = nullptr, *d_problem_arrivals = nullptr;
   vsf_dmatch* d_matches = nullptr;
@@ -549,8 +549,11 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       // refine + compaction as one kernel (engine flag 512: the two separate kernels, A/B timing)
       FinishArgs fa;
       std::memset(&fa, 0, sizeof(fa));
-      fa.epoch = c->finish_epoch + 1;
-      fa.ticket = c->d_finish_ticket + (fa.epoch & 1ull);
+      // two launch states, used alternately: the CTAs of a pose's finish kernel may draw their
+      // tickets while the previous pose's finish kernel is still running (early-start distance
+      // kernels let their successor launch at once); their epochs never meet (1.., 2^40 + 1..),
+      // so the two can share the look-back words
+      fa.state = c->d_finish_ticket + 4 * (c->finish_parity & 1);
       fa.flags = c->d_finish_flags;
       int phase = 0;
       if (pose) {
@@ -562,7 +565,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
         tb.early = pose->early;
         if (pose->partial) b.partial = pose->partial;
         if (pose->flags) fa.flags = pose->flags;
-        if (pose->ticket) fa.ticket = pose->ticket;
+        if (pose->ticket) fa.state = pose->ticket;
         fa.nowait = pose->nowait;
         if (pose->em && !wide) {
           fa.em = *pose->em;
@@ -576,8 +579,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
         VSF_CUDA(c, launch_knn2_tc64(b, tb, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream, fap, &launched, phase));
       else
         VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream, fap, &launched, phase));
-      if (phase != 1 && fap && !b.exact_second) ++c->finish_epoch;
       c->launches += launched;
+      if (phase != 1 && fap && !b.exact_second && !(pose && pose->ticket)) c->finish_parity ^= 1;
     }
     c->pev_valid = c->profile != 0;
     return VSF_OK;
@@ -790,9 +793,12 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   cudaMemset(c->d_qblock_arrivals, 0, qb_cap * sizeof(unsigned));
   cudaMemset(c->d_qblock_pass, 0, qb_cap * sizeof(unsigned));
   cudaMemset(c->d_problem_arrivals, 0, kMaxProblems * sizeof(unsigned));
-  VSF_ALLOC(c, c->d_finish_ticket, 2 * sizeof(unsigned long long));
+  VSF_ALLOC(c, c->d_finish_ticket, 8 * sizeof(unsigned long long));
   VSF_ALLOC(c, c->d_finish_flags, (qb_cap + 8) * sizeof(unsigned long long));
-  cudaMemset(c->d_finish_ticket, 0, 2 * sizeof(unsigned long long));
+  {
+    const unsigned long long init[8] = {0ull, 0ull, 1ull, 0ull, 0ull, 0ull, (1ull << 40) + 1ull, 0ull};   // epoch 0 is what the zeroed look-back words hold
+    cudaMemcpy(c->d_finish_ticket, init, sizeof(init), cudaMemcpyHostToDevice);
+  }
   cudaMemset(c->d_finish_flags, 0, (qb_cap + 8) * sizeof(unsigned long long));   // epoch 0 is never used
   VSF_ALLOC(c, c->d_matches, rows_cap * sizeof(vsf_dmatch));
   c->match_base = c->d_matches;
@@ -1349,6 +1355,27 @@ static int flights_init(vsf_ctx* c) {
 
 extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_count : 0; }
 
+// Per-slot state of the finish kernels of a group of poses / frames: look-back words and launch
+// states (FinishArgs::state, epoch 1: the zeroed look-back words hold epoch 0), survivor lists of
+// the poses that do not write the ctx's own.  Allocated on first use.
+static int group_state_init(vsf_ctx* c) {
+  if (c->grp_flags) return VSF_OK;
+  const size_t flag_words = c->qb_cap + 8;
+  const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
+  const size_t words = size_t(kMaxPoseGroup) * flag_words + 4 * kMaxPoseGroup;
+  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), words * sizeof(unsigned long long)));
+  VSF_CUDA(c, cudaMemset(c->grp_flags, 0, words * sizeof(unsigned long long)));
+  unsigned long long init[4 * kMaxPoseGroup];
+  for (int g = 0; g < kMaxPoseGroup; ++g) {
+    init[4 * g] = init[4 * g + 1] = init[4 * g + 3] = 0ull;
+    init[4 * g + 2] = 1ull;
+  }
+  VSF_CUDA(c, cudaMemcpy(c->grp_flags + size_t(kMaxPoseGroup) * flag_words, init, sizeof(init), cudaMemcpyHostToDevice));
+  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
+  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
+  return VSF_OK;
+}
+
 // Launch the kernels of the staged frames (vsf_window_submit stages one frame; ordinarily it is
 // flushed at once, vsf_window_run_sequence lets c->defer_group frames accumulate).  On the tensor
 // engine with 32-byte rows a group is launched like a group of poses of
@@ -1390,14 +1417,7 @@ static int flush_flights(vsf_ctx* c) {
   size_t flag_words = 0;
   if (grouped) {
     flag_words = c->qb_cap + 8;
-    if (!c->grp_flags) {
-      const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
-      const size_t bytes = (size_t(kMaxPoseGroup) * flag_words + kMaxPoseGroup) * sizeof(unsigned long long);
-      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), bytes));
-      VSF_CUDA(c, cudaMemsetAsync(c->grp_flags, 0, bytes, c->stream));
-      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
-      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
-    }
+    if ((rc = group_state_init(c))) return rc;
     tickets = c->grp_flags + size_t(kMaxPoseGroup) * flag_words;
     for (int g = 0; g < m; ++g)
       if (!fl[g]->d_partial)
@@ -1441,7 +1461,7 @@ static int flush_flights(vsf_ctx* c) {
         pl.early = (phase == 1 && g > 0) ? 1 : 0;
         pl.partial = f.d_partial;
         pl.flags = c->grp_flags + size_t(g) * flag_words;
-        pl.ticket = tickets + g;
+        pl.ticket = tickets + 4 * g;
         pl.nowait = (phase == 2 && g > 0) ? 1 : 0;
         rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1, false, &pl);
       } else {
@@ -2142,12 +2162,9 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
         else VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_exp[i]), image_bytes));
       }
     }
-    if (!c->grp_flags) {
-      const size_t bytes = (size_t(kMaxPoseGroup) * flag_words + kMaxPoseGroup) * sizeof(unsigned long long);
-      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), bytes));
-      VSF_CUDA(c, cudaMemsetAsync(c->grp_flags, 0, bytes, c->stream));
-      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
-      VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
+    {
+      const int rcs = group_state_init(c);
+      if (rcs) return rcs;
     }
     unsigned long long* tickets = c->grp_flags + size_t(kMaxPoseGroup) * flag_words;
     auto group_images = [&](int k0, int parity) {   // frames of poses k0 .. k0 + G - 1
@@ -2193,7 +2210,7 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
           pl.early = (phase == 1 && early_ok && g > 0) ? 1 : 0;
           pl.partial = c->grp_partial[parity * G + g];
           pl.flags = c->grp_flags + size_t(g) * flag_words;
-          pl.ticket = tickets + g;
+          pl.ticket = tickets + 4 * g;
           pl.nowait = (phase == 2 && g > 0 && early_ok) ? 1 : 0;
           if (phase == 2 && g == 0 && next_em.frames > 0 && !wide) pl.em = &next_em;
           // survivor lists: slot 0 = the ctx's own (the last pose of the call ends up there)
@@ -2255,7 +2272,8 @@ extern "C" int vsf_window_run_sequence(vsf_ctx* c, const uint8_t* h_seq, int n, 
     vsf_ctx* c;
     ~DeferGuard() { c->defer_group = 1; }
   } guard{c};
-  c->defer_group = std::max(1, std::min(c->pose_group, lag));
+  // (a group in flight, one being sorted / collected, one being staged: a third of the lag)
+  c->defer_group = std::max(1, std::min(c->pose_group, lag / 3));
   uint64_t fid = 0, fids[kMaxProblems];
   int nf = 0;
   long long collected = 0;

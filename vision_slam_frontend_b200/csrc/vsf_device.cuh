@@ -127,9 +127,13 @@ struct ExpandMulti {
 
 // Arguments of knn2_tc_finish_kernel (refine + ordered compaction in one kernel, see there).
 struct FinishArgs {
-  unsigned long long* ticket;        // (epoch << 24 | next block): raised to this launch's epoch by its first CTAs
+  // Device-side launch state, three words: [0] ticket = next logical block, [1] CTAs that have
+  // finished, [2] epoch of the launch that is running (or will run next).  The last CTA to
+  // finish resets [0] and [1] and advances [2]; nothing depends on host-side counters, so a
+  // launch captured in a CUDA graph can be replayed.  Launches that share a state (and its
+  // look-back words) never overlap: each starts after its predecessor on the state completed.
+  unsigned long long* state;
   unsigned long long* flags;         // [32-query blocks of the batch, KnnProblem::qb0 + block] (epoch << 8 | survivors)
-  unsigned long long epoch;
   int nqb;                           // 32-query blocks per problem (grid = nqb * num_problems)
   // nowait != 0 (the later finish kernels of a group of poses): the distance kernel this launch
   // reads from had completed before the stream predecessor - the previous pose's finish kernel -
