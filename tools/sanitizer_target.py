@@ -101,4 +101,29 @@ with vsf.Context(device=0, max_features=20000, desc_bytes=32, window=2) as ctx: 
     m = np.zeros(18000, vsf.DMATCH_DTYPE)
     m["queryIdx"] = np.arange(18000); m["distance"] = np.random.default_rng(2).integers(0, 40, 18000).astype(np.float32)
     ctx.debug_sort_device(m, 0.3, True)
+# round 2 (second half): groups of poses - early-start distance kernels, finish kernels side by side (both
+# widths), the host-buffer sequence call with grouped launches, every sort mode
+import torch
+for width, n, W in ((32, 1300, 3), (61, 1500, 2)):
+    with vsf.Context(device=0, max_features=2048, desc_bytes=width, window=W) as ctx:
+        ctx.set_engine(2, 0)
+        rb = ctx.row_bytes
+        poses = W + 9
+        buf = torch.empty((poses, n, rb), dtype=torch.uint8, device="cuda")
+        ctx.synth_sequence_device(buf.data_ptr(), n, 0, poses, 97, 5)
+        for group, count in ((4, 9), (1, 3), (3, 4)):
+            ctx.set_option(capi.OPT_POSE_GROUP, group)
+            ctx.window_match_block_device(buf.data_ptr(), n, poses, 1, count, ratio)
+            ctx.fetch_window(W)
+        ctx.set_option(capi.OPT_POSE_GROUP, 4)
+        host = torch.empty((poses, n, rb), dtype=torch.uint8).pin_memory()
+        host.copy_(buf)
+        torch.cuda.synchronize()
+        hp = host.numpy()
+        for p in range(W):
+            ctx.window_push(p, hp[p][:, :width])
+        out = np.zeros((4, W, n), capi.FEATURE_MATCH_DTYPE)
+        cnt = np.zeros((4, W), np.int32)
+        for mode in (1, 2, 0):
+            ctx.window_run_sequence(hp, W, 13, ratio, 0.3, mode, 12, out, cnt)
 print("sanitizer target ok")
