@@ -1507,7 +1507,12 @@ static int flush_flights(vsf_ctx* c) {
     }
   }
   restore_state();
-  if (rc) return rc;
+  if (rc) {
+    // nothing of the group can be collected: drop its flights (the frames stay in the window; a
+    // failed launch leaves the context unusable for anything but vsf_destroy anyway)
+    c->flight_count -= m;
+    return rc;
+  }
   c->main_dirty = false;
   // one event behind the kernels of the whole group
   cudaEvent_t chain = fl[m - 1]->ev_chain;
