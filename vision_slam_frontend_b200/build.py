@@ -54,6 +54,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         # per-CTA timeline stamps inside knn2_tc_kernel (tools/tc_timeline.py); costs ~6 % of the
         # kernel even when switched off at run time, so never part of a normal build
         flags.append("-DVSF_TC_TRACE")
+    if os.environ.get("VSF_TC_BUCKET"):
+        flags.append("-DVSF_TC_BUCKET=" + os.environ["VSF_TC_BUCKET"])   # selection bucket of the tensor engine (8, 16, 32; default 16)
     if os.environ.get("VSF_TC_BRINGUP"):
         flags.append("-DVSF_TC_BRINGUP")   # engine flags 2 / 4 (tools/tc_scaling.py, tools/tc_probe.py)
     objs = []
