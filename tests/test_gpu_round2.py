@@ -323,9 +323,9 @@ def test_window_match_block_device(width):
                                               (1237, 3, 5, 32), (2900, 2, 4, 32), (700, 10, 9, 32), (130, 38, 3, 32),
                                               (3000, 1, 3, 32), (1400, 4, 6, 61), (1237, 3, 9, 64), (700, 10, 5, 61)])
 def test_block_device_launch_variants(n, W, count, width):
-    """A pose of a device-resident block is two kernels (distance + finish), launched in groups
-    (all distance kernels of a group, then all its finish kernels, the first of which expands
-    the next group's frames); group 1: the distance kernel expands the next pose's frame.  Engine flag
+    """The poses of a device-resident block are launched in groups, each group as ONE batch of all
+    its frame pairs (group * window <= 40 problems): one distance kernel, which also expands the
+    next group's frames, and one finish kernel; group 1: a pose is launched alone.  Engine flag
     256 = pose by pose (three kernels), 512 = refine and compaction as separate kernels (four),
     1024 = no early starts.  Same lists every way, equal to the oracle's."""
     import torch
@@ -344,8 +344,11 @@ def test_block_device_launch_variants(n, W, count, width):
             got[len(got)] = ctx.fetch_window(W)
             if width <= 32:
                 # + the expansion of the first pose's / group's frames (flags 256 / 512: one per pose, in per_pose)
-                extra = 0 if flags & (256 | 512) else 1
-                assert ctx.launch_count() - before == per_pose * count + extra
+                if flags & (256 | 512):
+                    assert ctx.launch_count() - before == per_pose * count
+                else:
+                    g_eff = max(1, min(group, 40 // W))
+                    assert ctx.launch_count() - before == 2 * ((count + g_eff - 1) // g_eff) + 1
     cur = ((2 + count - 1) % (poses - W)) + W
     for j in range(W):
         exp = native.get_matches(synth.synth_pose(n, cur - W + j, stride, seed, width),

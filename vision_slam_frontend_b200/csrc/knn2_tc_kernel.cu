@@ -66,6 +66,23 @@ __device__ __forceinline__ uint4 expand16(uint32_t b16) {
   return r;
 }
 
+// One (row, group of 4 K-chunks) item of a frame's image (the unit of work of every expansion).
+template <bool I8>
+__device__ __forceinline__ void expand_item(const uint32_t* __restrict__ t, int nt, uint8_t* __restrict__ out, int row, int cg) {
+  uint2 w = make_uint2(0u, 0u);
+  const bool live = row < nt;
+  if (live) w = __ldg(reinterpret_cast<const uint2*>(t + size_t(row) * 8) + cg);
+  const int tile = row / kTcTileRows, r = row % kTcTileRows;
+  uint8_t* base = out + size_t(tile) * kTcBBytes + size_t(r) * 16;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t word = (c < 2) ? w.x : w.y;
+    const uint32_t b16 = (word >> (16 * (c & 1))) & 0xFFFFu;
+    uint4 v = live ? expand16<I8>(b16) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(base + size_t(4 * cg + c) * (kTcTileRows * 16)) = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Train expansion.  One thread = one (row, group of 4 K-chunks).  Rows >= nt of the last tile
 // are written as zeros (their columns are masked in the epilogue).
@@ -96,23 +113,6 @@ expand_train_kernel(const uint32_t* __restrict__ t, int nt_bound, const int* __r
     *reinterpret_cast<uint4*>(base + size_t(4 * cg + c) * (kTcTileRows * 16)) = v;
   }
   if (threadIdx.x == 0) ktrace_end(kt, 0);
-}
-
-// One (row, group of 4 K-chunks) item of a frame's image (the unit of work of every expansion).
-template <bool I8>
-__device__ __forceinline__ void expand_item(const uint32_t* __restrict__ t, int nt, uint8_t* __restrict__ out, int row, int cg) {
-  uint2 w = make_uint2(0u, 0u);
-  const bool live = row < nt;
-  if (live) w = __ldg(reinterpret_cast<const uint2*>(t + size_t(row) * 8) + cg);
-  const int tile = row / kTcTileRows, r = row % kTcTileRows;
-  uint8_t* base = out + size_t(tile) * kTcBBytes + size_t(r) * 16;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t word = (c < 2) ? w.x : w.y;
-    const uint32_t b16 = (word >> (16 * (c & 1))) & 0xFFFFu;
-    uint4 v = live ? expand16<I8>(b16) : make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(base + size_t(4 * cg + c) * (kTcTileRows * 16)) = v;
-  }
 }
 
 // The same for the frames of a group of poses, blockIdx.y = frame.
@@ -430,27 +430,14 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
       pdl_launch_dependents();
     }
     if (tid == 0) TC_TRACE(3);
-    if (tc.exp_src) {
-      // this CTA's share of the next launch's train image (layout of expand_train_kernel), while
-      // the tensor core works on the first tile.  The image it replaces was last read two
+    if (tc.em.frames > 0) {
+      // this CTA's share of the next launch's train images (layout of expand_train_kernel), while
+      // the tensor core works on the first tile.  The images they replace were last read two
       // launches ago.
-      const int rows_pad = (tc.exp_nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
-      for (int idx = blockIdx.x * (kTcEpiWarps * 32) + tid; idx < rows_pad * 4; idx += gridDim.x * (kTcEpiWarps * 32)) {
-        const int row = idx % rows_pad;
-        const int cg = idx / rows_pad;  // 0..3: K-chunks 4*cg .. 4*cg+3  (words 2*cg, 2*cg+1)
-        uint2 wd = make_uint2(0u, 0u);
-        const bool live = row < tc.exp_nt;
-        if (live) wd = __ldg(reinterpret_cast<const uint2*>(tc.exp_src + size_t(row) * 8) + cg);
-        const int tile = row / kTcTileRows, rr = row % kTcTileRows;
-        uint8_t* dst = tc.exp_out + size_t(tile) * kTcBBytes + size_t(rr) * 16;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t word = (c < 2) ? wd.x : wd.y;
-          const uint32_t b16 = (word >> (16 * (c & 1))) & 0xFFFFu;
-          const uint4 v = live ? expand16<I8>(b16) : make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(dst + size_t(4 * cg + c) * (kTcTileRows * 16)) = v;
-        }
-      }
+      const int rows_pad = (tc.em.nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
+      for (int f = 0; f < tc.em.frames; ++f)
+        for (int idx = blockIdx.x * (kTcEpiWarps * 32) + tid; idx < rows_pad * 4; idx += gridDim.x * (kTcEpiWarps * 32))
+          expand_item<I8>(tc.em.src[f], tc.em.nt, tc.em.out[f], idx % rows_pad, idx / rows_pad);
     }
     while (walk_more(wk)) {
       walk_next(wk, U);                       // wk now stands on the unit after U
@@ -892,15 +879,6 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   const int part = tid % kFinLanes;
   if (tid == 0) ktrace_start(batch.ktrace, 2);
   if (fa.nowait) pdl_launch_dependents();
-  if (fa.em.frames > 0) {
-    // the next group's train images; nothing here depends on the running distance kernels
-    const int rows_pad = (fa.em.nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
-    for (int f = 0; f < fa.em.frames; ++f)
-      for (int idx = blockIdx.x * kFinThreads + tid; idx < rows_pad * 4; idx += gridDim.x * kFinThreads) {
-        if (fa.em_int8) expand_item<true>(fa.em.src[f], fa.em.nt, fa.em.out[f], idx % rows_pad, idx / rows_pad);
-        else expand_item<false>(fa.em.src[f], fa.em.nt, fa.em.out[f], idx % rows_pad, idx / rows_pad);
-      }
-  }
   // one block per CTA, taken by ticket (the do-while only gives the early exits a common end)
   do {
     if (tid == 0) {
@@ -936,7 +914,8 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     if (nq <= 0) {                             // CTA-uniform, like the next test
       if (qb == 0 && tid == 0) {
         *P.match_count = 0;
-        if (batch.host_counts) batch.host_counts[P.region] = 0;
+        if (P.host_count) *P.host_count = 0;
+        else if (batch.host_counts) batch.host_counts[P.region] = 0;
       }
       break;
     }
@@ -1066,7 +1045,8 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     }
     if (qb == nqb - 1 && tid == 0) {
       *P.match_count = int(base + total);
-      if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
+      if (P.host_count) *P.host_count = int(base + total);
+      else if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
     }
   } while (false);
   if (fa.nowait) pdl_wait();

@@ -74,21 +74,21 @@ struct ProblemSpec {
   // in the operand kind t_exp_int8 says (1 = int8, 0 = e4m3); run_knn then skips its expansion
   const uint8_t* t_exp = nullptr;
   int t_exp_int8 = 1;
+  // optional (batches that span several frames' buffers): where the survivors / their count go
+  // instead of the ctx's region `region`, and a mapped host word that also receives the count
+  vsf_dmatch* out = nullptr;
+  int* out_count = nullptr;
+  int* host_count = nullptr;
 };
 
-// A stream of poses (vsf_window_match_block_device): how one pose's kernels are launched.
+// A stream of poses (vsf_window_match_block_device, vsf_window_run_sequence): how the kernels of
+// a launch - one pose, or a group of poses as ONE batch - are launched.
 struct PoseLaunch {
-  int phase = 0;                  // 0 distance + finish, 1 distance kernel only, 2 finish kernel only
-  // the distance kernel expands the NEXT pose's train frame (one pose at a time: group size 1)
-  const void* exp_src = nullptr;
-  int exp_nt = 0;
-  uint8_t* exp_out = nullptr;
-  int early = 0;                  // TcBatch::early
-  uint2* partial = nullptr;       // partial-key buffer of this pose (nullptr: the ctx's)
-  unsigned long long* flags = nullptr;    // look-back words / ticket counter of this pose's finish kernel
-  unsigned long long* ticket = nullptr;   //   (nullptr: the ctx's)
-  int nowait = 0;                 // FinishArgs::nowait
-  const ExpandMulti* em = nullptr;   // FinishArgs::em (the first finish kernel of a group)
+  const ExpandMulti* em = nullptr;   // TcBatch::em: the distance kernel expands the next launch's train frames
+  int early = 0;                     // TcBatch::early
+  uint2* partial = nullptr;          // partial-key buffer of this launch (nullptr: the ctx's)
+  unsigned long long* flags = nullptr;   // look-back words / launch state of the finish kernel
+  unsigned long long* state = nullptr;   //   (nullptr: the ctx's)
 };
 
 struct vsf_ctx {
@@ -130,10 +130,9 @@ struct vsf_ctx {
   uint2* d_partial2 = nullptr;              // streams of poses: every other pose (allocated on first use)
   // groups of poses (vsf_window_match_block_device): per-slot buffers, allocated on first use
   int pose_group = 4;                       // VSF_POSE_GROUP (1 .. kMaxPoseGroup)
-  uint2* grp_partial[2 * kMaxPoseGroup] = {};
-  uint8_t* grp_exp[2 * kMaxPoseGroup] = {};
-  unsigned long long* grp_flags = nullptr;  // [kMaxPoseGroup][qb_cap + 8] + [kMaxPoseGroup] ticket counters
-  vsf_dmatch* grp_matches = nullptr;        // [kMaxPoseGroup - 1][regions][rows_pad]
+  uint8_t* grp_exp[2 * kMaxPoseGroup] = {};   // +-1 images: a group reads one half while the next group's are made
+  unsigned long long* grp_flags = nullptr;  // look-back words of a batch of kMaxProblems problems + 2 launch states
+  vsf_dmatch* grp_matches = nullptr;        // [kMaxPoseGroup - 1][regions][rows_pad]: survivors of the poses that do not write the ctx's own lists
   int* grp_counts = nullptr;                // [kMaxPoseGroup - 1][kMaxProblems]
   size_t qb_cap = 0;
   long long launches = 0;                   // kernels launched by run_knn (vsf_debug_launch_count)
@@ -223,7 +222,6 @@ struct vsf_ctx {
     std::vector<ProblemSpec> specs;
     double ratio = 0.0;
     int n = 0, slot = 0, max_cnt = 0;
-    uint2* d_partial = nullptr;         // partial bucket keys of this frame's distance kernel (tensor engine)
     cudaEvent_t chain = nullptr;        // the ev_chain recorded behind this frame's kernels (its group's last frame's)
   };
   struct SortTask {
@@ -440,8 +438,9 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     p.nt_dev = s.nt_dev;
     p.nq = s.nq;
     p.nt = s.nt;
-    p.matches = c->region_ptr(s.region);
-    p.match_count = c->count_base + s.region;
+    p.matches = s.out ? s.out : c->region_ptr(s.region);
+    p.match_count = s.out_count ? s.out_count : c->count_base + s.region;
+    p.host_count = s.host_count;
     p.row0 = row0;
     p.qb0 = qb0;
     p.region = s.region;
@@ -454,7 +453,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   if (max_nq == 0) {
     // nothing to match: every problem reports zero survivors
     for (int i = 0; i < b.num_problems; ++i) {
-      VSF_CUDA(c, cudaMemsetAsync(c->count_base + specs[i].region, 0, sizeof(int), c->stream));
+      VSF_CUDA(c, cudaMemsetAsync(b.p[i].match_count, 0, sizeof(int), c->stream));
       if (mirror) c->mir_hcounts[specs[i].region] = 0;   // no kernel will write it
     }
     return VSF_OK;
@@ -470,6 +469,8 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
   bool tc_ok = (c->words == 8 || (c->words == 16 && c->engine != 3)) && max_nt >= 1;
   if (tc_ok) {
     for (int i = 0; i < b.num_problems && tc_ok; ++i) {
+      train_of[i] = -1;
+      if (specs[i].t_exp && specs[i].t_exp_int8 == (c->engine == 3 ? 0 : 1)) continue;   // expanded by the caller
       int k = 0;
       for (; k < n_trains; ++k)
         if (train_spec[k]->t == specs[i].t && train_spec[k]->nt == specs[i].nt && train_spec[k]->nt_dev == specs[i].nt_dev) break;
@@ -509,10 +510,6 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     b.ktrace = kt;
     const uint8_t* exp_image[kTcMaxTrains];
     for (int k = 0; k < n_trains; ++k) {
-      if (train_spec[k]->t_exp && train_spec[k]->t_exp_int8 == int8) {
-        exp_image[k] = train_spec[k]->t_exp;   // expanded by the caller (pipelined path: on the upload stream)
-        continue;
-      }
       exp_image[k] = c->d_train_exp[k];
       if (wide)
         VSF_CUDA(c, launch_expand_train64(train_spec[k]->t, train_spec[k]->nt, train_spec[k]->nt_dev,
@@ -528,7 +525,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     // contiguous ranges (see TcBatch).
     int qblocks = 0;
     for (int i = 0; i < b.num_problems; ++i) {
-      tb.t_exp[i] = exp_image[train_of[i]];
+      tb.t_exp[i] = train_of[i] < 0 ? specs[i].t_exp : exp_image[train_of[i]];   // (< 0: expanded by the caller)
       tb.qb_begin[i] = qblocks;
       qblocks += (specs[i].nq + unit_q - 1) / unit_q;
     }
@@ -555,23 +552,13 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       // so the two can share the look-back words
       fa.state = c->d_finish_ticket + 4 * (c->finish_parity & 1);
       fa.flags = c->d_finish_flags;
-      int phase = 0;
+      const int phase = 0;
       if (pose) {
-        if (!wide && pose->exp_src && pose->exp_nt > 0) {
-          tb.exp_src = static_cast<const uint32_t*>(pose->exp_src);
-          tb.exp_nt = pose->exp_nt;
-          tb.exp_out = pose->exp_out;
-        }
+        if (pose->em && !wide) tb.em = *pose->em;
         tb.early = pose->early;
         if (pose->partial) b.partial = pose->partial;
         if (pose->flags) fa.flags = pose->flags;
-        if (pose->ticket) fa.state = pose->ticket;
-        fa.nowait = pose->nowait;
-        if (pose->em && !wide) {
-          fa.em = *pose->em;
-          fa.em_int8 = int8;
-        }
-        phase = pose->phase;
+        if (pose->state) fa.state = pose->state;
       }
       int launched = 0;
       FinishArgs* fap = (c->engine_flags & 512) ? nullptr : &fa;
@@ -580,7 +567,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       else
         VSF_CUDA(c, launch_knn2_tc(b, tb, int8, max_nq, pdl, c->profile ? c->pev + 1 : nullptr, c->stream, fap, &launched, phase));
       c->launches += launched;
-      if (phase != 1 && fap && !b.exact_second && !(pose && pose->ticket)) c->finish_parity ^= 1;
+      if (fap && !b.exact_second && !(pose && pose->state)) c->finish_parity ^= 1;
     }
     c->pev_valid = c->profile != 0;
     return VSF_OK;
@@ -656,8 +643,6 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
     for (std::thread& t : c->workers) t.join();
   }
   std::free(c->h_keys);
-  for (uint2* p : c->grp_partial)
-    if (p && p != c->d_partial && p != c->d_partial2) cudaFree(p);
   for (uint8_t* p : c->grp_exp)
     if (p && p != c->d_train_exp[0] && p != c->d_train_exp[1]) cudaFree(p);
   if (c->grp_flags) cudaFree(c->grp_flags);
@@ -686,7 +671,6 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
       if (p) cudaFreeHost(p);
     if (f.d_matches) cudaFree(f.d_matches);
     if (f.d_train_exp) cudaFree(f.d_train_exp);
-    if (f.d_partial) cudaFree(f.d_partial);
     if (f.d_fm) cudaFree(f.d_fm);
     if (f.d_counts) cudaFree(f.d_counts);
     for (cudaEvent_t e : {f.ev_up, f.ev_chain, f.done, f.ev_sort})
@@ -1355,34 +1339,30 @@ static int flights_init(vsf_ctx* c) {
 
 extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_count : 0; }
 
-// Per-slot state of the finish kernels of a group of poses / frames: look-back words and launch
-// states (FinishArgs::state, epoch 1: the zeroed look-back words hold epoch 0), survivor lists of
-// the poses that do not write the ctx's own.  Allocated on first use.
+// State of the finish kernel of a batch that spans a group of poses / frames: look-back words
+// for kMaxProblems problems, two launch states used alternately (FinishArgs::state; epochs 1.. and
+// 2^40 + 1.. never meet, the zeroed look-back words hold epoch 0), survivor lists of the poses
+// that do not write the ctx's own.  Allocated on first use.
+static size_t group_flag_words(const vsf_ctx* c) { return size_t(kMaxProblems) * (size_t(c->rows_pad) / 32 + 4) + 8; }
 static int group_state_init(vsf_ctx* c) {
   if (c->grp_flags) return VSF_OK;
-  const size_t flag_words = c->qb_cap + 8;
+  const size_t flag_words = group_flag_words(c);
   const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
-  const size_t words = size_t(kMaxPoseGroup) * flag_words + 4 * kMaxPoseGroup;
-  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), words * sizeof(unsigned long long)));
-  VSF_CUDA(c, cudaMemset(c->grp_flags, 0, words * sizeof(unsigned long long)));
-  unsigned long long init[4 * kMaxPoseGroup];
-  for (int g = 0; g < kMaxPoseGroup; ++g) {
-    init[4 * g] = init[4 * g + 1] = init[4 * g + 3] = 0ull;
-    init[4 * g + 2] = 1ull;
-  }
-  VSF_CUDA(c, cudaMemcpy(c->grp_flags + size_t(kMaxPoseGroup) * flag_words, init, sizeof(init), cudaMemcpyHostToDevice));
+  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), (flag_words + 8) * sizeof(unsigned long long)));
+  VSF_CUDA(c, cudaMemset(c->grp_flags, 0, (flag_words + 8) * sizeof(unsigned long long)));
+  const unsigned long long init[8] = {0ull, 0ull, 1ull, 0ull, 0ull, 0ull, (1ull << 40) + 1ull, 0ull};
+  VSF_CUDA(c, cudaMemcpy(c->grp_flags + flag_words, init, sizeof(init), cudaMemcpyHostToDevice));
   VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
   VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
+  if (!c->d_partial2) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_partial2), c->partial_cap * sizeof(uint2)));
   return VSF_OK;
 }
 
 // Launch the kernels of the staged frames (vsf_window_submit stages one frame; ordinarily it is
 // flushed at once, vsf_window_run_sequence lets c->defer_group frames accumulate).  On the tensor
-// engine with 32-byte rows a group is launched like a group of poses of
-// vsf_window_match_block_device: the distance kernels back to back (each but the first starts
-// without waiting for its predecessor: their inputs were all uploaded and expanded before the
-// group started, their partial keys go to per-frame buffers), then the finish kernels side by
-// side, then the device sorts, one event for the whole group.
+// engine a group is launched like a group of poses of vsf_window_match_block_device: ONE batch of
+// all its frame pairs - one distance kernel, one finish kernel - whose problems write straight
+// into the frames' own buffers; then the device sorts, one event for the whole group.
 static int flush_flights(vsf_ctx* c) {
   const int m = c->flights_staged;
   if (m == 0) return VSF_OK;
@@ -1394,35 +1374,26 @@ static int flush_flights(vsf_ctx* c) {
   // the uploads (and expansions) of the whole group precede the last frame's event on the upload stream
   VSF_CUDA(c, cudaStreamWaitEvent(c->stream, fl[m - 1]->ev_up, 0));
   int rc = VSF_OK;
-  // grouped launch: every frame has work for the tensor engine's 32-byte kernels
+  // one batch for the group: every frame has work for the tensor engine
   bool grouped = m > 1 && (c->words == 8 || (c->words == 16 && c->engine != 3)) && c->engine != 1 &&
                  !(c->engine_flags & (8 | 512 | 1024)) && !c->profile;
   bool any_side_sort = false;
   for (int g = 0; g < m; ++g) {
     const vsf_ctx::Flight& f = *fl[g];
-    if (f.nf == 0 || f.n == 0 || f.max_cnt == 0) grouped = false;
-    else if (c->engine == 0 && double(f.nf) * double(f.max_cnt) * double(f.n) < c->tc_auto_min_cmp) grouped = false;   // (an upper bound of the batch's comparisons: frames with device-side row counts)
+    if (f.nf == 0 || f.n == 0 || f.max_cnt == 0 || !f.specs[0].t_exp || f.ratio != fl[0]->ratio) grouped = false;
     if (f.sort_mode != 1 && f.nf > 0 && !(c->engine_flags & 64)) any_side_sort = true;
   }
   if (grouped && c->engine == 0) {
-    // the automatic choice must come out as the tensor engine for every frame (run_knn decides on
-    // sum(nq) * nt); otherwise launch frame by frame
-    for (int g = 0; g < m && grouped; ++g) {
-      long long tq = 0;
+    // the automatic choice must come out as the tensor engine (run_knn decides on sum(nq) * max(nt))
+    long long tq = 0;
+    int mt = 0;
+    for (int g = 0; g < m; ++g) {
       for (const ProblemSpec& sp : fl[g]->specs) tq += sp.nq;
-      if (double(tq) * double(fl[g]->n) < c->tc_auto_min_cmp) grouped = false;
+      mt = std::max(mt, fl[g]->n);
     }
+    if (double(tq) * double(mt) < c->tc_auto_min_cmp) grouped = false;
   }
-  unsigned long long* tickets = nullptr;
-  size_t flag_words = 0;
-  if (grouped) {
-    flag_words = c->qb_cap + 8;
-    if ((rc = group_state_init(c))) return rc;
-    tickets = c->grp_flags + size_t(kMaxPoseGroup) * flag_words;
-    for (int g = 0; g < m; ++g)
-      if (!fl[g]->d_partial)
-        VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&fl[g]->d_partial), c->partial_cap * sizeof(uint2)));
-  }
+  if (grouped && (rc = group_state_init(c))) return rc;
   // ---- main stream: every resident past frame (query side) against the frame (train side); the
   // survivors go to the flight's own device buffer, the counts straight to mapped host memory.
   // A device sort (modes 0, 2) runs on its own stream while the main stream goes on with the next
@@ -1451,22 +1422,41 @@ static int flush_flights(vsf_ctx* c) {
     c->mir_dcounts = c->dm_region_counts;
     c->mir_hcounts = c->h_region_counts;
   };
-  for (int phase = grouped ? 1 : 0; phase <= (grouped ? 2 : 0) && !rc; ++phase) {
+  if (grouped) {
+    // chunks of at most kMaxProblems frame pairs; the first distance kernel follows the event
+    // wait, a later chunk's starts early (its inputs were complete before the group started, its
+    // partial keys go to the other buffer)
+    std::vector<ProblemSpec> specs;
+    int chunk = 0;
+    for (int g0 = 0; g0 < m && !rc;) {
+      specs.clear();
+      int g1 = g0;
+      while (g1 < m && int(specs.size()) + fl[g1]->nf <= kMaxProblems) {
+        vsf_ctx::Flight& f = *fl[g1];
+        for (int j = 0; j < f.nf; ++j) {
+          ProblemSpec sp = f.specs[j];
+          sp.out = f.d_matches + size_t(j) * c->rows_pad;
+          sp.out_count = f.d_counts + j;
+          sp.host_count = f.sort_mode == 1 ? f.dm_counts + j : nullptr;
+          specs.push_back(sp);
+        }
+        ++g1;
+      }
+      frame_state(*fl[g0]);   // (the sort reserve of the group's frames; the buffers come from the specs)
+      PoseLaunch pl;
+      pl.early = chunk > 0 ? 1 : 0;
+      pl.partial = (chunk & 1) ? c->d_partial2 : c->d_partial;
+      pl.flags = c->grp_flags;
+      pl.state = c->grp_flags + group_flag_words(c) + 4 * (chunk & 1);
+      rc = run_knn(c, specs, fl[g0]->ratio, false, false, &pl);
+      ++chunk;
+      g0 = g1;
+    }
+  } else {
     for (int g = 0; g < m && !rc; ++g) {
       vsf_ctx::Flight& f = *fl[g];
       frame_state(f);
-      if (grouped) {
-        PoseLaunch pl;
-        pl.phase = phase;
-        pl.early = (phase == 1 && g > 0) ? 1 : 0;
-        pl.partial = f.d_partial;
-        pl.flags = c->grp_flags + size_t(g) * flag_words;
-        pl.ticket = tickets + 4 * g;
-        pl.nowait = (phase == 2 && g > 0) ? 1 : 0;
-        rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1, false, &pl);
-      } else {
-        rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1);
-      }
+      rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1);
     }
   }
   // ---- device sort (stable, or the replay of the reference's std::sort) + cut; the kept counts
@@ -2122,140 +2112,105 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
   const size_t fb = size_t(n) * c->row_bytes;
   const uint8_t* base = static_cast<const uint8_t*>(d_seq);
   auto pose_frame = [&](int k) { return (first + k) % (n_poses - W) + W; };
-  // Tensor engine, 32-byte rows (engine flag 256: pose-by-pose launches, 1024: no early start;
-  // A/B timing).  A pose is two kernels, distance + finish, and the poses are launched in groups
-  // of G (ctx pose_group, VSF_POSE_GROUP): first the G distance kernels - each starts as soon as
-  // its predecessor's CTAs leave the SMs, it depends on nothing that one writes - then the G
-  // finish kernels, which run side by side; the first of them also expands the NEXT group's
-  // current frames.  The per-launch latencies between a distance kernel and the finish kernel that
-  // needs all of its CTAs' partial keys are paid once per group instead of once per pose.
-  // Per-slot buffers: partial keys and +-1 images 2 G deep (a group writes while the previous
-  // one is read), look-back words / ticket counters and survivor lists G deep; the last pose of
-  // the call writes the ctx's own lists (vsf_fetch_window).  With G = 1 the distance kernel
-  // expands the next pose's frame itself.
-  const bool tensor = c->engine >= 2 || (c->engine == 0 && double(W) * double(n) * double(n) >= c->tc_auto_min_cmp);
+  // Tensor engine (engine flag 256: pose-by-pose launches, 1024: no early start; A/B timing).
+  // The poses are launched in groups of G (ctx pose_group, VSF_POSE_GROUP; G * window <=
+  // kMaxProblems), each group as ONE batch of all its frame pairs: one distance kernel - its
+  // persistent CTAs walk the work slots of G poses without a kernel boundary in between - and one
+  // finish kernel.  The distance kernel also expands the NEXT group's current frames (each CTA
+  // its share while its epilogue warps wait for the first accumulators; 64-byte rows: a kernel
+  // of its own behind the distance kernel), so the next group's distance kernel depends on
+  // nothing its stream predecessor - this group's finish kernel - writes and starts as that
+  // one's CTAs leave the SMs (TcBatch::early).  Buffers: +-1 images 2 G deep, partial keys
+  // 2 deep (a group writes while the previous one is read), two finish-kernel launch states;
+  // the last pose of the call writes the ctx's own lists (vsf_fetch_window), the others scratch
+  // lists.  With G = 1 a pose is launched alone and expands the next pose's frame.
   const bool wide = c->words == 16;
-  bool ahead = tensor && (c->words == 8 || (wide && c->engine != 3)) && n > 0 && count > 0 && !(c->engine_flags & (256 | 512));
-  if (wide && (c->profile || c->pose_group < 2)) ahead = false;   // 64-byte rows: groups only (no expansion inside the distance kernel)
+  const bool tensor = c->engine >= 2 || (c->engine == 0 && double(W) * double(n) * double(n) >= c->tc_auto_min_cmp);
+  const bool ahead = tensor && (c->words == 8 || (wide && c->engine != 3)) && n > 0 && count > 0 &&
+                     !(c->engine_flags & (256 | 512)) && !c->profile;
   const int int8 = c->engine == 3 ? 0 : 1;
   const int pdl = (c->engine_flags & 8) ? 0 : 1;
   const bool early_ok = !(c->engine_flags & (8 | 1024));
-  const int G = (ahead && !c->profile) ? c->pose_group : 1;   // (per-kernel event timing: one pose at a time)
-  std::vector<ProblemSpec> specs(W);
-  auto fill_specs = [&](int k, const uint8_t* image) {
+  const int G = ahead ? std::max(1, std::min(c->pose_group, kMaxProblems / W)) : 1;
+  std::vector<ProblemSpec> specs;
+  auto add_pose = [&](int k, const uint8_t* image, int slot) {
     const long long cur = pose_frame(k);
+    const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
     for (int j = 0; j < W; ++j) {
-      specs[j] = ProblemSpec{base + size_t(cur - W + j) * fb, n, nullptr, base + size_t(cur) * fb, n, nullptr, j};
+      ProblemSpec sp{base + size_t(cur - W + j) * fb, n, nullptr, base + size_t(cur) * fb, n, nullptr, j};
       if (image) {
-        specs[j].t_exp = image;
-        specs[j].t_exp_int8 = int8;
+        sp.t_exp = image;
+        sp.t_exp_int8 = int8;
       }
+      if (slot > 0) {   // scratch lists (slot 0 = the ctx's own regions)
+        sp.out = c->grp_matches + size_t(slot - 1) * rows_cap + size_t(j) * c->rows_pad;
+        sp.out_count = c->grp_counts + size_t(slot - 1) * kMaxProblems + j;
+      }
+      specs.push_back(sp);
     }
   };
-  if (ahead && G > 1) {
-    // ---- per-slot buffers
-    const size_t image_bytes = size_t(round_up(c->max_features, kTcTileRows)) * size_t(c->row_bytes) * 8;
-    const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
-    const size_t flag_words = c->qb_cap + 8;
-    for (int i = 0; i < 2 * G; ++i) {
-      if (!c->grp_partial[i]) {
-        if (i == 0) c->grp_partial[i] = c->d_partial;
-        else VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_partial[i]), c->partial_cap * sizeof(uint2)));
-      }
-      if (!c->grp_exp[i]) {
-        if (i < kTcMaxTrains) c->grp_exp[i] = c->d_train_exp[i];
-        else VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_exp[i]), image_bytes));
-      }
-    }
-    {
-      const int rcs = group_state_init(c);
-      if (rcs) return rcs;
-    }
-    unsigned long long* tickets = c->grp_flags + size_t(kMaxPoseGroup) * flag_words;
-    auto group_images = [&](int k0, int parity) {   // frames of poses k0 .. k0 + G - 1
-      ExpandMulti em;
-      std::memset(&em, 0, sizeof(em));
-      em.nt = n;
-      for (int g = 0; g < G && k0 + g < count; ++g) {
-        em.src[g] = reinterpret_cast<const uint32_t*>(base + size_t(pose_frame(k0 + g)) * fb);
-        em.out[g] = c->grp_exp[parity * G + g];
-        em.frames = g + 1;
-      }
-      return em;
-    };
-    auto expand_images = [&](const ExpandMulti& em) -> int {
-      if (em.frames == 0) return VSF_OK;
-      if (wide) VSF_CUDA(c, launch_expand_train64_multi(em, pdl, c->stream));
-      else VSF_CUDA(c, launch_expand_train_multi(em, int8, pdl, c->stream));
-      ++c->launches;
-      return VSF_OK;
-    };
-    {
-      const int rc0 = expand_images(group_images(0, 0));
-      if (rc0) return rc0;
-    }
-    int rc = VSF_OK;
-    vsf_dmatch* const own_matches = c->match_base;
-    int* const own_counts = c->count_base;
-    for (int k0 = 0, grp = 0; k0 < count; k0 += G, ++grp) {
-      const int parity = grp & 1;
-      const int m = std::min(G, count - k0);
-      // the next group's images are made by this group's first finish kernel (64-byte rows: by
-      // a kernel of their own between the group's distance and finish kernels)
-      const ExpandMulti next_em = group_images(k0 + G, parity ^ 1);
-      for (int phase = 1; phase <= 2 && !rc; ++phase) {
-        for (int g = 0; g < m && !rc; ++g) {
-          const int k = k0 + g;
-          fill_specs(k, c->grp_exp[parity * G + g]);
-          PoseLaunch pl;
-          pl.phase = phase;
-          // the first distance kernel of a group waits for its predecessor (the expansion, or the
-          // previous group's last finish kernel, whose completion implies that of the first,
-          // which made this group's images); the others start at once
-          pl.early = (phase == 1 && early_ok && g > 0) ? 1 : 0;
-          pl.partial = c->grp_partial[parity * G + g];
-          pl.flags = c->grp_flags + size_t(g) * flag_words;
-          pl.ticket = tickets + 4 * g;
-          pl.nowait = (phase == 2 && g > 0 && early_ok) ? 1 : 0;
-          if (phase == 2 && g == 0 && next_em.frames > 0 && !wide) pl.em = &next_em;
-          // survivor lists: slot 0 = the ctx's own (the last pose of the call ends up there)
-          const int slot = (count - 1 - k) % G;
-          c->match_base = slot == 0 ? own_matches : c->grp_matches + size_t(slot - 1) * rows_cap;
-          c->count_base = slot == 0 ? own_counts : c->grp_counts + size_t(slot - 1) * kMaxProblems;
-          rc = run_knn(c, specs, ratio, false, false, &pl);
-        }
-        if (phase == 1 && wide && !rc) rc = expand_images(next_em);
-      }
-      c->match_base = own_matches;
-      c->count_base = own_counts;
+  if (!ahead) {
+    for (int k = 0; k < count; ++k) {
+      specs.clear();
+      add_pose(k, nullptr, 0);
+      const int rc = run_knn(c, specs, ratio);
       if (rc) return rc;
     }
     c->last_n_frames = W;
     return VSF_OK;
   }
-  if (ahead) {
-    if (!c->d_partial2) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_partial2), c->partial_cap * sizeof(uint2)));
-    VSF_CUDA(c, launch_expand_train(base + size_t(pose_frame(0)) * fb, n, nullptr, c->d_train_exp[0], int8, pdl,
-                                    c->stream, nullptr));
-    ++c->launches;
+  {
+    const int rcs = group_state_init(c);
+    if (rcs) return rcs;
   }
-  for (int k = 0; k < count; ++k) {
-    fill_specs(k, ahead ? c->d_train_exp[k & 1] : nullptr);
-    int rc;
-    if (ahead) {
-      PoseLaunch pl;
-      if (k + 1 < count) {
-        pl.exp_src = base + size_t(pose_frame(k + 1)) * fb;
-        pl.exp_nt = n;
-        pl.exp_out = c->d_train_exp[(k + 1) & 1];
-      }
-      pl.early = (k > 0 && early_ok) ? 1 : 0;
-      pl.partial = (k & 1) ? c->d_partial2 : c->d_partial;
-      rc = run_knn(c, specs, ratio, false, false, &pl);
-    } else {
-      rc = run_knn(c, specs, ratio);
+  const size_t image_bytes = size_t(round_up(c->max_features, kTcTileRows)) * size_t(c->row_bytes) * 8;
+  for (int i = 0; i < 2 * G; ++i)
+    if (!c->grp_exp[i]) {
+      if (i < kTcMaxTrains) c->grp_exp[i] = c->d_train_exp[i];
+      else VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_exp[i]), image_bytes));
     }
+  auto group_images = [&](int k0, int parity) {   // frames of poses k0 .. k0 + G - 1
+    ExpandMulti em;
+    std::memset(&em, 0, sizeof(em));
+    em.nt = n;
+    for (int g = 0; g < G && k0 + g < count; ++g) {
+      em.src[g] = reinterpret_cast<const uint32_t*>(base + size_t(pose_frame(k0 + g)) * fb);
+      em.out[g] = c->grp_exp[parity * G + g];
+      em.frames = g + 1;
+    }
+    return em;
+  };
+  auto expand_images = [&](const ExpandMulti& em) -> int {
+    if (em.frames == 0) return VSF_OK;
+    if (wide) VSF_CUDA(c, launch_expand_train64_multi(em, pdl, c->stream));
+    else VSF_CUDA(c, launch_expand_train_multi(em, int8, pdl, c->stream));
+    ++c->launches;
+    return VSF_OK;
+  };
+  int rc = expand_images(group_images(0, 0));
+  if (rc) return rc;
+  unsigned long long* const states = c->grp_flags + group_flag_words(c);
+  for (int k0 = 0, grp = 0; k0 < count; k0 += G, ++grp) {
+    const int parity = grp & 1;
+    const int m = std::min(G, count - k0);
+    specs.clear();
+    for (int g = 0; g < m; ++g) add_pose(k0 + g, c->grp_exp[parity * G + g], (count - 1 - (k0 + g)) % G);
+    const ExpandMulti next_em = group_images(k0 + G, parity ^ 1);
+    PoseLaunch pl;
+    // (the very first distance kernel of the call follows the expansion it needs; 64-byte rows:
+    // every one follows the expansion kernel of its images)
+    pl.early = (grp > 0 && early_ok && !wide) ? 1 : 0;
+    pl.partial = parity ? c->d_partial2 : c->d_partial;
+    pl.flags = c->grp_flags;
+    pl.state = states + 4 * parity;
+    if (!wide && next_em.frames > 0) pl.em = &next_em;
+    if (wide && grp > 0) {
+      // 64-byte rows: the images of this group are expanded by a kernel in front of its distance
+      // kernel (it overlaps the previous group's finish kernel only through its launch latency)
+    }
+    rc = run_knn(c, specs, ratio, false, false, &pl);
     if (rc) return rc;
+    if (wide && (rc = expand_images(next_em))) return rc;
   }
   c->last_n_frames = W;
   return VSF_OK;

@@ -40,6 +40,8 @@ struct KnnProblem {
   int row0;                // first row of this problem in knn_out / partial
   int qb0;                 // first slot of this problem in the per-query-block counters
   int region;              // index of `matches` among the ctx's match regions (host mirror slot)
+  int* host_count;         // when non-null: the survivor count is also stored here (mapped host memory) instead
+                           //   of KnnBatch::host_counts[region] (batches that span several frames' buffers)
 };
 
 struct KnnBatch {
@@ -78,6 +80,15 @@ constexpr int kTcABytes = kTcQ * kTcRowBytes;
 constexpr int kTcBBytes = kTcTileRows * kTcRowBytes;
 constexpr int kTcMaxTrains = 2;      // distinct train frames per batch that can be expanded
 
+// Several frames expanded to +-1 images by one launch (a group of poses).
+constexpr int kMaxPoseGroup = 8;
+struct ExpandMulti {
+  const uint32_t* src[kMaxPoseGroup];
+  uint8_t* out[kMaxPoseGroup];
+  int frames;
+  int nt;                            // rows of every frame
+};
+
 // The work of a launch is the flattened list of (256-query block, piece) slots, query block
 // major, where a piece is tiles_per_piece consecutive train tiles and a block has `pieces` of
 // them: T = blocks * pieces slots.  CTA i of the G CTAs of the persistent kernel owns the
@@ -102,28 +113,18 @@ struct TcBatch {
   int unit_q;                          // 64-byte engine: queries per block (128: one CTA per unit, 256: a CTA pair per unit)
   int flags;                           // bring-up knobs (timing experiments; results invalid): 2 = skip the bucket reduction, 4 = skip the TMEM loads
   long long* trace;                    // flag 16 (builds with -DVSF_TC_TRACE): per-CTA timeline, kTcTraceSlots values per CTA
-  // A stream of poses (vsf_window_match_block_device).  exp_src != nullptr: the distance kernel
-  // also expands the NEXT launch's train frame (packed rows exp_src, exp_nt of them) into
-  // exp_out, each CTA its share, while its epilogue warps wait for the first accumulators.
+  // A stream of poses (vsf_window_match_block_device).  em.frames > 0: the distance kernel
+  // also expands the train frames of the NEXT launch (packed rows em.src[f], em.nt of them each)
+  // into em.out[f], each CTA its share, while its epilogue warps wait for the first accumulators.
   // early != 0: everything this launch reads was complete before its stream predecessor (the
-  // previous pose's finish kernel) let it launch, and its partial keys go to another buffer than
+  // previous launch's finish kernel) let it launch, and its partial keys go to another buffer than
   // the one that kernel reads: it starts without waiting for the predecessor and only waits for
   // it just before it exits (so that "complete" still implies "everything before it complete").
-  const uint32_t* exp_src;
-  uint8_t* exp_out;
-  int exp_nt;
+  ExpandMulti em;
   int early;
 };
 constexpr int kTcTraceSlots = 16;
 
-// Several frames expanded to +-1 images by one launch (a group of poses).
-constexpr int kMaxPoseGroup = 8;
-struct ExpandMulti {
-  const uint32_t* src[kMaxPoseGroup];
-  uint8_t* out[kMaxPoseGroup];
-  int frames;
-  int nt;                            // rows of every frame
-};
 
 // Arguments of knn2_tc_finish_kernel (refine + ordered compaction in one kernel, see there).
 struct FinishArgs {
@@ -140,10 +141,6 @@ struct FinishArgs {
   // passed its own wait, so the kernel starts at once and only waits for the predecessor just
   // before it exits ("complete" still implies "everything before it complete").
   int nowait;
-  // A group of poses: the first finish kernel of the group also expands the NEXT group's train
-  // frames (em.frames > 0), each CTA its share, before it waits for the distance kernels.
-  ExpandMulti em;
-  int em_int8;
 };
 
 
