@@ -73,7 +73,8 @@ def main():
         ctx._check(ctx._L.vsf_debug_kernel_trace(ctx._h, buf.ctypes.data, 256, C.byref(got)))
         tr = buf[: got.value].astype(np.float64)
         recs = []
-        lo = 32 if group > 1 and not (flags & 512) else 16
+        # (a group of poses is one record: 40 poses = 10 records at group 4)
+        lo = 3 if group > 1 and not (flags & 512) else 16
         t0 = None
         for p in range(lo, min(lo + 16, got.value)):
             r = {}

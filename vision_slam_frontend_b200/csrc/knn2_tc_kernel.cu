@@ -871,6 +871,10 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   static_assert(WORDS == 8 || WORDS == 16, "32- or 64-byte rows");
   constexpr int kRecs = WORDS / 8;             // 16-byte partial records per segment
   __shared__ unsigned s_woff[kFinThreads / 32];
+  __shared__ unsigned s_ccnt[kFinThreads / 32];   // candidates per warp
+  __shared__ int2 s_keys[kFinQ];                  // (best, second-best) bucket keys of the block's candidates
+  __shared__ int2 s_out[kFinQ];                   // (trainIdx or -1, distance) of the block's candidates
+  __shared__ unsigned char s_list[kFinQ];         // the candidates' indices in the block, ascending
   __shared__ unsigned s_base;
   __shared__ int s_where[3];
   __shared__ unsigned long long s_epoch;
@@ -895,17 +899,13 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     const int problem = s_where[0], qb = s_where[1];
     const unsigned long long epoch = s_epoch;
     const KnnProblem& P = batch.p[problem];
-    // The descriptors and row counts were written before the launch sequence began (see
-    // knn2_tc_kernel): the query words are fetched while the distance kernel is still finishing.
+    // (the descriptors and row counts were written before the launch sequence began, see
+    // knn2_tc_kernel)
     int nq = P.nq, nt = P.nt;
     if (P.nq_dev) nq = min(nq, *P.nq_dev);
     if (P.nt_dev) nt = min(nt, *P.nt_dev);
     const int q0 = qb * kFinQ;
     const int q = q0 + tid / kFinLanes;
-    // lane `part` of a query works on 16-byte half `part & 1` of every second row of the bucket
-    // (64-byte rows: on quarter `part` of every row)
-    uint4 qh = make_uint4(0u, 0u, 0u, 0u);
-    if (q < nq) qh = __ldg(reinterpret_cast<const uint4*>(P.q + size_t(q) * WORDS) + (WORDS == 8 ? (part & 1) : part));
     if (!fa.nowait) {
       pdl_wait();                              // the partial bucket keys are complete
       if (tid == 0) ktrace_start(batch.ktrace, 4);
@@ -952,55 +952,106 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       key = b1;
       key2 = b2;
     }
-    // ---- exact distances to the rows of the best bucket.  The bucket is 2 * kTcBucket 16-byte
-    // pieces; in step j the query's four lanes read pieces 4j .. 4j+3 (64 contiguous bytes = rows
-    // 2j, 2j+1), a lane and its neighbour add up the two halves of a row.  (64-byte rows: 4 *
-    // kTcBucket pieces, a step is one row, the four lanes add up its quarters.)
-    uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
-    {
-      const bool have = key != kTcKeySentinel;
-      const int row_base = have ? (kBucketIdMask - (key & kBucketIdMask)) * kTcBucket : 0;
-      const uint4* pieces = reinterpret_cast<const uint4*>(P.t + size_t(row_base) * WORDS) + part;
-      const int rsub = WORDS == 8 ? (part >> 1) : 0;
-      constexpr int kSteps = WORDS == 8 ? kTcBucket / 2 : kTcBucket;
-      constexpr int kRowsPerStep = WORDS == 8 ? 2 : 1;
-#pragma unroll
-      for (int j0 = 0; j0 < kSteps; j0 += 4) {
-        uint4 t[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          t[u] = (have && row_base + kRowsPerStep * (j0 + u) + rsub < nt) ? __ldg(pieces + 4 * (j0 + u)) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint32_t d = __popc(t[u].x ^ qh.x) + __popc(t[u].y ^ qh.y) + __popc(t[u].z ^ qh.z) + __popc(t[u].w ^ qh.w);
-          d += __shfl_xor_sync(0xffffffffu, d, 1);
-          if (WORDS == 16) d += __shfl_xor_sync(0xffffffffu, d, 2);
-          const int row = row_base + kRowsPerStep * (j0 + u) + rsub;
-          if (have && row < nt) top2_insert(k1, k2, (d << kIdxBits) + uint32_t(row));
-        }
+    // ---- early verdict.  The best bucket's maximum dot is the query's exact best distance, the
+    // second-best bucket's the exact smallest distance d2b outside the best bucket; the second
+    // neighbour's distance is min(d2b, the best bucket's second smallest) <= d2b, so a query with
+    // !(d0 < ratio * d2b) fails the ratio test (src/slam_frontend.cc:529-536) whatever the rows of
+    // its best bucket are (ratio >= 0: the double product is monotone in the distance).  Only
+    // the other queries - the candidates - need their best bucket's rows; they are re-packed
+    // onto consecutive lane groups, so whole warps skip the rescan.
+    bool cand = false;
+    if (q < nq && key != kTcKeySentinel) {
+      cand = true;
+      if (key2 != kTcKeySentinel && batch.ratio >= 0.0) {
+        const int d0b = (32 * WORDS - (key >> kBucketIdBits)) >> 1;
+        const int d2b = (32 * WORDS - (key2 >> kBucketIdBits)) >> 1;
+        cand = double(d0b) < batch.ratio * double(d2b);
       }
     }
-    if (WORDS == 8) {
-      // the two lane pairs of a query saw the even / the odd rows
-      const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, 2), o2 = __shfl_xor_sync(0xffffffffu, k2, 2);
-      top2_merge(k1, k2, o1, o2);
+    const int lq = tid / kFinLanes;                  // the query's index in the block
+    const unsigned cbal = __ballot_sync(0xffffffffu, cand && part == 0);
+    if (lane == 0) s_ccnt[warp] = __popc(cbal);
+    if (cand && part == 0) s_keys[lq] = make_int2(key, key2);
+    __syncthreads();
+    unsigned cbase = 0, ncand = 0;
+#pragma unroll
+    for (int w = 0; w < kFinThreads / 32; ++w) {
+      if (w < warp) cbase += s_ccnt[w];
+      ncand += s_ccnt[w];
     }
-    if (key2 != kTcKeySentinel) {
-      // the second-best bucket's best distance is exact (its maximum dot is); its first row stands
-      // in as the index, which nobody reads on this path
-      const int dot = key2 >> kBucketIdBits;
-      top2_insert(k1, k2, (uint32_t((32 * WORDS - dot) >> 1) << kIdxBits) +
-                              uint32_t((kBucketIdMask - (key2 & kBucketIdMask)) * kTcBucket));
+    if (cand && part == 0) s_list[cbase + __popc(cbal & ((1u << lane) - 1u))] = static_cast<unsigned char>(lq);
+    __syncthreads();
+    // ---- exact distances to the rows of a candidate's best bucket.  The bucket is 2 * kTcBucket
+    // 16-byte pieces; in step j the four lanes of a lane group read pieces 4j .. 4j+3 (64
+    // contiguous bytes = rows 2j, 2j+1), a lane and its neighbour add up the two halves of a row.
+    // (64-byte rows: 4 * kTcBucket pieces, a step is one row, the four lanes add up its quarters.)
+    if (unsigned(warp * (32 / kFinLanes)) < ncand) {     // warp-uniform
+      const bool have = unsigned(lq) < ncand;           // lane group lq works on candidate number lq
+      const int cq = have ? int(s_list[lq]) : 0;
+      int ckey = kTcKeySentinel, ckey2 = kTcKeySentinel;
+      // lane `part` works on 16-byte half `part & 1` of every second row of the bucket (64-byte
+      // rows: on quarter `part` of every row)
+      uint4 qh = make_uint4(0u, 0u, 0u, 0u);
+      if (have) {
+        const int2 kk = s_keys[cq];
+        ckey = kk.x;
+        ckey2 = kk.y;
+        qh = __ldg(reinterpret_cast<const uint4*>(P.q + size_t(q0 + cq) * WORDS) + (WORDS == 8 ? (part & 1) : part));
+      }
+      uint32_t k1 = kKeySentinel, k2 = kKeySentinel;
+      {
+        const int row_base = have ? (kBucketIdMask - (ckey & kBucketIdMask)) * kTcBucket : 0;
+        const uint4* pieces = reinterpret_cast<const uint4*>(P.t + size_t(row_base) * WORDS) + part;
+        const int rsub = WORDS == 8 ? (part >> 1) : 0;
+        constexpr int kSteps = WORDS == 8 ? kTcBucket / 2 : kTcBucket;
+        constexpr int kRowsPerStep = WORDS == 8 ? 2 : 1;
+#pragma unroll
+        for (int j0 = 0; j0 < kSteps; j0 += 4) {
+          uint4 t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            t[u] = (have && row_base + kRowsPerStep * (j0 + u) + rsub < nt) ? __ldg(pieces + 4 * (j0 + u)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t d = __popc(t[u].x ^ qh.x) + __popc(t[u].y ^ qh.y) + __popc(t[u].z ^ qh.z) + __popc(t[u].w ^ qh.w);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            if (WORDS == 16) d += __shfl_xor_sync(0xffffffffu, d, 2);
+            const int row = row_base + kRowsPerStep * (j0 + u) + rsub;
+            if (have && row < nt) top2_insert(k1, k2, (d << kIdxBits) + uint32_t(row));
+          }
+        }
+      }
+      if (WORDS == 8) {
+        // the two lane pairs of a group saw the even / the odd rows
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, 2), o2 = __shfl_xor_sync(0xffffffffu, k2, 2);
+        top2_merge(k1, k2, o1, o2);
+      }
+      if (ckey2 != kTcKeySentinel) {
+        // the second-best bucket's best distance is exact (its maximum dot is); its first row stands
+        // in as the index, which nobody reads on this path
+        const int dot = ckey2 >> kBucketIdBits;
+        top2_insert(k1, k2, (uint32_t((32 * WORDS - dot) >> 1) << kIdxBits) +
+                                uint32_t((kBucketIdMask - (ckey2 & kBucketIdMask)) * kTcBucket));
+      }
+      // ---- ratio test (src/slam_frontend.cc:529-536), one lane per candidate
+      if (have && part == 0) {
+        const int ci0 = (k1 == kKeySentinel) ? -1 : int(k1 & kIdxMask);
+        const int cd0 = (k1 == kKeySentinel) ? -1 : int(k1 >> kIdxBits);
+        const int i1 = (k2 == kKeySentinel) ? -1 : int(k2 & kIdxMask);
+        const int d1 = (k2 == kKeySentinel) ? -1 : int(k2 >> kIdxBits);
+        const bool ok = (i1 >= 0) && (double(cd0) < batch.ratio * double(d1));
+        s_out[cq] = make_int2(ok ? ci0 : -1, cd0);
+      }
     }
-    // ---- ratio test (src/slam_frontend.cc:529-536), one lane per query
+    __syncthreads();
+    // back to one lane group per query of the block, in query order
     bool pass = false;
     int i0 = -1, d0 = -1;
-    if (q < nq && part == 0) {
-      i0 = (k1 == kKeySentinel) ? -1 : int(k1 & kIdxMask);
-      d0 = (k1 == kKeySentinel) ? -1 : int(k1 >> kIdxBits);
-      const int i1 = (k2 == kKeySentinel) ? -1 : int(k2 & kIdxMask);
-      const int d1 = (k2 == kKeySentinel) ? -1 : int(k2 >> kIdxBits);
-      pass = (i1 >= 0) && (double(d0) < batch.ratio * double(d1));
+    if (cand && part == 0) {
+      const int2 r = s_out[lq];
+      pass = r.x >= 0;
+      i0 = r.x;
+      d0 = r.y;
     }
     // ---- publish this block's survivor count, fetch the ones before it
     const unsigned bal = __ballot_sync(0xffffffffu, pass);
