@@ -824,30 +824,39 @@ knn2_compact_kernel(const __grid_constant__ KnnBatch batch) {
 
 // ---------------------------------------------------------------------------------------------
 // Refine + ordered compaction in one kernel (every entry point that does not need the second
-// neighbour's index).  Four lanes per query, 32 queries per 128-thread CTA, no shared-memory
-// staging: step by step the four lanes of a query read 64 contiguous bytes (two rows) of its
-// best bucket, neighbouring lanes add up the two halves of a row's exact Hamming distance, and
-// one shuffle step merges the packed (distance, trainIdx) top-2 keys of the even and the odd
-// rows (lowest train index winning ties, as everywhere).  Short dependency chains, 12 CTAs per SM:
-// the whole launch is resident at once, and a CTA is small enough to sit beside a CTA of
-// knn2_tc_kernel.
+// neighbour's index).  A CTA owns a block of 256 consecutive queries of one problem:
+//   1. one lane per query merges the query's partial bucket keys and gives the early verdict:
+//      the best bucket's maximum dot is the exact best distance d0, the second-best bucket's the
+//      exact smallest distance d2b outside the best bucket, and the second neighbour's distance
+//      is <= d2b, so !(d0 < ratio * d2b) already fails the ratio test;
+//   2. the other queries - the candidates - are re-packed onto consecutive groups of four lanes
+//      (64 groups per pass): step by step the four lanes read 64 contiguous bytes (two rows) of
+//      the candidate's best bucket, neighbouring lanes add up the two halves of a row's exact
+//      Hamming distance, and one shuffle step merges the packed (distance, trainIdx) top-2 keys
+//      of the even and the odd rows (lowest train index winning ties, as everywhere); whole
+//      warps skip the pass when the candidates run out;
+//   3. back in query order the survivors are counted and stored in ascending queryIdx order.
 // The compaction needs the survivor counts of the query blocks before this one: each CTA
-// publishes its count as (epoch << 8 | count) with a release store and reads its predecessors'
-// with acquire loads ("decoupled look-back": the blocks of a problem are refined side by side,
-// so the wait is short).  A CTA only ever waits for CTAs with a smaller logical index, and the
-// logical index is handed out by an atomic ticket in the order the CTAs start, so every CTA
-// that is waited for is already running: no deadlock whatever order the hardware dispatches
-// the grid in.  The look-back words carry the launch's epoch in their upper bits (64-bit words,
-// the epoch only grows) and are never reset; the epoch and the ticket counter live in device
-// memory (FinishArgs::state) and are advanced / reset by the last CTA of a launch to finish.
-constexpr int kFinLanes = 4;                          // lanes per query
+// publishes its count as (epoch << 16 | count) and reads its predecessors' ("decoupled
+// look-back": the blocks of a problem are refined side by side, so the wait is short).  A CTA
+// only ever waits for CTAs with a smaller logical index, and the logical index is handed out by
+// an atomic ticket in the order the CTAs start, so every CTA that is waited for is already
+// running: no deadlock whatever order the hardware dispatches the grid in.  The look-back words
+// carry the launch's epoch in their upper bits (64-bit words, the epoch only grows) and are
+// never reset; the epoch and the ticket counter live in device memory (FinishArgs::state) and
+// are advanced / reset by the last CTA of a launch to finish.
+constexpr int kFinLanes = 4;                          // lanes per candidate in the rescan
 #ifndef VSF_FIN_THREADS
 #define VSF_FIN_THREADS 256
 #endif
 constexpr int kFinThreads = VSF_FIN_THREADS;
-constexpr int kFinQ = kFinThreads / kFinLanes;        // queries per CTA (= one survivor counter)
+constexpr int kFinGroups = kFinThreads / kFinLanes;   // candidates per rescan pass
+constexpr int kFinCountBits = 16;
 static_assert(kFinLanes == 4 && kTcBucket % 8 == 0, "knn2_tc_finish_kernel: 4 lanes x 4 steps of 2 rows");
-static_assert(kFinQ % 32 == 0 && kFinQ <= 128, "FinishArgs::flags is indexed in 32-query units (KnnProblem::qb0); the count has 8 bits");
+// Queries per CTA (QPB, = one survivor counter): 256 keeps the most queries in flight per SM and
+// is what a batch that fills the machine wants (a group of poses); a small batch is a chain of
+// dependent L2 round trips on a few CTAs, which 64 queries per CTA - one rescan pass, four times
+// the CTAs - keeps short.  The first QPB lanes of the CTA do step 1.
 
 // The look-back words carry their payload themselves (epoch | count): relaxed accesses at GPU
 // scope are enough, and an acquire load in the polling loop would invalidate the SM's L1 on
@@ -864,11 +873,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 // WORDS = 8: 32-byte rows (knn2_tc_kernel's partial keys: one 16-byte record per segment), 16:
 // 64-byte rows (knn2_tc64_kernel.cu: two records per segment; a step reads one row, 16 bytes
 // per lane, and the four lanes add up their quarters).
-template <int WORDS>
+template <int WORDS, int QPB>
 __global__ void __launch_bounds__(kFinThreads, 1536 / kFinThreads)
 knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ TcBatch tc,
                       const __grid_constant__ FinishArgs fa) {
   static_assert(WORDS == 8 || WORDS == 16, "32- or 64-byte rows");
+  static_assert(QPB % 32 == 0 && QPB <= kFinThreads && QPB <= 256 && QPB < (1 << kFinCountBits),
+                "FinishArgs::flags is indexed in 32-query units (KnnProblem::qb0); candidate indices are bytes");
+  constexpr int kFinQ = QPB;
   constexpr int kRecs = WORDS / 8;             // 16-byte partial records per segment
   __shared__ unsigned s_woff[kFinThreads / 32];
   __shared__ unsigned s_ccnt[kFinThreads / 32];   // candidates per warp
@@ -876,7 +888,7 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   __shared__ int2 s_out[kFinQ];                   // (trainIdx or -1, distance) of the block's candidates
   __shared__ unsigned char s_list[kFinQ];         // the candidates' indices in the block, ascending
   __shared__ unsigned s_base;
-  __shared__ int s_where[3];
+  __shared__ int s_where[4];
   __shared__ unsigned long long s_epoch;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -892,8 +904,12 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       const int pr = id / fa.nqb, b = id - pr * fa.nqb;
       s_where[0] = pr;
       s_where[1] = b;
-      // (the queries of a block are in one query block of the distance kernel)
-      s_where[2] = tc_block_segments(tc, tc.qb_begin[pr] + (b * kFinQ) / (WORDS == 8 ? kTcQ : tc.unit_q));
+      // segments per query of the distance kernel's query block(s) this block lies in (64-byte
+      // rows, one CTA per unit: two 128-query blocks)
+      const int uq = WORDS == 8 ? kTcQ : tc.unit_q;
+      const int gqb = tc.qb_begin[pr] + (b * kFinQ) / uq;
+      s_where[2] = tc_block_segments(tc, gqb);
+      s_where[3] = (uq < kFinQ && gqb + 1 < tc.qb_begin[pr + 1]) ? tc_block_segments(tc, gqb + 1) : s_where[2];
     }
     __syncthreads();
     const int problem = s_where[0], qb = s_where[1];
@@ -905,7 +921,7 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     if (P.nq_dev) nq = min(nq, *P.nq_dev);
     if (P.nt_dev) nt = min(nt, *P.nt_dev);
     const int q0 = qb * kFinQ;
-    const int q = q0 + tid / kFinLanes;
+    const int q = q0 + tid;
     if (!fa.nowait) {
       pdl_wait();                              // the partial bucket keys are complete
       if (tid == 0) ktrace_start(batch.ktrace, 4);
@@ -922,13 +938,13 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     if (q0 >= nq) break;
     const int nqb = (nq + kFinQ - 1) / kFinQ;
 
-    // ---- merge the query's partial bucket keys (the four lanes of a query read the same words)
-    int key = kTcKeySentinel, key2 = kTcKeySentinel;
-    if (q < nq) {
+    // ---- 1. merge the query's partial bucket keys, early verdict (one lane per query)
+    bool cand = false;
+    if (tid < kFinQ && q < nq) {
       int b1 = kTcKeySentinel, b2 = kTcKeySentinel;
       // the query block's tile slots were shared out to consecutive CTAs, one partial segment each
-      const int nseg = s_where[2] * kRecs;
-      static_assert(kTcColSplit == 2 && kTcQ % kFinQ == 0 && 128 % kFinQ == 0, "one uint4 = two partial pairs of a segment");
+      const int nseg = ((WORDS == 8 || tc.unit_q >= kFinQ || tid < kFinQ / 2) ? s_where[2] : s_where[3]) * kRecs;
+      static_assert(kTcColSplit == 2 && kTcQ % kFinQ == 0 && (2 * 128) % kFinQ == 0, "one uint4 = two partial pairs of a segment");
       const uint4* part_keys = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(batch.partial) +
                                                                size_t(P.row0 + q) * (tc.slots * kTcColSplit * kRecs));
       auto merge = [&](int a1, int a2) {   // merge two descending pairs
@@ -949,29 +965,18 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
           merge(int(p[j].z), int(p[j].w));
         }
       }
-      key = b1;
-      key2 = b2;
-    }
-    // ---- early verdict.  The best bucket's maximum dot is the query's exact best distance, the
-    // second-best bucket's the exact smallest distance d2b outside the best bucket; the second
-    // neighbour's distance is min(d2b, the best bucket's second smallest) <= d2b, so a query with
-    // !(d0 < ratio * d2b) fails the ratio test (src/slam_frontend.cc:529-536) whatever the rows of
-    // its best bucket are (ratio >= 0: the double product is monotone in the distance).  Only
-    // the other queries - the candidates - need their best bucket's rows; they are re-packed
-    // onto consecutive lane groups, so whole warps skip the rescan.
-    bool cand = false;
-    if (q < nq && key != kTcKeySentinel) {
-      cand = true;
-      if (key2 != kTcKeySentinel && batch.ratio >= 0.0) {
-        const int d0b = (32 * WORDS - (key >> kBucketIdBits)) >> 1;
-        const int d2b = (32 * WORDS - (key2 >> kBucketIdBits)) >> 1;
-        cand = double(d0b) < batch.ratio * double(d2b);
+      if (b1 != kTcKeySentinel) {
+        cand = true;
+        if (b2 != kTcKeySentinel && batch.ratio >= 0.0) {   // (ratio >= 0: the double product is monotone in the distance)
+          const int d0b = (32 * WORDS - (b1 >> kBucketIdBits)) >> 1;
+          const int d2b = (32 * WORDS - (b2 >> kBucketIdBits)) >> 1;
+          cand = double(d0b) < batch.ratio * double(d2b);
+        }
+        if (cand) s_keys[tid] = make_int2(b1, b2);
       }
     }
-    const int lq = tid / kFinLanes;                  // the query's index in the block
-    const unsigned cbal = __ballot_sync(0xffffffffu, cand && part == 0);
+    const unsigned cbal = __ballot_sync(0xffffffffu, cand);
     if (lane == 0) s_ccnt[warp] = __popc(cbal);
-    if (cand && part == 0) s_keys[lq] = make_int2(key, key2);
     __syncthreads();
     unsigned cbase = 0, ncand = 0;
 #pragma unroll
@@ -979,15 +984,17 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       if (w < warp) cbase += s_ccnt[w];
       ncand += s_ccnt[w];
     }
-    if (cand && part == 0) s_list[cbase + __popc(cbal & ((1u << lane) - 1u))] = static_cast<unsigned char>(lq);
+    if (cand) s_list[cbase + __popc(cbal & ((1u << lane) - 1u))] = static_cast<unsigned char>(tid);
     __syncthreads();
-    // ---- exact distances to the rows of a candidate's best bucket.  The bucket is 2 * kTcBucket
-    // 16-byte pieces; in step j the four lanes of a lane group read pieces 4j .. 4j+3 (64
-    // contiguous bytes = rows 2j, 2j+1), a lane and its neighbour add up the two halves of a row.
-    // (64-byte rows: 4 * kTcBucket pieces, a step is one row, the four lanes add up its quarters.)
-    if (unsigned(warp * (32 / kFinLanes)) < ncand) {     // warp-uniform
-      const bool have = unsigned(lq) < ncand;           // lane group lq works on candidate number lq
-      const int cq = have ? int(s_list[lq]) : 0;
+    // ---- 2. exact distances to the rows of the candidates' best buckets, kFinGroups candidates
+    // per pass.  The bucket is 2 * kTcBucket 16-byte pieces; in step j the four lanes of a group
+    // read pieces 4j .. 4j+3 (64 contiguous bytes = rows 2j, 2j+1), a lane and its neighbour add up
+    // the two halves of a row.  (64-byte rows: 4 * kTcBucket pieces, a step is one row, the four
+    // lanes add up its quarters.)
+    for (unsigned c0 = 0; c0 + unsigned(warp * (32 / kFinLanes)) < ncand; c0 += kFinGroups) {   // warp-uniform
+      const unsigned ci = c0 + unsigned(tid / kFinLanes);
+      const bool have = ci < ncand;
+      const int cq = have ? int(s_list[ci]) : 0;
       int ckey = kTcKeySentinel, ckey2 = kTcKeySentinel;
       // lane `part` works on 16-byte half `part & 1` of every second row of the bucket (64-byte
       // rows: on quarter `part` of every row)
@@ -1033,7 +1040,7 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
         top2_insert(k1, k2, (uint32_t((32 * WORDS - dot) >> 1) << kIdxBits) +
                                 uint32_t((kBucketIdMask - (ckey2 & kBucketIdMask)) * kTcBucket));
       }
-      // ---- ratio test (src/slam_frontend.cc:529-536), one lane per candidate
+      // the ratio test (src/slam_frontend.cc:529-536), one lane per candidate
       if (have && part == 0) {
         const int ci0 = (k1 == kKeySentinel) ? -1 : int(k1 & kIdxMask);
         const int cd0 = (k1 == kKeySentinel) ? -1 : int(k1 >> kIdxBits);
@@ -1044,11 +1051,11 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       }
     }
     __syncthreads();
-    // back to one lane group per query of the block, in query order
+    // ---- 3. back to one lane per query of the block, in query order
     bool pass = false;
     int i0 = -1, d0 = -1;
-    if (cand && part == 0) {
-      const int2 r = s_out[lq];
+    if (cand) {
+      const int2 r = s_out[tid];
       pass = r.x >= 0;
       i0 = r.x;
       d0 = r.y;
@@ -1064,17 +1071,17 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       total += s_woff[w];
     }
     unsigned long long* flags = fa.flags + P.qb0;              // qb0 counts 32-query units: every (kFinQ / 32)-th word is used
-    if (tid == 0) st_relaxed_u64(flags + qb * (kFinQ / 32), (epoch << 8) | total);
+    if (tid == 0) st_relaxed_u64(flags + qb * (kFinQ / 32), (epoch << kFinCountBits) | total);
     if (warp == 0) {
       // one warp polls (with a back-off: the other CTAs of the SM are still refining)
       unsigned sum = 0;
       for (int i = lane; i < qb; i += 32) {
         unsigned long long v = ld_relaxed_u64(flags + i * (kFinQ / 32));
-        while ((v >> 8) != epoch) {
+        while ((v >> kFinCountBits) != epoch) {
           __nanosleep(40);
           v = ld_relaxed_u64(flags + i * (kFinQ / 32));
         }
-        sum += unsigned(v & 0xFFull);
+        sum += unsigned(v & ((1ull << kFinCountBits) - 1ull));
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -1183,6 +1190,20 @@ cudaError_t launch_knn2_compact(const KnnBatch& batch, int max_nq, bool pdl, cud
   return launch_pdl(knn2_compact_kernel, cgrid, dim3(kCompactQB), 0, stream, pdl, batch);
 }
 
+// Queries per CTA of the finish kernel (see kFinThreads): by the number of queries of the batch
+// (host-side bounds), VSF_FIN_QPB overrides (64, 128, 256; tuning).
+static int finish_block_queries(const KnnBatch& batch) {
+  static const int forced = [] {
+    const char* e = std::getenv("VSF_FIN_QPB");
+    const int v = e ? std::atoi(e) : 0;
+    return (v == 64 || v == 128 || v == 256) ? v : 0;
+  }();
+  if (forced) return forced;
+  long long total = 0;
+  for (int i = 0; i < batch.num_problems; ++i) total += batch.p[i].nq;
+  return total >= 150000 ? 256 : total >= 75000 ? 128 : 64;
+}
+
 // ev (optional, 4 events): recorded before the main kernel, after it, after the refine and
 // after the compaction kernel (per-kernel timing for bench.py's roofline; an event between two
 // kernels removes their programmatic overlap, so it is only used in dedicated timing passes).
@@ -1191,9 +1212,12 @@ cudaError_t launch_knn2_compact(const KnnBatch& batch, int max_nq, bool pdl, cud
 // The finish kernel alone, for the 64-byte engine (knn2_tc64_kernel.cu).
 cudaError_t launch_knn2_tc64_finish(const KnnBatch& batch, const TcBatch& tc, int max_nq, bool pdl,
                                     cudaStream_t stream, FinishArgs* fa) {
-  fa->nqb = (max_nq + kFinQ - 1) / kFinQ;
+  const int qpb = finish_block_queries(batch);
+  fa->nqb = (max_nq + qpb - 1) / qpb;
   const int grid = fa->nqb * batch.num_problems;
-  return launch_pdl(knn2_tc_finish_kernel<16>, dim3(grid), dim3(kFinThreads), 0, stream, pdl, batch, tc, *fa);
+  return qpb == 256 ? launch_pdl(knn2_tc_finish_kernel<16, 256>, dim3(grid), dim3(kFinThreads), 0, stream, pdl, batch, tc, *fa)
+       : qpb == 128 ? launch_pdl(knn2_tc_finish_kernel<16, 128>, dim3(grid), dim3(kFinThreads), 0, stream, pdl, batch, tc, *fa)
+                    : launch_pdl(knn2_tc_finish_kernel<16, 64>, dim3(grid), dim3(kFinThreads), 0, stream, pdl, batch, tc, *fa);
 }
 
 // phase: 0 = the whole sequence, 1 = the distance kernel only, 2 = the finish kernel only (a
@@ -1218,9 +1242,12 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
   if (ev) cudaEventRecord(ev[1], stream);
   if (phase == 1) return cudaSuccess;
   if (fa && !batch.exact_second) {
-    fa->nqb = (max_nq + kFinQ - 1) / kFinQ;
+    const int qpb = finish_block_queries(batch);
+    fa->nqb = (max_nq + qpb - 1) / qpb;
     const int grid = fa->nqb * batch.num_problems;
-    e = launch_pdl(knn2_tc_finish_kernel<8>, dim3(grid), dim3(kFinThreads), 0, stream, p, batch, tc, *fa);
+    e = qpb == 256 ? launch_pdl(knn2_tc_finish_kernel<8, 256>, dim3(grid), dim3(kFinThreads), 0, stream, p, batch, tc, *fa)
+      : qpb == 128 ? launch_pdl(knn2_tc_finish_kernel<8, 128>, dim3(grid), dim3(kFinThreads), 0, stream, p, batch, tc, *fa)
+                   : launch_pdl(knn2_tc_finish_kernel<8, 64>, dim3(grid), dim3(kFinThreads), 0, stream, p, batch, tc, *fa);
     if (ev) {
       cudaEventRecord(ev[2], stream);
       cudaEventRecord(ev[3], stream);
