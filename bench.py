@@ -4,9 +4,10 @@
 Workload (BASELINE.json configs[3], "C4"): a synthetic 10k-pose sequence, 5000 packed 256-bit
 descriptors per pose, every pose matched (k=2 Hamming kNN + Lowe ratio test + ordered
 compaction) against each of the 10 prior frames of the sliding window: 10 x 5000 x 5000 =
-2.5e8 comparisons and 10 matched frame pairs per pose.  A STEP is one batch of 512 consecutive
-poses (1.28e11 comparisons, 5120 frame pairs, 2048 kernel launches), so the driver's
-`--steps 20` walks the whole 10k-pose sequence and the timed region lasts ~0.6 s.  With N GPUs
+2.5e8 comparisons and 10 matched frame pairs per pose.  A STEP is one batch of 768 consecutive
+poses (1.92e11 comparisons, 7680 frame pairs; 192 groups of four poses, three kernel launches
+each), so the driver's `--steps 20` walks the 10k-pose sequence one and a half times and the
+timed region lasts ~0.65 s (512 poses per step gave 0.45 s once a pose took 44 us).  With N GPUs
 every rank walks its own pose range (weak scaling, no data-path collective); match lists are
 gathered with NCCL after the timed region only.
 
@@ -55,7 +56,7 @@ def parse_args():
     ap.add_argument("--desc-bytes", type=int, default=32,
                     help="descriptor width: 32 = ORB (BASELINE's 256-bit shape), 61 = AKAZE (the reference's "
                          "default extractor, src/slam_frontend.cc:553), 64 = BRISK/FREAK")
-    ap.add_argument("--poses-per-step", type=int, default=512, help="poses in one step (batch)")
+    ap.add_argument("--poses-per-step", type=int, default=768, help="poses in one step (batch)")
     ap.add_argument("--stride", type=int, default=0, help="landmark stride per pose (default N/10)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -517,9 +518,9 @@ def run_b200(a):
                         "comparison; the tensor-core engine is not bound by it (frac > 1)",
             },
             "gpu_launches": int(launches),
-            "kernel": (("knn2_tc (distance) + knn2_tc_finish (refine + ordered compaction) kernels, 2 launches per "
-                        "pose, launched in groups of poses (the distance kernels of a group back to back, then "
-                        "its finish kernels side by side), programmatic dependent launch")
+            "kernel": (("knn2_tc (distance) + knn2_tc_finish (refine + ordered compaction) kernels; the poses are "
+                        "launched in groups of four, a group as ONE batch of its 40 frame pairs = 2 launches "
+                        "(the distance kernel also expands the next group's frames), programmatic dependent launch")
                        if two_kernels else
                        ("expand_train + knn2_tc + refine + compact kernels "
                         "(4 launches per pose, programmatic dependent launch)")) if tensor

@@ -286,8 +286,9 @@ int vsf_get_stereo_threshold(vsf_ctx* ctx, float* value);
 enum {
   VSF_OPT_RESIDUAL_ORDER = 1,
   VSF_OPT_HOLD_THRESHOLD_ON_EMPTY = 2,
-  VSF_OPT_POSE_GROUP = 3,          /* 1 .. 8, default 4: poses whose kernels vsf_window_match_block_device launches
-                                      together (all distance kernels, then all finish kernels); results do not depend on it */
+  VSF_OPT_POSE_GROUP = 3,          /* 1 .. 8, default 4: poses vsf_window_match_block_device / vsf_window_run_sequence launch
+                                      as ONE batch (at most 40 frame pairs: one distance kernel, one finish kernel); results
+                                      do not depend on it */
   VSF_OPT_DEBUG_SORT_DEPTH = 100   /* tests: depth limit of sort_mode 2's introsort replay, -1 = 2 * floor(lg n) */
 };
 int vsf_set_option(vsf_ctx* ctx, int option, int value);
@@ -401,11 +402,10 @@ int vsf_fetch_window(vsf_ctx* ctx, int n_frames, int* counts, vsf_dmatch* out,
  * k in [0, count) the current frame is c = (first + k) mod (n_poses - window) + window and the
  * query frames are c - window .. c - 1 (the bag loop of src/slam_frontend_main.cc:236-328 with
  * src/slam_frontend.cc:424-434 inside, device-resident).  Asynchronous; the results of the last
- * pose stay in the ctx's device buffers (vsf_fetch_window).  On the tensor engine with rows of
- * at most 32 bytes a pose is two kernels, the distance kernel and one kernel for refine +
- * ordered compaction (csrc/knn2_tc_kernel.cu: knn2_tc_finish_kernel), and the poses are
- * launched in groups (VSF_OPT_POSE_GROUP): the distance kernels of a group back to back, then
- * its finish kernels side by side. */
+ * pose stay in the ctx's device buffers (vsf_fetch_window).  On the tensor engine the poses are
+ * launched in groups (VSF_OPT_POSE_GROUP, group x window <= 40 frame pairs), a group as ONE batch
+ * of two kernels: the distance kernel, which also expands the next group's frames, and one
+ * kernel for refine + ordered compaction (csrc/knn2_tc_kernel.cu: knn2_tc_finish_kernel). */
 int vsf_window_match_block_device(vsf_ctx* ctx, const void* d_seq, int n, int n_poses,
                                   long long first, int count, double nn_match_ratio);
 
@@ -420,8 +420,8 @@ int vsf_window_match_block_device(vsf_ctx* ctx, const void* d_seq, int n, int n_
  * the caller wants frame `first` matched against (vsf_window_push).  Returns after every frame
  * has been collected; *h2d_bytes / *d2h_bytes (optional) accumulate vsf_window_last_transfer.
  * Knowing the frames ahead, the call uploads min(VSF_OPT_POSE_GROUP, lag / 3) of them before
- * it launches their kernels together (like vsf_window_match_block_device); the lists are the
- * same.  lag = 12 keeps groups of four frames flowing. */
+ * it launches their kernels as one batch (like vsf_window_match_block_device); the lists are
+ * the same.  lag = 12 keeps groups of four frames flowing. */
 int vsf_window_run_sequence(vsf_ctx* ctx, const uint8_t* h_seq, int n, int n_poses,
                             long long first, int count, double nn_match_ratio,
                             float best_percent, int sort_mode, int lag,

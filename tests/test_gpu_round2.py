@@ -324,8 +324,8 @@ def test_window_match_block_device(width):
                                               (3000, 1, 3, 32), (1400, 4, 6, 61), (1237, 3, 9, 64), (700, 10, 5, 61)])
 def test_block_device_launch_variants(n, W, count, width):
     """The poses of a device-resident block are launched in groups, each group as ONE batch of all
-    its frame pairs (group * window <= 40 problems): one distance kernel, which also expands the
-    next group's frames, and one finish kernel; group 1: a pose is launched alone.  Engine flag
+    its frame pairs (group * window <= 40 problems): one distance kernel and one finish kernel,
+    the next group's frames expanded beside them on a side stream; group 1: a pose is launched alone.  Engine flag
     256 = pose by pose (three kernels), 512 = refine and compaction as separate kernels (four),
     1024 = no early starts.  Same lists every way, equal to the oracle's."""
     import torch
@@ -347,8 +347,9 @@ def test_block_device_launch_variants(n, W, count, width):
                 if flags & (256 | 512):
                     assert ctx.launch_count() - before == per_pose * count
                 else:
+                    # per group: the expansion of its frames (side stream), distance, finish
                     g_eff = max(1, min(group, 40 // W))
-                    assert ctx.launch_count() - before == 2 * ((count + g_eff - 1) // g_eff) + 1
+                    assert ctx.launch_count() - before == 3 * ((count + g_eff - 1) // g_eff)
     cur = ((2 + count - 1) % (poses - W)) + W
     for j in range(W):
         exp = native.get_matches(synth.synth_pose(n, cur - W + j, stride, seed, width),

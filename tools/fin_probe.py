@@ -32,7 +32,7 @@ def main():
     ctx.synth_sequence_device(seq.data_ptr(), n, 0, n_poses, max(1, n // 10), 7)
     base = seq.data_ptr()
     B = 256
-    ctx.set_engine(2, 0)
+    ctx.set_engine(2, int(os.environ.get("VSF_ENGINE_FLAGS", "0")))
 
     def timed(reps=3):
         ctx.window_match_block_device(base, n, n_poses, 0, B, RATIO)
@@ -48,7 +48,7 @@ def main():
             best = min(best, e0.elapsed_time(e1) * 1e3 / (4 * B))
         return round(best, 2)
 
-    res = {"qpb": os.environ.get("VSF_FIN_QPB", "auto"), "features": n, "window": W, "desc_bytes": width, "us_per_pose": {}}
+    res = {"qpb": os.environ.get("VSF_FIN_QPB", "auto"), "flags": os.environ.get("VSF_ENGINE_FLAGS", "0"), "features": n, "window": W, "desc_bytes": width, "us_per_pose": {}}
     for g in (1, 2, 4, 1, 2, 4):
         ctx.set_option(capi.OPT_POSE_GROUP, g)
         res["us_per_pose"].setdefault(str(g), []).append(timed())

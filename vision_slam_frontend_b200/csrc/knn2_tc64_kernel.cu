@@ -164,7 +164,7 @@ __device__ __forceinline__ void epi_barrier() {   // the 16 epilogue warps only
 __device__ __forceinline__ void role_wait(const TcBatch& tc) {
   if (!tc.early) {
     pdl_wait();
-    pdl_launch_dependents();
+    if (!tc.late) pdl_launch_dependents();   // (TcBatch::late: the TMA producer does it after its last load)
   }
 }
 
@@ -185,7 +185,7 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  if (tc.early) pdl_launch_dependents();
+  if (tc.early && !tc.late) pdl_launch_dependents();
 
   if (tid == 0) {
 #pragma unroll
@@ -233,6 +233,7 @@ knn2_tc64_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__
       }
     }
     __syncwarp();
+    if (tc.late) pdl_launch_dependents();   // the last tile load is on its way
   } else if (warp == kEpiWarps + 1) {
     // ------------------------------ MMA issuer ------------------------------
     role_wait(tc);
@@ -462,7 +463,7 @@ knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  if (tc.early) pdl_launch_dependents();
+  if (tc.early && !tc.late) pdl_launch_dependents();
   const uint32_t rank = tc::cluster_ctarank();
 
   if (tid == 0) {
@@ -512,6 +513,7 @@ knn2_tc64_pair_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       }
     }
     __syncwarp();
+    if (tc.late) pdl_launch_dependents();   // the last tile load is on its way
   } else if (warp == kEpiWarps + 1) {
     role_wait(tc);
     if (lane == 0 && rank == 0) {

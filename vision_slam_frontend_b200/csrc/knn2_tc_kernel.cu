@@ -254,7 +254,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     tr[1] = clock64();
   }
   if (tid == 0) ktrace_start(batch.ktrace, 1);
-  if (tc.early) pdl_launch_dependents();
+  if (tc.early && !tc.late) pdl_launch_dependents();
 
   if (tid == 0) {
 #pragma unroll
@@ -296,7 +296,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     if (lane == 0 && walk_more(wk)) U = walk_unit(batch, tc, wk);
     if (!tc.early) {
       pdl_wait();               // the expanded train image is complete
-      pdl_launch_dependents();
+      if (!tc.late) pdl_launch_dependents();
     }
     if (lane == 0) {
       uint32_t it = 0;
@@ -316,11 +316,12 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
       }
     }
     __syncwarp();
+    if (tc.late) pdl_launch_dependents();   // the last tile load is on its way
   } else if (warp == kTcEpiWarps + 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (!tc.early) {
       pdl_wait();
-      pdl_launch_dependents();
+      if (!tc.late) pdl_launch_dependents();
     }
     if (lane == 0) {
       uint32_t it = 0, unit_it = 0, acc_use[2] = {0u, 0u};
@@ -427,7 +428,7 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
     }
     if (!tc.early) {
       pdl_wait();               // partial keys of the previous launch have been consumed
-      pdl_launch_dependents();
+      if (!tc.late) pdl_launch_dependents();
     }
     if (tid == 0) TC_TRACE(3);
     if (tc.em.frames > 0) {

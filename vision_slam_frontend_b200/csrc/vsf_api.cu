@@ -86,6 +86,7 @@ struct ProblemSpec {
 struct PoseLaunch {
   const ExpandMulti* em = nullptr;   // TcBatch::em: the distance kernel expands the next launch's train frames
   int early = 0;                     // TcBatch::early
+  int late = 0;                      // TcBatch::late
   uint2* partial = nullptr;          // partial-key buffer of this launch (nullptr: the ctx's)
   unsigned long long* flags = nullptr;   // look-back words / launch state of the finish kernel
   unsigned long long* state = nullptr;   //   (nullptr: the ctx's)
@@ -136,6 +137,8 @@ struct vsf_ctx {
   int* grp_counts = nullptr;                // [kMaxPoseGroup - 1][kMaxProblems]
   size_t qb_cap = 0;
   long long launches = 0;                   // kernels launched by run_knn (vsf_debug_launch_count)
+  double tm_wait = 0.0, tm_copy = 0.0, tm_ready = 0.0;   // VSF_TIMING: collect's wait / copy-out, launch -> ready (us, summed)
+  long long tm_n = 0;
   // knn2_tc_finish_kernel: ticket counter, per-block (epoch | survivor count) words, and the
   // host's copies of the running values
   unsigned long long *d_finish_ticket = nullptr, *d_finish_flags = nullptr;   // ticket: two FinishArgs::state (4 words each)
@@ -192,6 +195,7 @@ struct vsf_ctx {
   // pipelined window matching (vsf_window_submit / vsf_window_collect): buffers allocated on
   // first use, one set per frame in flight
   struct Flight {
+    std::chrono::steady_clock::time_point t_flush;   // VSF_TIMING: when the frame's kernels were launched
     cudaEvent_t ev_up = nullptr;        // upload stream: the frame's rows are in the ring
     cudaEvent_t ev_chain = nullptr;     // main stream: the kernels of this frame have finished
     cudaEvent_t done = nullptr;         // download stream: the lists are in host memory
@@ -242,6 +246,11 @@ struct vsf_ctx {
   bool dispatch_spin = false;   // dispatcher waits with cudaEventSynchronize (spins on a core) instead of polling
   Flight flights[VSF_PIPELINE_DEPTH];
   cudaStream_t up_stream = nullptr, down_stream = nullptr;   // copy engines of the pipelined path
+  // device-resident blocks of poses: the +-1 images of the next group are made on a side stream
+  // beside the running distance kernel; ev_img[p] = the images of parity p are complete,
+  // ev_grp[p] = the group that read them has finished, ev_blk = what preceded the call has
+  cudaStream_t exp_stream = nullptr;
+  cudaEvent_t ev_img[2] = {nullptr, nullptr}, ev_grp[2] = {nullptr, nullptr}, ev_blk = nullptr;
   cudaEvent_t ev_main = nullptr;
   bool main_dirty = false;   // non-pipelined kernels launched since the last submit may still read the ring
   std::vector<cudaEvent_t> slot_last_chain;   // per ring slot: ev_chain of the last pipelined frame that read it
@@ -556,6 +565,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       if (pose) {
         if (pose->em && !wide) tb.em = *pose->em;
         tb.early = pose->early;
+        tb.late = pose->late;
         if (pose->partial) b.partial = pose->partial;
         if (pose->flags) fa.flags = pose->flags;
         if (pose->state) fa.state = pose->state;
@@ -665,6 +675,12 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
   if (c->down_stream) cudaStreamSynchronize(c->down_stream);
   for (cudaStream_t st : c->sort_stream)
     if (st) cudaStreamSynchronize(st);
+  if (c->exp_stream) {
+    cudaStreamSynchronize(c->exp_stream);
+    cudaStreamDestroy(c->exp_stream);
+  }
+  for (cudaEvent_t e : {c->ev_img[0], c->ev_img[1], c->ev_grp[0], c->ev_grp[1], c->ev_blk})
+    if (e) cudaEventDestroy(e);
   for (vsf_ctx::Flight& f : c->flights) {
     void* fh[] = {f.h_desc, f.h_matches, f.h_fm, f.h_counts};
     for (void* p : fh)
@@ -876,6 +892,7 @@ extern "C" int vsf_set_stream(vsf_ctx* c, void* cuda_stream) {
   for (cudaStream_t st : c->sort_stream)
     if (st) VSF_CUDA(c, cudaStreamSynchronize(st));
   if (c->obs_up_stream) VSF_CUDA(c, cudaStreamSynchronize(c->obs_up_stream));
+  if (c->exp_stream) VSF_CUDA(c, cudaStreamSynchronize(c->exp_stream));
   c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
   return VSF_OK;
 }
@@ -1355,6 +1372,9 @@ static int group_state_init(vsf_ctx* c) {
   VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
   VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
   if (!c->d_partial2) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_partial2), c->partial_cap * sizeof(uint2)));
+  VSF_CUDA(c, cudaStreamCreateWithFlags(&c->exp_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&c->ev_img[0], &c->ev_img[1], &c->ev_grp[0], &c->ev_grp[1], &c->ev_blk})
+    VSF_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   return VSF_OK;
 }
 
@@ -1445,6 +1465,7 @@ static int flush_flights(vsf_ctx* c) {
       frame_state(*fl[g0]);   // (the sort reserve of the group's frames; the buffers come from the specs)
       PoseLaunch pl;
       pl.early = chunk > 0 ? 1 : 0;
+      pl.late = 1;   // (the next frames' expansion kernels on the upload stream need the room beside the distance CTAs)
       pl.partial = (chunk & 1) ? c->d_partial2 : c->d_partial;
       pl.flags = c->grp_flags;
       pl.state = c->grp_flags + group_flag_words(c) + 4 * (chunk & 1);
@@ -1511,6 +1532,10 @@ static int flush_flights(vsf_ctx* c) {
     vsf_ctx::Flight& f = *fl[g];
     f.chain = chain;
     f.launched = true;
+    f.t_flush = std::chrono::steady_clock::now();
+    if (g == 0 && std::getenv("VSF_TIMING2"))
+      std::fprintf(stderr, "FLUSH %.1f frames %llu..+%d\n", std::chrono::duration<double, std::micro>(f.t_flush.time_since_epoch()).count(),
+                   (unsigned long long)f.frame_id, m);
     for (const ProblemSpec& sp : f.specs) {
       const int slot = int((static_cast<const uint8_t*>(sp.q) - c->d_ring) / (size_t(c->rows_pad) * c->row_bytes));
       c->slot_last_chain[slot] = chain;
@@ -1646,6 +1671,7 @@ extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* fram
     if (rc) return rc;
   }
   cudaError_t werr = cudaSuccess;
+  const auto tw0 = std::chrono::steady_clock::now();
   if (f.sort_mode == 1) {
     std::unique_lock<std::mutex> lk(c->done_mu);
     c->done_cv.wait(lk, [&f] { return f.pending.load(std::memory_order_acquire) == 0; });
@@ -1653,6 +1679,13 @@ extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* fram
   } else {
     werr = cudaEventSynchronize(f.done);
   }
+  const auto tw1 = std::chrono::steady_clock::now();
+  c->tm_wait += std::chrono::duration<double, std::micro>(tw1 - tw0).count();
+  c->tm_ready += std::chrono::duration<double, std::micro>(tw1 - f.t_flush).count();
+  ++c->tm_n;
+  if (std::getenv("VSF_TIMING2"))
+    std::fprintf(stderr, "READY %.1f frame %llu entered %.1f\n", std::chrono::duration<double, std::micro>(tw1.time_since_epoch()).count(),
+                 (unsigned long long)f.frame_id, std::chrono::duration<double, std::micro>(tw0.time_since_epoch()).count());
   // the flight is consumed whatever happens next
   c->flight_head = (c->flight_head + 1) % VSF_PIPELINE_DEPTH;
   --c->flight_count;
@@ -1670,6 +1703,7 @@ extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* fram
   }
   for (int j = 0; j < nf; ++j)
     if (counts[j]) std::memcpy(out + size_t(j) * cap_per_frame, f.h_fm + size_t(j) * c->rows_pad, size_t(counts[j]) * sizeof(vsf_feature_match));
+  c->tm_copy += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tw1).count();
   return VSF_OK;
 }
 
@@ -2112,25 +2146,21 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
   const size_t fb = size_t(n) * c->row_bytes;
   const uint8_t* base = static_cast<const uint8_t*>(d_seq);
   auto pose_frame = [&](int k) { return (first + k) % (n_poses - W) + W; };
-  // Tensor engine (engine flag 256: pose-by-pose launches, 1024: no early start; A/B timing).
-  // The poses are launched in groups of G (ctx pose_group, VSF_POSE_GROUP; G * window <=
-  // kMaxProblems), each group as ONE batch of all its frame pairs: one distance kernel - its
-  // persistent CTAs walk the work slots of G poses without a kernel boundary in between - and one
-  // finish kernel.  The distance kernel also expands the NEXT group's current frames (each CTA
-  // its share while its epilogue warps wait for the first accumulators; 64-byte rows: a kernel
-  // of its own behind the distance kernel), so the next group's distance kernel depends on
-  // nothing its stream predecessor - this group's finish kernel - writes and starts as that
-  // one's CTAs leave the SMs (TcBatch::early).  Buffers: +-1 images 2 G deep, partial keys
-  // 2 deep (a group writes while the previous one is read), two finish-kernel launch states;
-  // the last pose of the call writes the ctx's own lists (vsf_fetch_window), the others scratch
-  // lists.  With G = 1 a pose is launched alone and expands the next pose's frame.
+  // Tensor engine (engine flag 256: pose-by-pose launches; A/B timing).  The poses are launched
+  // in groups of G (ctx pose_group, VSF_POSE_GROUP; G * window <= kMaxProblems), each group as
+  // ONE batch of all its frame pairs: one distance kernel - its persistent CTAs walk the work
+  // slots of G poses without a kernel boundary in between - and one finish kernel.  The +-1
+  // images of the NEXT group's current frames are made by one small kernel on a side stream while
+  // this group's distance kernel runs (its 128-thread CTAs fit beside the distance CTAs; the
+  // finish kernel is let in late, TcBatch::late, so that it does not take that room), which is
+  // how the host-buffer path has always done it on its upload stream.  Buffers: +-1 images 2 G
+  // deep, partial keys 2 deep, two finish-kernel launch states; the last pose of the call writes
+  // the ctx's own lists (vsf_fetch_window), the others scratch lists.
   const bool wide = c->words == 16;
   const bool tensor = c->engine >= 2 || (c->engine == 0 && double(W) * double(n) * double(n) >= c->tc_auto_min_cmp);
   const bool ahead = tensor && (c->words == 8 || (wide && c->engine != 3)) && n > 0 && count > 0 &&
                      !(c->engine_flags & (256 | 512)) && !c->profile;
   const int int8 = c->engine == 3 ? 0 : 1;
-  const int pdl = (c->engine_flags & 8) ? 0 : 1;
-  const bool early_ok = !(c->engine_flags & (8 | 1024));
   const int G = ahead ? std::max(1, std::min(c->pose_group, kMaxProblems / W)) : 1;
   std::vector<ProblemSpec> specs;
   auto add_pose = [&](int k, const uint8_t* image, int slot) {
@@ -2180,37 +2210,45 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
     }
     return em;
   };
+  // the images of a group are made on the side stream (ordinary launches: nothing to overlap with
+  // on that stream)
   auto expand_images = [&](const ExpandMulti& em) -> int {
     if (em.frames == 0) return VSF_OK;
-    if (wide) VSF_CUDA(c, launch_expand_train64_multi(em, pdl, c->stream));
-    else VSF_CUDA(c, launch_expand_train_multi(em, int8, pdl, c->stream));
+    if (wide) VSF_CUDA(c, launch_expand_train64_multi(em, 0, c->exp_stream));
+    else VSF_CUDA(c, launch_expand_train_multi(em, int8, 0, c->exp_stream));
     ++c->launches;
     return VSF_OK;
   };
+  // whatever the stream holds so far may still read the image buffers
+  VSF_CUDA(c, cudaEventRecord(c->ev_blk, c->stream));
+  VSF_CUDA(c, cudaStreamWaitEvent(c->exp_stream, c->ev_blk, 0));
   int rc = expand_images(group_images(0, 0));
   if (rc) return rc;
+  VSF_CUDA(c, cudaEventRecord(c->ev_img[0], c->exp_stream));
   unsigned long long* const states = c->grp_flags + group_flag_words(c);
   for (int k0 = 0, grp = 0; k0 < count; k0 += G, ++grp) {
     const int parity = grp & 1;
     const int m = std::min(G, count - k0);
+    // ---- side stream: the next group's images, beside this group's distance kernel (the
+    // buffers they go to were last read by the previous group)
+    const ExpandMulti next_em = group_images(k0 + G, parity ^ 1);
+    if (next_em.frames > 0) {
+      if (grp > 0) VSF_CUDA(c, cudaStreamWaitEvent(c->exp_stream, c->ev_grp[parity ^ 1], 0));
+      if ((rc = expand_images(next_em))) return rc;
+      VSF_CUDA(c, cudaEventRecord(c->ev_img[parity ^ 1], c->exp_stream));
+    }
+    // ---- main stream: this group as one batch
     specs.clear();
     for (int g = 0; g < m; ++g) add_pose(k0 + g, c->grp_exp[parity * G + g], (count - 1 - (k0 + g)) % G);
-    const ExpandMulti next_em = group_images(k0 + G, parity ^ 1);
+    VSF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_img[parity], 0));
     PoseLaunch pl;
-    // (the very first distance kernel of the call follows the expansion it needs; 64-byte rows:
-    // every one follows the expansion kernel of its images)
-    pl.early = (grp > 0 && early_ok && !wide) ? 1 : 0;
+    pl.late = 1;   // the finish kernel must not sit beside the distance CTAs: the side stream's kernels need that room
     pl.partial = parity ? c->d_partial2 : c->d_partial;
     pl.flags = c->grp_flags;
     pl.state = states + 4 * parity;
-    if (!wide && next_em.frames > 0) pl.em = &next_em;
-    if (wide && grp > 0) {
-      // 64-byte rows: the images of this group are expanded by a kernel in front of its distance
-      // kernel (it overlaps the previous group's finish kernel only through its launch latency)
-    }
     rc = run_knn(c, specs, ratio, false, false, &pl);
     if (rc) return rc;
-    if (wide && (rc = expand_images(next_em))) return rc;
+    if (k0 + G < count) VSF_CUDA(c, cudaEventRecord(c->ev_grp[parity], c->stream));
   }
   c->last_n_frames = W;
   return VSF_OK;
@@ -2247,15 +2285,42 @@ extern "C" int vsf_window_run_sequence(vsf_ctx* c, const uint8_t* h_seq, int n, 
     if (d2h_bytes) *d2h_bytes += c->last_d2h;
     return VSF_OK;
   };
+  // VSF_TIMING: where the calling thread's time goes (submits that stage a frame, submits that
+  // also launch a group, collects)
+  static const bool timing = std::getenv("VSF_TIMING") != nullptr;
+  double t_stage = 0.0, t_launch = 0.0, t_collect = 0.0;
+  int n_launch = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
   for (int k = 0; k < count; ++k) {
     const uint8_t* D = h_seq + size_t((first + k) % n_poses) * fb;
+    const auto t0 = now();
+    const int staged_before = c->flights_staged;
     int rc = vsf_window_submit(c, uint64_t(first + k), D, n, size_t(c->row_bytes), ratio, best_percent, sort_mode, flags);
     if (rc) return rc;
+    const auto t1 = now();
+    if (c->flights_staged <= staged_before) {
+      t_launch += us(t0, t1);
+      ++n_launch;
+    } else {
+      t_stage += us(t0, t1);
+    }
     if (c->flight_count > lag && (rc = collect_one())) return rc;
+    t_collect += us(t1, now());
   }
   while (c->flight_count > 0) {
     const int rc = collect_one();
     if (rc) return rc;
+  }
+  if (timing && count > 0) {
+    std::fprintf(stderr, "vsf_window_run_sequence: %d frames; submit (stage only) %.1f us each, submit + group launch %.1f us each (%d), "
+                 "collect %.1f us per frame (wait %.1f, copy-out %.1f; launch -> ready %.1f us)\n", count,
+                 t_stage / std::max(1, count - n_launch), t_launch / std::max(1, n_launch), n_launch, t_collect / count,
+                 c->tm_wait / std::max(1LL, c->tm_n), c->tm_copy / std::max(1LL, c->tm_n), c->tm_ready / std::max(1LL, c->tm_n));
+    c->tm_wait = c->tm_copy = c->tm_ready = 0.0;
+    c->tm_n = 0;
   }
   return VSF_OK;
 }

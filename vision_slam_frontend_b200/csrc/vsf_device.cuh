@@ -122,6 +122,11 @@ struct TcBatch {
   // it just before it exits (so that "complete" still implies "everything before it complete").
   ExpandMulti em;
   int early;
+  // late != 0: the CTAs let the stream successor (the finish kernel) launch only when their TMA
+  // producer has issued its last tile load, not at the start.  A finish kernel launched at the
+  // start sits in the room a distance CTA leaves on its SM for as long as the distance kernel runs,
+  // and the expansion kernels of the upload stream (host-buffer sequences) find no room.
+  int late;
 };
 constexpr int kTcTraceSlots = 16;
 
