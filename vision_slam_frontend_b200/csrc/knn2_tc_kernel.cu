@@ -431,15 +431,6 @@ knn2_tc_kernel(const __grid_constant__ KnnBatch batch, const __grid_constant__ T
       if (!tc.late) pdl_launch_dependents();
     }
     if (tid == 0) TC_TRACE(3);
-    if (tc.em.frames > 0) {
-      // this CTA's share of the next launch's train images (layout of expand_train_kernel), while
-      // the tensor core works on the first tile.  The images they replace were last read two
-      // launches ago.
-      const int rows_pad = (tc.em.nt + kTcTileRows - 1) / kTcTileRows * kTcTileRows;
-      for (int f = 0; f < tc.em.frames; ++f)
-        for (int idx = blockIdx.x * (kTcEpiWarps * 32) + tid; idx < rows_pad * 4; idx += gridDim.x * (kTcEpiWarps * 32))
-          expand_item<I8>(tc.em.src[f], tc.em.nt, tc.em.out[f], idx % rows_pad, idx / rows_pad);
-    }
     while (walk_more(wk)) {
       walk_next(wk, U);                       // wk now stands on the unit after U
       const bool more = walk_more(wk);

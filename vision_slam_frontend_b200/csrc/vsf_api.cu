@@ -84,7 +84,6 @@ struct ProblemSpec {
 // A stream of poses (vsf_window_match_block_device, vsf_window_run_sequence): how the kernels of
 // a launch - one pose, or a group of poses as ONE batch - are launched.
 struct PoseLaunch {
-  const ExpandMulti* em = nullptr;   // TcBatch::em: the distance kernel expands the next launch's train frames
   int early = 0;                     // TcBatch::early
   int late = 0;                      // TcBatch::late
   uint2* partial = nullptr;          // partial-key buffer of this launch (nullptr: the ctx's)
@@ -563,7 +562,6 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       fa.flags = c->d_finish_flags;
       const int phase = 0;
       if (pose) {
-        if (pose->em && !wide) tb.em = *pose->em;
         tb.early = pose->early;
         tb.late = pose->late;
         if (pose->partial) b.partial = pose->partial;
@@ -2159,7 +2157,7 @@ extern "C" int vsf_window_match_block_device(vsf_ctx* c, const void* d_seq, int 
   const bool wide = c->words == 16;
   const bool tensor = c->engine >= 2 || (c->engine == 0 && double(W) * double(n) * double(n) >= c->tc_auto_min_cmp);
   const bool ahead = tensor && (c->words == 8 || (wide && c->engine != 3)) && n > 0 && count > 0 &&
-                     !(c->engine_flags & (256 | 512)) && !c->profile;
+                     !(c->engine_flags & (256 | 512));   // (vsf_set_profile: events around the kernels of every batch)
   const int int8 = c->engine == 3 ? 0 : 1;
   const int G = ahead ? std::max(1, std::min(c->pose_group, kMaxProblems / W)) : 1;
   std::vector<ProblemSpec> specs;

@@ -113,14 +113,11 @@ struct TcBatch {
   int unit_q;                          // 64-byte engine: queries per block (128: one CTA per unit, 256: a CTA pair per unit)
   int flags;                           // bring-up knobs (timing experiments; results invalid): 2 = skip the bucket reduction, 4 = skip the TMEM loads
   long long* trace;                    // flag 16 (builds with -DVSF_TC_TRACE): per-CTA timeline, kTcTraceSlots values per CTA
-  // A stream of poses (vsf_window_match_block_device).  em.frames > 0: the distance kernel
-  // also expands the train frames of the NEXT launch (packed rows em.src[f], em.nt of them each)
-  // into em.out[f], each CTA its share, while its epilogue warps wait for the first accumulators.
+  // A sequence of batches (vsf_window_match_block_device, vsf_window_run_sequence).
   // early != 0: everything this launch reads was complete before its stream predecessor (the
   // previous launch's finish kernel) let it launch, and its partial keys go to another buffer than
   // the one that kernel reads: it starts without waiting for the predecessor and only waits for
   // it just before it exits (so that "complete" still implies "everything before it complete").
-  ExpandMulti em;
   int early;
   // late != 0: the CTAs let the stream successor (the finish kernel) launch only when their TMA
   // producer has issued its last tile load, not at the start.  A finish kernel launched at the
