@@ -359,6 +359,35 @@ def test_block_device_launch_variants(n, W, count, width):
 
 
 @pytest.mark.parametrize("width", [32, 61])
+def test_block_device_large_batches(width):
+    """Groups large enough for the finish kernel's 256-query blocks (four poses x ten frames x
+    4200 queries = 168 000 >= 150 000) and 128-query blocks (two poses: 84 000 >= 75 000); one pose
+    at a time runs the 64-query blocks.  Same lists every way, equal to the oracle's."""
+    import torch
+    from vision_slam_frontend_b200 import capi
+    n, W, count = 4200, 10, 8
+    poses, stride, seed = W + 9, 420, 11
+    with new_ctx(desc_bytes=width, max_features=4352, window=W) as ctx:
+        buf = torch.empty((poses, n, ctx.row_bytes), dtype=torch.uint8, device="cuda")
+        ctx.synth_sequence_device(buf.data_ptr(), n, 0, poses, stride, seed)
+        ctx.set_engine(2, 0)
+        got = []
+        for group in (4, 2, 1):
+            ctx.set_option(capi.OPT_POSE_GROUP, group)
+            ctx.window_match_block_device(buf.data_ptr(), n, poses, 1, count, RATIO)
+            got.append(ctx.fetch_window(W))
+    cur = ((1 + count - 1) % (poses - W)) + W
+    total = 0
+    for j in range(W):
+        exp = native.get_matches(synth.synth_pose(n, cur - W + j, stride, seed, width),
+                                 synth.synth_pose(n, cur, stride, seed, width), RATIO)
+        total += len(exp)
+        for g in got:
+            np.testing.assert_array_equal(g[j], exp)
+    assert total > 5000
+
+
+@pytest.mark.parametrize("width", [32, 61])
 def test_tensor_launch_replayed_from_a_cuda_graph(width):
     """The finish kernel's ticket counter and look-back epoch live on the device and are advanced by
     the launch itself, so a captured launch sequence can be replayed (bench.py's C2 leg does) - also
@@ -412,22 +441,27 @@ def test_tensor_launch_replayed_from_a_cuda_graph(width):
             np.testing.assert_array_equal(got[j], native.get_matches(frames[j], frames[W], RATIO))
 
 
-@pytest.mark.parametrize("sort_mode,width,lag", [(0, 32, 12), (1, 32, 12), (2, 32, 12), (1, 61, 12), (2, 61, 9), (1, 32, 5),
-                                                  (2, 32, 1)])
-def test_window_run_sequence_equals_per_frame_calls(sort_mode, width, lag):
-    """vsf_window_run_sequence (groups of frames uploaded, then launched together) returns per
+@pytest.mark.parametrize("sort_mode,width,lag,shape", [
+    (0, 32, 12, None), (1, 32, 12, None), (2, 32, 12, None), (1, 61, 12, None), (2, 61, 9, None), (1, 32, 5, None),
+    (2, 32, 1, None),
+    # batches of four frames x ten past frames that are large enough for the finish kernel's 256- and
+    # 128-query blocks (>= 150 000 / 75 000 queries per batch), both widths
+    (1, 32, 12, (4200, 10, 15, 9)), (0, 61, 12, (4200, 10, 15, 9)), (1, 32, 12, (2100, 10, 15, 9)),
+    (2, 61, 12, (2100, 10, 15, 9))])
+def test_window_run_sequence_equals_per_frame_calls(sort_mode, width, lag, shape):
+    """vsf_window_run_sequence (groups of frames uploaded, then launched as one batch) returns per
     frame what the oracle's GetMatches + sort + cut gives for the window of that moment."""
     import torch
     from vision_slam_frontend_b200 import capi
-    n, W, n_pool, count = 1100, 3, 9, 14
+    n, W, n_pool, count = shape or (1100, 3, 9, 14)
     rb = 32 if width <= 32 else 64
-    frames = [synth.synth_pose(n, p, 110, 3, width) for p in range(n_pool)]
+    frames = [synth.synth_pose(n, p, max(1, n // 10), 3, width) for p in range(n_pool)]
     padded = np.zeros((n_pool, n, rb), np.uint8)
     for p in range(n_pool):
         padded[p, :, :width] = frames[p]
     pool = torch.from_numpy(padded).pin_memory()
     hp = pool.numpy()
-    with new_ctx(desc_bytes=width, max_features=2048, window=W) as ctx:
+    with new_ctx(desc_bytes=width, max_features=max(2048, n), window=W) as ctx:
         ctx.set_engine(2, 0)
         for p in range(W):
             ctx.window_push(1000 + p, frames[p])
