@@ -106,10 +106,10 @@ int vsf_set_tuning(vsf_ctx* ctx, int popc_mode, int train_split,
  * results.  flags: pass 0; 128 keeps 33..64-byte rows on the single-CTA tensor kernel instead of
  * CTA pairs (A/B timing); 64 keeps the device sort of the pipelined frame stream (sort_mode 0 / 2)
  * on the main stream instead of a side stream with reserved SMs (A/B timing); 512 runs the
- * tensor engine's refine and compaction as two kernels instead of one (A/B timing); 256 stops
- * vsf_window_match_block_device from expanding the next pose's frame inside the running pose's
- * distance kernel, 1024 from starting a pose's distance kernel before the previous pose's
- * finish kernel has completed (A/B timing); 16 / 32 record the per-CTA / per-kernel
+ * tensor engine's refine and compaction as two kernels instead of one (A/B timing); 256 makes
+ * vsf_window_match_block_device launch pose by pose instead of in groups, 4096 makes the
+ * distance kernels of the host-buffer frame stream let their finish kernel launch at their start
+ * instead of near their end (A/B timing; 1024 and 2048 are accepted and do nothing any more); 16 / 32 record the per-CTA / per-kernel
  * timelines read by vsf_debug_tc_trace / vsf_debug_kernel_trace (16, and the
  * timing-only flags 2 / 4, exist only in libraries built with VSF_TC_TRACE /
  * VSF_TC_BRINGUP, see vision_slam_frontend_b200/build.py). */

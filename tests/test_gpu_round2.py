@@ -327,7 +327,7 @@ def test_block_device_launch_variants(n, W, count, width):
     its frame pairs (group * window <= 40 problems): one distance kernel and one finish kernel,
     the next group's frames expanded beside them on a side stream; group 1: a pose is launched alone.  Engine flag
     256 = pose by pose (three kernels), 512 = refine and compaction as separate kernels (four),
-    1024 = no early starts.  Same lists every way, equal to the oracle's."""
+    1024 = accepted, no effect any more.  Same lists every way, equal to the oracle's."""
     import torch
     from vision_slam_frontend_b200 import capi
     poses, stride, seed = W + 9, 97, 5

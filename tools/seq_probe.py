@@ -1,7 +1,7 @@
 """Kernel-level timeline (engine flag 32) of the host-buffer sequence path: vsf_window_run_sequence
 over a few dozen frames, one record per launched batch.  Under gpurun:
 
-    python tools/seq_probe.py [features] [window] [desc_bytes] [sort_mode] [lag]
+    python tools/seq_probe.py [features] [window] [desc_bytes] [sort_mode] [lag] [pose_group]
 """
 import ctypes as C
 import json
@@ -39,14 +39,18 @@ def main():
     ring = 4
     out = np.zeros((ring, W, n), dtype=vsf.FEATURE_MATCH_DTYPE)
     cnts = np.zeros((ring, W), np.int32)
-    ctx.set_engine(2, 0)
+    flags = int(os.environ.get("VSF_ENGINE_FLAGS", "0"))
+    ctx.set_engine(2, flags)
+    if len(sys.argv) > 6:
+        from vision_slam_frontend_b200 import capi
+        ctx.set_option(capi.OPT_POSE_GROUP, int(sys.argv[6]))
     ctx.window_run_sequence(hp, W, 256, RATIO, 0.3, sort_mode, lag, out, cnts)   # warm-up
     t0 = time.perf_counter()
     ctx.window_run_sequence(hp, W + 256, 512, RATIO, 0.3, sort_mode, lag, out, cnts)
     wall = time.perf_counter() - t0
     res = {"features": n, "window": W, "desc_bytes": width, "sort_mode": sort_mode, "lag": lag,
            "us_per_frame": round(1e6 * wall / 512, 2)}
-    ctx.set_engine(2, 32)
+    ctx.set_engine(2, 32 | flags)
     ctx.window_run_sequence(hp, W + 768, 96, RATIO, 0.3, sort_mode, lag, out, cnts)
     buf = np.zeros((256, 8, 2), np.int64)
     got = C.c_int(0)

@@ -853,7 +853,7 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   VSF_ALLOC_HOST(c, c->h_fm, size_t(window) * N * sizeof(vsf_feature_match));
   if (const char* e = std::getenv("VSF_RESERVE_SMS")) c->reserve_override = std::atoi(e);
   if (const char* e = std::getenv("VSF_SORT_STREAMS")) c->sort_streams = std::atoi(e) == 1 ? 1 : 2;
-  if (const char* e = std::getenv("VSF_ENGINE_FLAGS")) c->engine_flags = std::atoi(e) & (8 | 64 | 128 | 256 | 512 | 1024);   // A/B timing
+  if (const char* e = std::getenv("VSF_ENGINE_FLAGS")) c->engine_flags = std::atoi(e) & (8 | 64 | 128 | 256 | 512 | 4096);   // A/B timing
   if (const char* e = std::getenv("VSF_ENGINE")) {   // test / bench override of the automatic choice
     const int v = std::atoi(e);
     if (v >= 0 && v <= 3 && (v < 3 || c->words == 8)) c->engine = v;
@@ -1394,7 +1394,7 @@ static int flush_flights(vsf_ctx* c) {
   int rc = VSF_OK;
   // one batch for the group: every frame has work for the tensor engine
   bool grouped = m > 1 && (c->words == 8 || (c->words == 16 && c->engine != 3)) && c->engine != 1 &&
-                 !(c->engine_flags & (8 | 512 | 1024)) && !c->profile;
+                 !(c->engine_flags & (8 | 512)) && !c->profile;
   bool any_side_sort = false;
   for (int g = 0; g < m; ++g) {
     const vsf_ctx::Flight& f = *fl[g];
@@ -1419,11 +1419,13 @@ static int flush_flights(vsf_ctx* c) {
   // list), which costs the distance kernel a few per cent and takes the sort off the frame
   // stream's critical path.  Measured on C4 (10 lists, 148 SMs): the 10 us stable sort is best
   // served by 8 SMs (57.2 us/pose; 58.7 with 10), the 55 us exact sort - whose CTAs of two
-  // consecutive frames overlap - by 14-16 (62.7; 64.4 with 10, 68.0 with 8)
+  // consecutive frames overlap - by 14-16 (62.7; 64.4 with 10, 68.0 with 8) while a pose took
+  // 55 us; now that a pose takes 44 us the sorts of two frames have to run fully side by side:
+  // 20 SMs (46.4 us/frame with 15, 44.6 with 20, 45.5 with 24, 48.0 with 30)
   auto frame_state = [&](vsf_ctx::Flight& f) {
     const bool side_sort = f.sort_mode != 1 && f.nf > 0 && !(c->engine_flags & 64);
     c->reserve_sms = !side_sort ? 0
-                     : f.sort_mode == 2 ? std::min(f.nf + f.nf / 2, std::max(1, c->sm_count / 9))
+                     : f.sort_mode == 2 ? std::min(2 * f.nf, std::max(1, c->sm_count / 7))
                                         : std::min(f.nf, std::max(1, c->sm_count / 18));
     if (side_sort && c->reserve_override >= 0) c->reserve_sms = std::min(c->reserve_override, c->sm_count - 1);
     c->match_base = f.d_matches;
@@ -1463,7 +1465,7 @@ static int flush_flights(vsf_ctx* c) {
       frame_state(*fl[g0]);   // (the sort reserve of the group's frames; the buffers come from the specs)
       PoseLaunch pl;
       pl.early = chunk > 0 ? 1 : 0;
-      pl.late = 1;   // (the next frames' expansion kernels on the upload stream need the room beside the distance CTAs)
+      pl.late = (c->engine_flags & 4096) ? 0 : 1;   // (the next frames' expansion kernels on the upload stream need the room beside the distance CTAs; flag 4096: A/B timing)
       pl.partial = (chunk & 1) ? c->d_partial2 : c->d_partial;
       pl.flags = c->grp_flags;
       pl.state = c->grp_flags + group_flag_words(c) + 4 * (chunk & 1);
@@ -1472,10 +1474,14 @@ static int flush_flights(vsf_ctx* c) {
       g0 = g1;
     }
   } else {
+    // frame by frame (vsf_window_submit alone; small frames): the finish kernel is let in late here
+    // too, the next frame's expansion on the upload stream wants the room beside the distance CTAs
+    PoseLaunch pl;
+    pl.late = (c->engine_flags & 4096) ? 0 : 1;   // (flag 4096: trigger at the start, A/B timing)
     for (int g = 0; g < m && !rc; ++g) {
       vsf_ctx::Flight& f = *fl[g];
       frame_state(f);
-      rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1);
+      rc = run_knn(c, f.specs, f.ratio, f.sort_mode == 1, false, &pl);
     }
   }
   // ---- device sort (stable, or the replay of the reference's std::sort) + cut; the kept counts
