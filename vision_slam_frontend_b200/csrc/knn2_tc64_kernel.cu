@@ -11,6 +11,7 @@
 //              epilogue warps are (tile parity) x (lane quarter) x (column half of 64)
 // A unit's queries may only be replaced once every MMA of the unit has completed; the epilogue
 // warps of the two parities meet on a named barrier for that.
+#include <atomic>
 #include <utility>
 
 #include "tc_ptx.cuh"
@@ -878,15 +879,25 @@ cudaError_t launch_knn2_tc64(const KnnBatch& batch, const TcBatch& tc, int max_n
                              cudaStream_t stream, FinishArgs* fa, int* launched, int phase) {
   if (launched) *launched = 0;
   if (batch.num_problems <= 0 || tc.total <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(w64::knn2_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::kSmemBytes);
-  if (e != cudaSuccess) return e;
+  // per-device function attributes, set once per device (one bit each)
+  static std::atomic<unsigned long long> smem_done{0ull};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  const bool attrs_set = (smem_done.load(std::memory_order_acquire) & bit) != 0;
+  cudaError_t e = cudaSuccess;
+  if (!attrs_set) {
+    e = cudaFuncSetAttribute(w64::knn2_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(w64::pair::knn2_tc64_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::pair::kSmemBytesP);
+    if (e != cudaSuccess) return e;
+    smem_done.fetch_or(bit, std::memory_order_release);
+  }
   const bool p = pdl != 0;
   if (ev) cudaEventRecord(ev[0], stream);
   if (phase != 2) {
     if (tc.unit_q == 2 * w64::kQ) {
       // CTA pairs: tc.grid counts pairs; cluster dimensions are a compile-time attribute of the kernel
-      e = cudaFuncSetAttribute(w64::pair::knn2_tc64_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w64::pair::kSmemBytesP);
-      if (e != cudaSuccess) return e;
       e = w64::launch_pdl(w64::pair::knn2_tc64_pair_kernel, dim3(2 * tc.grid), dim3(w64::kThreads), w64::pair::kSmemBytesP, stream, p,
                           batch, tc);
     } else {

@@ -1219,10 +1219,20 @@ cudaError_t launch_knn2_tc(const KnnBatch& batch, const TcBatch& tc, int int8, i
   if (launched) *launched = 0;
   if (batch.num_problems <= 0 || tc.total <= 0) return cudaSuccess;
   cudaError_t e;
-  // per-device attribute; setting it is a cheap host-side call
-  e = int8 ? cudaFuncSetAttribute(knn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes)
-           : cudaFuncSetAttribute(knn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-  if (e != cudaSuccess) return e;
+  {
+    // per-device function attribute, set once per device and operand kind (one bit each)
+    static std::atomic<unsigned long long> smem_done[2] = {{0ull}, {0ull}};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::atomic<unsigned long long>& done = smem_done[int8 ? 1 : 0];
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+      e = int8 ? cudaFuncSetAttribute(knn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes)
+               : cudaFuncSetAttribute(knn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+      if (e != cudaSuccess) return e;
+      done.fetch_or(bit, std::memory_order_release);
+    }
+  }
   const bool p = pdl != 0;
   if (ev) cudaEventRecord(ev[0], stream);
   if (phase != 2) {

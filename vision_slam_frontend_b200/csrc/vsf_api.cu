@@ -331,9 +331,7 @@ static void commit_staging(vsf_ctx* c, uint64_t frame_id, int count) {
 
 // Pack caller rows (stride apart, desc_bytes wide) into pinned staging padded to
 // row_bytes, then one async H2D copy.
-static int upload_desc(vsf_ctx* c, uint8_t* h, const uint8_t* src, int n, size_t stride,
-                       uint8_t* d_dst) {
-  if (n == 0) return VSF_OK;
+static void pack_desc(const vsf_ctx* c, uint8_t* h, const uint8_t* src, int n, size_t stride) {
   if (stride == size_t(c->row_bytes) && c->desc_bytes == c->row_bytes) {
     std::memcpy(h, src, size_t(n) * c->row_bytes);
   } else {
@@ -343,6 +341,12 @@ static int upload_desc(vsf_ctx* c, uint8_t* h, const uint8_t* src, int n, size_t
         std::memset(h + size_t(i) * c->row_bytes + c->desc_bytes, 0, c->row_bytes - c->desc_bytes);
     }
   }
+}
+
+static int upload_desc(vsf_ctx* c, uint8_t* h, const uint8_t* src, int n, size_t stride,
+                       uint8_t* d_dst) {
+  if (n == 0) return VSF_OK;
+  pack_desc(c, h, src, n, stride);
   VSF_CUDA(c, cudaMemcpyAsync(d_dst, h, size_t(n) * c->row_bytes, cudaMemcpyHostToDevice, c->stream));
   return VSF_OK;
 }
@@ -416,6 +420,9 @@ static void plan_tc_partition(TcBatch* tbp, int qblocks, int sm, int force_split
 static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double ratio, bool mirror = false,
                    bool latency = false, const PoseLaunch* pose = nullptr) {
   if (specs.empty()) return VSF_OK;
+  // VSF_TIMING: host time of a blocking call's stages (prepare, expansion launch, distance + finish launches)
+  static const bool timing = std::getenv("VSF_TIMING") != nullptr;
+  const auto tk0 = std::chrono::steady_clock::now();
   c->main_dirty = true;
   if (int(specs.size()) > kMaxProblems) return fail(c, VSF_ERR_CAPACITY, "too many problems in one batch");
   KnnBatch b;
@@ -517,6 +524,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
     }
     b.ktrace = kt;
     const uint8_t* exp_image[kTcMaxTrains];
+    const auto tk1 = std::chrono::steady_clock::now();
     for (int k = 0; k < n_trains; ++k) {
       exp_image[k] = c->d_train_exp[k];
       if (wide)
@@ -527,6 +535,7 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
                                         c->d_train_exp[k], int8, pdl, c->stream, kt));
       ++c->launches;
     }
+    const auto tk2 = std::chrono::steady_clock::now();
     TcBatch tb;
     std::memset(&tb, 0, sizeof(tb));
     // Work = (256-query block, piece of train tiles) slots, shared out to the CTAs as equal
@@ -578,6 +587,14 @@ static int run_knn(vsf_ctx* c, const std::vector<ProblemSpec>& specs, double rat
       if (fap && !b.exact_second && !(pose && pose->state)) c->finish_parity ^= 1;
     }
     c->pev_valid = c->profile != 0;
+    if (timing && latency) {
+      const auto tk3 = std::chrono::steady_clock::now();
+      auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+      };
+      std::fprintf(stderr, "  run_knn: prepare %.1f us, expansion launch(es) %.1f us, plan + distance + finish launches %.1f us\n",
+                   us(tk0, tk1), us(tk1, tk2), us(tk2, tk3));
+    }
     return VSF_OK;
   }
 
@@ -656,7 +673,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
   if (c->grp_flags) cudaFree(c->grp_flags);
   if (c->grp_matches) cudaFree(c->grp_matches);
   if (c->grp_counts) cudaFree(c->grp_counts);
-  void* dev[] = {c->d_ring, c->d_raw_left, c->d_raw_right, c->d_right_c, c->d_xy_left, c->d_xy_right,
+  void* dev[] = {c->d_ring, c->d_raw_left, c->d_right_c, c->d_xy_left, c->d_xy_right,
                  c->d_xy_left_c, c->d_xy_right_c, c->d_knn_out, c->d_partial, c->d_partial2, c->d_finish_ticket, c->d_finish_flags, c->d_qblock_arrivals,
                  c->d_qblock_pass, c->d_problem_arrivals, c->d_matches, c->d_match_count, c->d_resid,
                  c->d_chunk_keep, c->d_chunk_off, c->d_ticket, c->d_kept_left, c->d_kept_right, c->d_slot_rows, c->d_thresh, c->d_X4,
@@ -664,7 +681,7 @@ extern "C" void vsf_destroy(vsf_ctx* c) {
                  c->d_ktrace, c->d_sort_scratch};
   for (void* p : dev)
     if (p) cudaFree(p);
-  void* host[] = {c->h_desc[0], c->h_desc[1], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches, c->h_region_counts,
+  void* host[] = {c->h_desc[0], c->h_xy[0], c->h_xy[1], c->h_counts, c->h_matches, c->h_region_counts,
                   c->h_kept[0], c->h_kept[1], c->h_resid, c->h_X4, c->h_knn, c->h_tri_io,
                   c->h_scalar, c->h_fm};
   for (void* p : host)
@@ -772,8 +789,10 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
   // their kernels; a slot must not be reused while a staged frame still has to read it)
   c->ring_slots = window + 2 + (kMaxPoseGroup - 1);
   VSF_ALLOC(c, c->d_ring, size_t(c->ring_slots) * N * c->row_bytes);
-  VSF_ALLOC(c, c->d_raw_left, N * c->row_bytes);
-  VSF_ALLOC(c, c->d_raw_right, N * c->row_bytes);
+  // (one block: a pair call packs its train rows right behind its query rows and uploads both
+  // with one copy)
+  VSF_ALLOC(c, c->d_raw_left, 2 * N * c->row_bytes);
+  c->d_raw_right = c->d_raw_left + N * c->row_bytes;
   VSF_ALLOC(c, c->d_right_c, N * c->row_bytes);
   VSF_ALLOC(c, c->d_xy_left, N * sizeof(float2));
   VSF_ALLOC(c, c->d_xy_right, N * sizeof(float2));
@@ -824,8 +843,9 @@ extern "C" int vsf_create(int device, int max_features, int desc_bytes, int wind
     const float init[2] = {10000.0f, 10000.0f};  // stereo_ambig_constraint (src/slam_frontend.cc:353)
     cudaMemcpy(c->d_thresh, init, sizeof(init), cudaMemcpyHostToDevice);
   }
+  VSF_ALLOC_HOST(c, c->h_desc[0], 2 * N * c->row_bytes);
+  c->h_desc[1] = c->h_desc[0] + N * c->row_bytes;
   for (int k = 0; k < 2; ++k) {
-    VSF_ALLOC_HOST(c, c->h_desc[k], N * c->row_bytes);
     VSF_ALLOC_HOST(c, c->h_xy[k], N * sizeof(float2));
     VSF_ALLOC_HOST(c, c->h_kept[k], N * sizeof(int));
   }
@@ -977,15 +997,18 @@ static int check_pair(vsf_ctx* c, const uint8_t* q, int nq, size_t qs, const uin
 static int knn_pair(vsf_ctx* c, const uint8_t* q, int nq, size_t qs, const uint8_t* t, int nt, size_t ts,
                     double ratio, bool mirror = false) {
   cudaSetDevice(c->device);
-  int rc;
   static const bool timing = std::getenv("VSF_TIMING") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
-  if ((rc = upload_desc(c, 0, q, nq, qs, c->d_raw_left))) return rc;
-  if ((rc = upload_desc(c, 1, t, nt, ts, c->d_raw_right))) return rc;
-  if (timing) std::fprintf(stderr, "  knn_pair: staging + 2 cudaMemcpyAsync %.1f us\n",
+  // one upload: the train rows are packed right behind the query rows (the left / right staging
+  // and device buffers are one block each)
+  const size_t qb = size_t(nq) * c->row_bytes, tb = size_t(nt) * c->row_bytes;
+  if (nq > 0) pack_desc(c, c->h_desc[0], q, nq, qs);
+  if (nt > 0) pack_desc(c, c->h_desc[0] + qb, t, nt, ts);
+  if (qb + tb > 0) VSF_CUDA(c, cudaMemcpyAsync(c->d_raw_left, c->h_desc[0], qb + tb, cudaMemcpyHostToDevice, c->stream));
+  if (timing) std::fprintf(stderr, "  knn_pair: staging + 1 cudaMemcpyAsync %.1f us\n",
                            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
   std::vector<ProblemSpec> specs(1);
-  specs[0] = ProblemSpec{c->d_raw_left, nq, nullptr, c->d_raw_right, nt, nullptr, c->window + 1};
+  specs[0] = ProblemSpec{c->d_raw_left, nq, nullptr, c->d_raw_left + qb, nt, nullptr, c->window + 1};
   return run_knn(c, specs, ratio, mirror, true);
 }
 
