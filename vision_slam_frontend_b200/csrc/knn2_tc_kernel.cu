@@ -886,7 +886,6 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
   const int warp = tid >> 5, lane = tid & 31;
   const int part = tid % kFinLanes;
   if (tid == 0) ktrace_start(batch.ktrace, 2);
-  if (fa.nowait) pdl_launch_dependents();
   // one block per CTA, taken by ticket (the do-while only gives the early exits a common end)
   do {
     if (tid == 0) {
@@ -914,11 +913,9 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
     if (P.nt_dev) nt = min(nt, *P.nt_dev);
     const int q0 = qb * kFinQ;
     const int q = q0 + tid;
-    if (!fa.nowait) {
-      pdl_wait();                              // the partial bucket keys are complete
-      if (tid == 0) ktrace_start(batch.ktrace, 4);
-      pdl_launch_dependents();
-    }
+    pdl_wait();                                // the partial bucket keys are complete
+    if (tid == 0) ktrace_start(batch.ktrace, 4);
+    pdl_launch_dependents();
     if (nq <= 0) {                             // CTA-uniform, like the next test
       if (qb == 0 && tid == 0) {
         *P.match_count = 0;
@@ -1099,7 +1096,6 @@ knn2_tc_finish_kernel(const __grid_constant__ KnnBatch batch, const __grid_const
       else if (batch.host_counts) batch.host_counts[P.region] = int(base + total);
     }
   } while (false);
-  if (fa.nowait) pdl_wait();
   // the last CTA to get here leaves the state ready for the next launch on it
   __syncthreads();
   if (tid == 0) {

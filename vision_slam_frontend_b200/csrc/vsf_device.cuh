@@ -136,13 +136,8 @@ struct FinishArgs {
   // launch captured in a CUDA graph can be replayed.  Launches that share a state (and its
   // look-back words) never overlap: each starts after its predecessor on the state completed.
   unsigned long long* state;
-  unsigned long long* flags;         // [32-query blocks of the batch, KnnProblem::qb0 + block] (epoch << 8 | survivors)
-  int nqb;                           // 32-query blocks per problem (grid = nqb * num_problems)
-  // nowait != 0 (the later finish kernels of a group of poses): the distance kernel this launch
-  // reads from had completed before the stream predecessor - the previous pose's finish kernel -
-  // passed its own wait, so the kernel starts at once and only waits for the predecessor just
-  // before it exits ("complete" still implies "everything before it complete").
-  int nowait;
+  unsigned long long* flags;         // [32-query units of the batch, KnnProblem::qb0 + unit] (epoch << 16 | survivors of a block)
+  int nqb;                           // query blocks (of 64 / 128 / 256 queries) per problem (grid = nqb * num_problems)
 };
 
 
