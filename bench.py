@@ -646,9 +646,9 @@ def measure_e2e(a, ctx, seq, n, W, K, WU, B, world, dist, torch, host_threads):
         res[key] = {"value": world * Ks * W * n * n / el, "us_per_pose": 1e6 * el / Ks, "frames": Ks}
 
     # headline e2e: pipelined, the reference's bit-identical order, computed where
-    # VSF_SORT_EXACT_AUTO puts it: host std::sort with >= 8 host threads per rank, else the device
-    # replay of std::sort (e.g. 8 ranks sharing a 32-core node)
-    auto_mode = 1 if host_threads >= 8 else 2
+    # VSF_SORT_EXACT_AUTO puts it: host std::sort with >= 12 host threads per rank, else the device
+    # replay of std::sort (e.g. 4 or 8 ranks sharing a 32-core node)
+    auto_mode = 1 if host_threads >= 12 else 2
     head = res["pipelined_exact_host_sort" if auto_mode == 1 else "pipelined_exact_device_sort"]
     return {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"],
             "d2h_bytes_per_step": head["d2h_bytes_per_step"], "steps": K,

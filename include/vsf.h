@@ -187,9 +187,10 @@ int vsf_window_match(vsf_ctx* ctx, const uint8_t* desc, int n, size_t stride,
  * produced on the device by replaying libstdc++'s introsort (csrc/sort_kernel.cu) -
  * no host cores needed, only the kept FeatureMatches cross PCIe; needs
  * max_features <= 24576 (VSF_ERR_CAPACITY otherwise); sort_mode 3: the reference
- * order wherever it is cheaper - on the host (mode 1) when the ctx may use at least 8
- * host threads (vsf_set_host_threads) or max_features > 24576, on the device (mode 2)
- * otherwise, e.g. when the ranks of a many-GPU node share its cores.  Modes 0 and
+ * order wherever it is cheaper - on the host (mode 1) when the ctx may use at least 12
+ * host threads (vsf_set_host_threads; 8 for the blocking vsf_window_feature_matches) or
+ * max_features > 24576, on the device (mode 2) otherwise, e.g. when the ranks of a
+ * many-GPU node share its cores.  Modes 0 and
  * 1 / 2 / 3 differ only inside groups of equal distance. */
 #define VSF_SORT_STABLE_DEVICE 0
 #define VSF_SORT_EXACT_HOST 1
