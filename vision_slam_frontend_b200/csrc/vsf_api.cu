@@ -1560,7 +1560,8 @@ static int flush_flights(vsf_ctx* c) {
     f.chain = chain;
     f.launched = true;
     f.t_flush = std::chrono::steady_clock::now();
-    if (g == 0 && std::getenv("VSF_TIMING2"))
+    static const bool trace_events = std::getenv("VSF_TIMING2") != nullptr;   // host time of every launch / collect
+    if (g == 0 && trace_events)
       std::fprintf(stderr, "FLUSH %.1f frames %llu..+%d\n", std::chrono::duration<double, std::micro>(f.t_flush.time_since_epoch()).count(),
                    (unsigned long long)f.frame_id, m);
     for (const ProblemSpec& sp : f.specs) {
@@ -1712,7 +1713,8 @@ extern "C" int vsf_window_collect(vsf_ctx* c, uint64_t* frame_id, uint64_t* fram
   c->tm_wait += std::chrono::duration<double, std::micro>(tw1 - tw0).count();
   c->tm_ready += std::chrono::duration<double, std::micro>(tw1 - f.t_flush).count();
   ++c->tm_n;
-  if (std::getenv("VSF_TIMING2"))
+  static const bool trace_events = std::getenv("VSF_TIMING2") != nullptr;
+  if (trace_events)
     std::fprintf(stderr, "READY %.1f frame %llu entered %.1f\n", std::chrono::duration<double, std::micro>(tw1.time_since_epoch()).count(),
                  (unsigned long long)f.frame_id, std::chrono::duration<double, std::micro>(tw0.time_since_epoch()).count());
   // the flight is consumed whatever happens next
