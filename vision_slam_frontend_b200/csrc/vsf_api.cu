@@ -248,6 +248,7 @@ struct vsf_ctx {
   // device-resident blocks of poses: the +-1 images of the next group are made on a side stream
   // beside the running distance kernel; ev_img[p] = the images of parity p are complete,
   // ev_grp[p] = the group that read them has finished, ev_blk = what preceded the call has
+  bool grp_ready = false;                   // group_state_init has completed
   cudaStream_t exp_stream = nullptr;
   cudaEvent_t ev_img[2] = {nullptr, nullptr}, ev_grp[2] = {nullptr, nullptr}, ev_blk = nullptr;
   cudaEvent_t ev_main = nullptr;
@@ -1383,19 +1384,31 @@ extern "C" int vsf_window_in_flight(const vsf_ctx* c) { return c ? c->flight_cou
 // that do not write the ctx's own.  Allocated on first use.
 static size_t group_flag_words(const vsf_ctx* c) { return size_t(kMaxProblems) * (size_t(c->rows_pad) / 32 + 4) + 8; }
 static int group_state_init(vsf_ctx* c) {
-  if (c->grp_flags) return VSF_OK;
+  if (c->grp_ready) return VSF_OK;
+  // (a call that failed half way is completed by the next one: every piece is made only once)
   const size_t flag_words = group_flag_words(c);
   const size_t rows_cap = size_t(c->regions) * size_t(c->rows_pad);
-  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_flags), (flag_words + 8) * sizeof(unsigned long long)));
-  VSF_CUDA(c, cudaMemset(c->grp_flags, 0, (flag_words + 8) * sizeof(unsigned long long)));
-  const unsigned long long init[8] = {0ull, 0ull, 1ull, 0ull, 0ull, 0ull, (1ull << 40) + 1ull, 0ull};
-  VSF_CUDA(c, cudaMemcpy(c->grp_flags + flag_words, init, sizeof(init), cudaMemcpyHostToDevice));
-  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
-  VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
+  if (!c->grp_flags) {
+    unsigned long long* p = nullptr;
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&p), (flag_words + 8) * sizeof(unsigned long long)));
+    const unsigned long long init[8] = {0ull, 0ull, 1ull, 0ull, 0ull, 0ull, (1ull << 40) + 1ull, 0ull};
+    cudaError_t e = cudaMemset(p, 0, (flag_words + 8) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpy(p + flag_words, init, sizeof(init), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      VSF_CUDA(c, e);
+    }
+    c->grp_flags = p;
+  }
+  if (!c->grp_matches)
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_matches), size_t(kMaxPoseGroup - 1) * rows_cap * sizeof(vsf_dmatch)));
+  if (!c->grp_counts)
+    VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->grp_counts), size_t(kMaxPoseGroup - 1) * kMaxProblems * sizeof(int)));
   if (!c->d_partial2) VSF_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_partial2), c->partial_cap * sizeof(uint2)));
-  VSF_CUDA(c, cudaStreamCreateWithFlags(&c->exp_stream, cudaStreamNonBlocking));
+  if (!c->exp_stream) VSF_CUDA(c, cudaStreamCreateWithFlags(&c->exp_stream, cudaStreamNonBlocking));
   for (cudaEvent_t* e : {&c->ev_img[0], &c->ev_img[1], &c->ev_grp[0], &c->ev_grp[1], &c->ev_blk})
-    VSF_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (!*e) VSF_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  c->grp_ready = true;
   return VSF_OK;
 }
 
