@@ -110,3 +110,14 @@ def test_most_uniform_queries_are_rejected_without_a_rescan():
     T = rng.integers(0, 256, (800, 32), dtype=np.uint8)
     rescans = check(Q, T)
     assert rescans < 20
+
+
+def test_look_back_words_fit_the_problem_slots():
+    """FinishArgs::flags is indexed in 32-query units: run_knn reserves round_up(nq, 128) / 32
+    words per problem (KnnProblem::qb0), a block of QPB queries publishes into word
+    block * (QPB / 32) - whatever QPB the launch picks, the last block's word is inside."""
+    for qpb in (64, 128, 256):
+        for nq in list(range(1, 1200)) + [4999, 5000, 5001, 20000, 24576]:
+            words = ((max(nq, 1) + 127) // 128 * 128) // 32
+            nqb = (nq + qpb - 1) // qpb
+            assert (nqb - 1) * (qpb // 32) < words, (qpb, nq)
