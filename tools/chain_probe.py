@@ -1,4 +1,4 @@
-"""Two / three / four kernels per pose in vsf_window_match_block_device (engine flags 0 / 256 / 512):
+"""Groups of poses as one batch / pose by pose / four kernels per pose in vsf_window_match_block_device (engine flags 0 / 256 / 512):
 per-pose time of each and the kernel-level timeline (engine flag 32) of a few consecutive poses.  Run under gpurun:
 
     python tools/chain_probe.py [features] [window] [desc_bytes] [out.json]
@@ -57,7 +57,6 @@ def main():
     res["us_per_pose_two_kernels"] = timed(0)
     res["us_per_pose_three_kernels"] = timed(256)
     res["us_per_pose_four_kernels"] = timed(512)
-    res["us_per_pose_two_kernels_no_early_start"] = timed(1024)
     res["us_per_pose_two_kernels_again"] = timed(0)
     counts = ctx.fetch_window(W, with_matches=False)
     res["survivors_last_pose"] = [int(c) for c in counts]
